@@ -1,0 +1,140 @@
+/*
+ * rnascan_b200 -- C ABI of the B200 (sm_100a) motif-scoring library, librnascan_b200.so.
+ *
+ * This is the drop-in boundary for rnascan's sliding-window scoring path.  The reference
+ * has exactly one native entry point on that path,
+ *
+ *     rnascan.BioAddons.motifs._pwm.calculate(sequence, matrix) -> float32[n-m+1]
+ *         /root/reference/rnascan/BioAddons/motifs/_pwm.c:79-121 (arithmetic :8-70)
+ *
+ * called once per window by Biopython's search() from rnascan.py:263; everything else
+ * on the path is Python (matrix.py:25-43 one-hot structure scoring, rnascan.py:293-315
+ * averaged-profile scoring, rnascan.py:440-465 background counting).  The entry points
+ * below replace those loops; each cites what it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; `d_*` pointers are CUDA device addresses, others are host;
+ *  - every function returns 0 (RS_OK) or an RS_ERR_* code; rs_last_error() gives text;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work
+ *    is enqueued on it, nothing synchronises, nothing allocates: the caller supplies the
+ *    workspace (rs_scan_workspace_bytes) and reads counters after syncing the stream;
+ *  - there is NO CPU fallback: without a CUDA device every device entry point fails.
+ *
+ * Symbol stream ("codes"), 1 byte per symbol, records concatenated with ONE separator:
+ *    bits 0-2 letter index, bit 3 "not counted in the background", 0xFF separator.
+ *    RNA   : A=0 C=1 G=2 U/T=3 (either case), anything else 0x0C (window -> NaN)
+ *    struct: B=0 E=1 H=2 L=3 M=4 R=5 T=6 ; lower case = index|8 (scored, not counted:
+ *            rnascan.py:196-197 + :450-453 count case-sensitively) ; anything else 0x0F
+ *    A window that contains a separator is not a window of any record; hit scans never
+ *    report it, dense outputs hold NaN there.
+ *  Device arrays read by the scan kernels must be allocated with rs_padded_count(n)
+ *  elements (codes) / rows (profiles); the padding is never interpreted.
+ *
+ * Structure channel order everywhere in this ABI is B,E,H,L,M,R,T (the profile file
+ * order, pfmutil.py:62-69); PSSM tables are row-major [W][channels].
+ */
+#ifndef RNASCAN_B200_H
+#define RNASCAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_OK            0
+#define RS_ERR_INVALID   1   /* bad argument (the reference raises ValueError)          */
+#define RS_ERR_CUDA      2   /* CUDA runtime error, including "no device"               */
+#define RS_ERR_WORKSPACE 3   /* workspace too small                                     */
+
+#define RS_SEP        0xFF
+#define RS_RNA_OTHER  0x0C
+#define RS_SS_OTHER   0x0F
+#define RS_MAX_W      64     /* widest motif the scan kernels accept                    */
+
+#define RS_F32 0
+#define RS_F64 1
+
+#define RS_MODE_STRUCT 0     /* hit iff struct score > m                                */
+#define RS_MODE_AND    1     /* hit iff seq score > m AND struct score > m (combine(),  */
+                             /* rnascan.py:416-434 is an inner join of two thresholded  */
+                             /* result sets)                              */
+
+/* ---- library ---------------------------------------------------------------------- */
+int         rs_version(void);
+const char *rs_last_error(void);                       /* thread-local                  */
+int         rs_device_info(int *sm_count, int *cc_major, int *cc_minor);
+int64_t     rs_padded_count(int64_t n);                /* elements/rows to allocate     */
+int64_t     rs_scan_workspace_bytes(int64_t n, int64_t hit_capacity);
+
+/* ---- host-side encoding (CPU threads; replaces str.upper()/transcribe() + the char
+ *      switch of _pwm.c:41-63 and the dict lookup of matrix.py:36-41) ---------------- */
+int rs_host_encode_rna(const uint8_t *text, int64_t n, uint8_t *codes);
+int rs_host_encode_struct(const uint8_t *text, int64_t n, uint8_t *codes);
+
+/* ---- background counts (replaces the Seq.count loop of rnascan.py:450-453) ---------
+ * d_counts8[k] += number of symbols with index k and bit 3 clear (k = 0..7); exact
+ * integers.  The caller zeroes d_counts8 first (so shards can accumulate).            */
+int rs_hist(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream);
+
+/* ---- dense scores: the calculate() semantics, every window, NaN in band ------------
+ * seq    : _pwm.c:34-68   out[i] = (float)(sum_j table[j][code]) double accumulation
+ * struct : matrix.py:25-43 out[i] = sum_j table[j][code] in double
+ * profile: rnascan.py:302-307 out[i] = sum_j nan_to_num(dot(profile[i+j,:], table[j,:]))
+ * n_out = n - W + 1 values are written (nothing if n < W).                            */
+int rs_scores_dense_seq(const uint8_t *d_codes, int64_t n, const double *table_Wx4, int W,
+                        float *d_out, void *stream);
+int rs_scores_dense_struct(const uint8_t *d_codes, int64_t n, const double *table_Wx7, int W,
+                           double *d_out, void *stream);
+int rs_scores_dense_profile(const void *d_profile, int profile_dtype, int64_t n_rows,
+                            const uint8_t *d_codes /* may be NULL: no separators */,
+                            const double *table_Wx7, int W, double *d_out, void *stream);
+
+/* ---- profile statistics, once per uploaded profile ---------------------------------
+ * d_stats[0] = max over rows of sum_c |p[r][c]| ; d_stats[1] = number of non-finite
+ * entries ; d_stats[2] = number of negative entries.  Feeds the guard band of
+ * rs_scan_fused: pass profile_absrow_max = NaN there unless [1] == [2] == 0.          */
+int rs_profile_stats(const void *d_profile, int profile_dtype, int64_t n_rows,
+                     double *d_stats3, void *stream);
+
+/* ---- thresholded scans: Biopython<=1.77 search(threshold, both=False) as driven by
+ *      rnascan.py:263 -- strict `>`, NaN/-inf windows never reported -----------------
+ * Hits come back sorted by position in the symbol stream.  d_counters[0] = number of
+ * hits found (may exceed hit_capacity: then only the first hit_capacity are stored and
+ * the caller re-runs with a larger buffer), d_counters[1] = windows re-scored exactly
+ * (guard band + hits; diagnostic).
+ *
+ * rs_scan_seq           : float32 scores, bit-identical to _pwm.c for every hit.
+ * rs_scan_struct_onehot : float64 scores as matrix.py:25-43.
+ * rs_scan_pair_onehot   : both streams, hit iff both > m (two-FASTA RNASS mode).
+ * rs_scan_fused         : sequence PSSM + averaged 7-channel profile in one pass.
+ *                         The profile correlation runs in fp32 as a conservative filter;
+ *                         every window within the guard band of the threshold is
+ *                         re-scored in fp64 exactly as rnascan.py:302-307, so hit sets
+ *                         and reported scores do not depend on the fp32 arithmetic.
+ *                         d_hit_seq may be NULL in RS_MODE_STRUCT.                     */
+int rs_scan_seq(const uint8_t *d_codes, int64_t n, const double *table_Wx4, int W,
+                double threshold, int64_t hit_capacity, int64_t *d_hit_pos,
+                float *d_hit_score, uint64_t *d_counters2, void *d_work, int64_t work_bytes,
+                void *stream);
+int rs_scan_struct_onehot(const uint8_t *d_codes, int64_t n, const double *table_Wx7, int W,
+                          double threshold, int64_t hit_capacity, int64_t *d_hit_pos,
+                          double *d_hit_score, uint64_t *d_counters2, void *d_work,
+                          int64_t work_bytes, void *stream);
+int rs_scan_pair_onehot(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes, int64_t n,
+                        const double *seq_table_Wx4, const double *struct_table_Wx7, int W,
+                        double threshold, int64_t hit_capacity, int64_t *d_hit_pos,
+                        float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2,
+                        void *d_work, int64_t work_bytes, void *stream);
+int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                  const double *seq_table_Wx4 /* NULL in RS_MODE_STRUCT */,
+                  const double *struct_table_Wx7, int W, double threshold,
+                  double profile_absrow_max, int mode, int64_t hit_capacity,
+                  int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                  uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNASCAN_B200_H */

@@ -1,0 +1,75 @@
+"""ctypes binding of librnascan_b200.so (the C ABI declared in include/rnascan_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded the import
+of this module raises, and every device entry point raises ``RnascanCudaError`` when the
+CUDA runtime reports an error (including "no device").
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librnascan_b200.so")
+
+RS_OK, RS_ERR_INVALID, RS_ERR_CUDA, RS_ERR_WORKSPACE = 0, 1, 2, 3
+RS_F32, RS_F64 = 0, 1
+RS_MODE_STRUCT, RS_MODE_AND = 0, 1
+RS_SEP, RS_RNA_OTHER, RS_SS_OTHER, RS_MAX_W = 0xFF, 0x0C, 0x0F, 64
+
+
+class RnascanCudaError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "rnascan_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C rnascan_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_i64, _vp, _int, _dbl = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_SIGS = {
+    "rs_version": ([], _int),
+    "rs_last_error": ([], ctypes.c_char_p),
+    "rs_device_info": ([_vp, _vp, _vp], _int),
+    "rs_padded_count": ([_i64], _i64),
+    "rs_scan_workspace_bytes": ([_i64, _i64], _i64),
+    "rs_host_encode_rna": ([_vp, _i64, _vp], _int),
+    "rs_host_encode_struct": ([_vp, _i64, _vp], _int),
+    "rs_hist": ([_vp, _i64, _vp, _vp], _int),
+    "rs_scores_dense_seq": ([_vp, _i64, _vp, _int, _vp, _vp], _int),
+    "rs_scores_dense_struct": ([_vp, _i64, _vp, _int, _vp, _vp], _int),
+    "rs_scores_dense_profile": ([_vp, _int, _i64, _vp, _vp, _int, _vp, _vp], _int),
+    "rs_profile_stats": ([_vp, _int, _i64, _vp, _vp], _int),
+    "rs_scan_seq": ([_vp, _i64, _vp, _int, _dbl, _i64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "rs_scan_struct_onehot": ([_vp, _i64, _vp, _int, _dbl, _i64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "rs_scan_pair_onehot": ([_vp, _vp, _i64, _vp, _vp, _int, _dbl, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
+                             _vp], _int),
+    "rs_scan_fused": ([_vp, _vp, _int, _i64, _vp, _vp, _int, _dbl, _dbl, _int, _i64, _vp, _vp, _vp, _vp,
+                       _vp, _i64, _vp], _int),
+}
+EXPORTS = sorted(_SIGS)
+for _name, (_args, _res) in _SIGS.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+
+def last_error():
+    return lib.rs_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Raise the Python exception matching the C status (the reference raises ValueError
+    for malformed matrices, _pwm.c:96-113)."""
+    if rc == RS_OK:
+        return
+    msg = last_error()
+    if rc == RS_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == RS_ERR_WORKSPACE:
+        raise MemoryError(msg)
+    raise RnascanCudaError(msg)

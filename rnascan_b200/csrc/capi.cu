@@ -1,0 +1,82 @@
+// Library-level pieces of the C ABI: error reporting, device info, buffer sizing.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rs_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int rs_cuda_fail(cudaError_t e, const char *what)
+{
+    rs_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return RS_ERR_CUDA;
+}
+
+int rs_sm_count()
+{
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+extern "C" int rs_version(void) { return 100; }            // 0.1.0
+
+extern "C" const char *rs_last_error(void) { return g_err; }
+
+extern "C" int rs_device_info(int *sm_count, int *cc_major, int *cc_minor)
+{
+    int dev = 0, n = 0;
+    RS_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) { rs_set_error("no CUDA device"); return RS_ERR_CUDA; }
+    RS_CUDA(cudaGetDevice(&dev));
+    int sm = 0, ma = 0, mi = 0;
+    RS_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    RS_CUDA(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev));
+    RS_CUDA(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm_count) *sm_count = sm;
+    if (cc_major) *cc_major = ma;
+    if (cc_minor) *cc_minor = mi;
+    return RS_OK;
+}
+
+extern "C" int64_t rs_padded_count(int64_t n)
+{
+    if (n < 0) n = 0;
+    return rs_roundup(n, RS_PAD) + RS_PAD;
+}
+
+// workspace: staging hit arrays (capacity entries) + per-tile segment table + scan scratch
+WorkLayout rs_work_layout(int64_t n, int64_t capacity)
+{
+    WorkLayout wl;
+    const int64_t cap = capacity > 0 ? capacity : 0;
+    const int64_t tiles = (n > 0 ? n : 0) / RS_MIN_TILE + 2;
+    int64_t off = 0;
+    wl.off_pos = off;  off += rs_roundup(cap * 8, 256);
+    wl.off_str = off;  off += rs_roundup(cap * 8, 256);
+    wl.off_seq = off;  off += rs_roundup(cap * 4, 256);
+    wl.off_seg = off;  off += rs_roundup(tiles * 16, 256);
+    wl.off_scan = off; off += rs_roundup(16 + 8 * (tiles / 8192 + 2), 256);
+    wl.total = off;
+    return wl;
+}
+
+extern "C" int64_t rs_scan_workspace_bytes(int64_t n, int64_t hit_capacity)
+{
+    return rs_work_layout(n, hit_capacity).total;
+}

@@ -1,0 +1,142 @@
+// Shared device/host helpers for the rnascan_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include "../../include/rnascan_b200.h"
+
+#define RS_CHANNELS 7            // B,E,H,L,M,R,T
+#define RS_PAD      256          // rs_padded_count(n) = roundup(n, RS_PAD) + RS_PAD
+
+// --------------------------------------------------------------------------- errors
+void rs_set_error(const char *fmt, ...);
+int  rs_cuda_fail(cudaError_t e, const char *what);
+#define RS_CUDA(call)                                                     \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return rs_cuda_fail(e__, #call);          \
+    } while (0)
+
+static inline int64_t rs_roundup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+int rs_sm_count();               // SMs of the current device (cached)
+
+// --------------------------------------------------------------------------- PTX: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// --------------------------------------------------------------------------- exact scoring primitives (shared by all kernels)
+// numpy.nan_to_num on a double: NaN -> 0, +-inf -> +-DBL_MAX   (rnascan.py:306)
+__device__ __forceinline__ double rs_nan_to_num(double d)
+{
+    if (d != d) return 0.0;
+    if (isinf(d)) return d > 0 ? DBL_MAX : -DBL_MAX;
+    return d;
+}
+
+// One window of the averaged-profile score, exactly rnascan.py:302-307:
+//   sum_j nan_to_num( sum_c p[i+j][c] * m[j][c] ), separate multiply and add, c then j.
+template <typename PT>
+__device__ __forceinline__ double rs_exact_profile_window(const PT *rows /* first row of window */,
+                                                          const double *tab /* [W][7] */, int W)
+{
+    double score = 0.0;
+    for (int j = 0; j < W; j++) {
+        double d = 0.0;
+#pragma unroll
+        for (int c = 0; c < RS_CHANNELS; c++)
+            d = __dadd_rn(d, __dmul_rn((double)rows[j * RS_CHANNELS + c], tab[j * RS_CHANNELS + c]));
+        score = __dadd_rn(score, rs_nan_to_num(d));
+    }
+    return score;
+}
+
+// One window of a one-hot PSSM score: sequential double adds in j order (_pwm.c:36-60,
+// matrix.py:34-38).  A = number of valid letters (4 or 7), table row stride TS doubles.
+// Returns false when the window holds an invalid symbol (score is NaN in the reference).
+template <int A, int TS>
+__device__ __forceinline__ bool rs_exact_onehot_window(const uint8_t *codes, const double *tab, int W,
+                                                       double &score)
+{
+    double s = 0.0;
+    bool ok = true;
+    for (int j = 0; j < W; j++) {
+        int idx = codes[j] & 7;
+        if (idx >= A) { ok = false; break; }
+        s = __dadd_rn(s, tab[j * TS + idx]);
+    }
+    score = s;
+    return ok;
+}
+
+// true when symbols [0, W) hold no separator
+__device__ __forceinline__ bool rs_no_separator(const uint8_t *codes, int W)
+{
+    for (int j = 0; j < W; j++)
+        if (codes[j] == RS_SEP) return false;
+    return true;
+}
+
+// --------------------------------------------------------------------------- hit staging
+// Scan kernels append the hits of one tile, in position order, to a staging area at an
+// atomically claimed offset and record (offset,count) per tile; order.cu then copies the
+// segments out in tile order, so the final list is sorted by position.
+struct HitStage {
+    int64_t  *pos;        // staging arrays, capacity entries each
+    float    *seq;
+    double   *str;
+    ulonglong2 *tile_seg; // per tile: (staging offset, count)   [n_tiles]
+    unsigned long long *counters;   // [0] hits, [1] exact re-scores
+    int64_t   capacity;
+};
+
+struct WorkLayout {
+    int64_t off_pos, off_seq, off_str, off_seg, off_scan, total;
+};
+WorkLayout rs_work_layout(int64_t n, int64_t capacity);
+int rs_order_hits(const HitStage &st, int64_t n_tiles, int64_t *d_hit_pos, float *d_hit_seq,
+                  double *d_hit_str, void *d_scan_tmp, cudaStream_t stream);
+
+#define RS_MIN_TILE 1024         // smallest tile any scan kernel uses (sizes the segment table)

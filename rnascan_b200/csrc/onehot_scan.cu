@@ -1,0 +1,280 @@
+// One-hot PSSM scans over symbol codes: sequence (A=4, float32 scores) and structure
+// context (A=7, float64 scores), dense or thresholded, single stream or a pair of
+// streams (two-FASTA RNASS mode).
+//
+// Replaces   _pwm.c:34-68 (driven per window by Biopython search(), rnascan.py:263)
+//            BioAddons/motifs/matrix.py:25-43 (_py_calculate)
+//
+// Arithmetic: sequential double adds of table[j][code] in j order, then one cast to float
+// for the sequence alphabet -- the reference's exact operation order, so results are
+// bit-identical.  Persistent CTAs stream tiles of symbol codes into a shared-memory ring
+// with 1-D bulk async copies; the W x 8 double table is staged in shared memory; lanes of
+// a warp take consecutive windows (conflict-free byte gathers, coalesced dense stores).
+// Hits are found with a first pass that only keeps a bit per window, ordered with warp
+// ballot/popc + a block prefix sum + ONE atomic per tile, and re-scored when written.
+#include "common.cuh"
+
+#define OH_THREADS 256
+#define OH_PER     16
+#define OH_TILE    (OH_THREADS * OH_PER)     // 4096 windows per tile
+#define OH_STAGES  3
+#define OH_TS      8                         // table row stride in doubles
+
+struct OneHotParams {
+    const uint8_t *codes_a;      // sequence codes (A=4) or structure codes (A=7)
+    const uint8_t *codes_b;      // PAIR: structure codes
+    void          *dense_out;    // float* (A=4) or double* (A=7)
+    int64_t        n, padded, n_tiles;
+    double         threshold;
+    int            W;
+    HitStage       st;
+    double         ta[RS_MAX_W * OH_TS];     // table for stream a, row stride 8
+    double         tb[RS_MAX_W * OH_TS];     // table for stream b (PAIR)
+};
+
+__host__ __device__ constexpr uint32_t oh_ru16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// MODE: 0 dense, 1 hits.  A: alphabet of stream a.  PAIR: second stream (A_b = 7), hits only.
+template <int A, bool PAIR, bool DENSE>
+__global__ void __launch_bounds__(OH_THREADS) onehot_kernel(const __grid_constant__ OneHotParams prm)
+{
+    constexpr uint32_t CODE_BYTES = oh_ru16(OH_TILE + RS_MAX_W - 1);
+    constexpr uint32_t STAGE_BYTES = CODE_BYTES * (PAIR ? 2 : 1);
+    __shared__ __align__(128) uint8_t s_stage[OH_STAGES * STAGE_BYTES];
+    __shared__ __align__(16) double s_ta[RS_MAX_W * OH_TS];
+    __shared__ __align__(16) double s_tb[PAIR ? RS_MAX_W * OH_TS : 1];
+    __shared__ uint64_t bars[OH_STAGES];
+    __shared__ unsigned s_cnt[OH_THREADS / 32][OH_PER];
+    __shared__ unsigned long long s_base;
+
+    const int W = prm.W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < W * OH_TS; k += OH_THREADS) {
+        s_ta[k] = prm.ta[k];
+        if (PAIR) s_tb[k] = prm.tb[k];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < OH_STAGES; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t stride = gridDim.x, first = blockIdx.x;
+    const int64_t my_tiles = first < prm.n_tiles ? (prm.n_tiles - first + stride - 1) / stride : 0;
+    const uint32_t need = oh_ru16(OH_TILE + W - 1);
+
+    auto issue = [&](int64_t it) {
+        const int s = (int)(it % OH_STAGES);
+        const int64_t t0 = (first + it * stride) * OH_TILE;
+        const uint32_t bytes = (uint32_t)min((int64_t)need, prm.padded - t0);
+        uint8_t *dst = s_stage + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&bars[s], bytes * (PAIR ? 2 : 1));
+        bulk_g2s(dst, prm.codes_a + t0, bytes, &bars[s]);
+        if (PAIR) bulk_g2s(dst + CODE_BYTES, prm.codes_b + t0, bytes, &bars[s]);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < OH_STAGES - 1 && it < my_tiles; it++) issue(it);
+
+    // score of window w of the staged tile; returns hit decision, fills scores
+    auto score = [&](const uint8_t *ca, const uint8_t *cb, int w, int64_t gpos, float &fa, double &da,
+                     double &db) -> bool {
+        if (gpos + W > prm.n) return false;
+        double sa;
+        bool ok = rs_exact_onehot_window<A, OH_TS>(ca + w, s_ta, W, sa);
+        if (A == 4) { fa = (float)sa; da = (double)fa; }      // _pwm.c:65 ; compare widened (note N1)
+        else        { fa = 0.f; da = sa; }
+        if (!ok || !(da > prm.threshold)) return false;
+        if (PAIR) {
+            double sb;
+            if (!rs_exact_onehot_window<7, OH_TS>(cb + w, s_tb, W, sb)) return false;
+            db = sb;
+            return sb > prm.threshold;
+        }
+        return true;
+    };
+
+    for (int64_t it = 0; it < my_tiles; it++) {
+        const int s = (int)(it % OH_STAGES);
+        if (tid == 0 && it + OH_STAGES - 1 < my_tiles) issue(it + OH_STAGES - 1);
+        mbar_wait(&bars[s], (uint32_t)((it / OH_STAGES) & 1));
+        const int64_t tile = first + it * stride;
+        const int64_t t0 = tile * OH_TILE;
+        const uint8_t *ca = s_stage + (size_t)s * STAGE_BYTES;
+        const uint8_t *cb = PAIR ? ca + CODE_BYTES : nullptr;
+
+        if (DENSE) {
+#pragma unroll 4
+            for (int k = 0; k < OH_PER; k++) {
+                const int w = warp * (32 * OH_PER) + k * 32 + lane;
+                const int64_t gpos = t0 + w;
+                if (gpos + W <= prm.n) {
+                    double sa;
+                    bool ok = rs_exact_onehot_window<A, OH_TS>(ca + w, s_ta, W, sa);
+                    if (A == 4) reinterpret_cast<float *>(prm.dense_out)[gpos] = ok ? (float)sa : nanf("");
+                    else        reinterpret_cast<double *>(prm.dense_out)[gpos] = ok ? sa : nan("");
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+
+        unsigned hitmask = 0;
+#pragma unroll 4
+        for (int k = 0; k < OH_PER; k++) {
+            const int w = warp * (32 * OH_PER) + k * 32 + lane;
+            float fa; double da, db;
+            if (score(ca, cb, w, t0 + w, fa, da, db)) hitmask |= 1u << k;
+        }
+        const int any = __syncthreads_or(hitmask != 0);
+        if (any) {
+            for (int k = 0; k < OH_PER; k++) {
+                unsigned b = __ballot_sync(0xffffffffu, (hitmask >> k) & 1u);
+                if (lane == 0) s_cnt[warp][k] = __popc(b);
+            }
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (int ww = 0; ww < OH_THREADS / 32; ww++)
+#pragma unroll
+                for (int k = 0; k < OH_PER; k++) {
+                    unsigned v = s_cnt[ww][k];
+                    if (ww < warp) before += v;
+                    total += v;
+                }
+            if (tid == 0) {
+                unsigned long long base = atomicAdd(prm.st.counters, (unsigned long long)total);
+                s_base = base;
+                prm.st.tile_seg[tile] = make_ulonglong2(base, (unsigned long long)total);
+            }
+            __syncthreads();
+            unsigned long long kk = s_base + before;
+            for (int k = 0; k < OH_PER; k++) {
+                unsigned b = __ballot_sync(0xffffffffu, (hitmask >> k) & 1u);
+                if ((hitmask >> k) & 1u) {
+                    unsigned long long dst = kk + __popc(b & ((1u << lane) - 1u));
+                    if ((int64_t)dst < prm.st.capacity) {
+                        const int w = warp * (32 * OH_PER) + k * 32 + lane;
+                        float fa; double da, db = 0.0;
+                        score(ca, cb, w, t0 + w, fa, da, db);
+                        prm.st.pos[dst] = t0 + w;
+                        if (A == 4) prm.st.seq[dst] = fa;
+                        else        prm.st.str[dst] = da;
+                        if (PAIR)   prm.st.str[dst] = db;
+                    }
+                }
+                kk += __popc(b);
+            }
+            __syncthreads();
+        } else if (tid == 0) {
+            prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static void fill_table(double *dst, const double *src, int W, int A)
+{
+    for (int j = 0; j < W; j++)
+        for (int c = 0; c < OH_TS; c++) dst[j * OH_TS + c] = c < A ? src[j * A + c] : 0.0;
+}
+
+static int check_args(const uint8_t *codes, int64_t n, const double *table, int W)
+{
+    if (!codes || !table) { rs_set_error("null codes or table"); return RS_ERR_INVALID; }
+    if ((uintptr_t)codes & 15) { rs_set_error("codes pointer must be 16-byte aligned"); return RS_ERR_INVALID; }
+    if (W < 1 || W > RS_MAX_W) { rs_set_error("motif width %d outside [1, %d]", W, RS_MAX_W); return RS_ERR_INVALID; }
+    if (n < 0) { rs_set_error("negative length"); return RS_ERR_INVALID; }
+    return RS_OK;
+}
+
+template <int A, bool PAIR, bool DENSE>
+static int launch(const OneHotParams &prm, cudaStream_t stream)
+{
+    int64_t grid = (int64_t)rs_sm_count() * (2048 / OH_THREADS);
+    if (grid > prm.n_tiles) grid = prm.n_tiles;
+    onehot_kernel<A, PAIR, DENSE><<<(unsigned)grid, OH_THREADS, 0, stream>>>(prm);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+template <int A>
+static int dense_impl(const uint8_t *d_codes, int64_t n, const double *table, int W, void *d_out, void *stream)
+{
+    int rc = check_args(d_codes, n, table, W);
+    if (rc) return rc;
+    if (n < W) return RS_OK;
+    if (!d_out) { rs_set_error("null output"); return RS_ERR_INVALID; }
+    OneHotParams prm = {};
+    prm.codes_a = d_codes; prm.dense_out = d_out; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.n_tiles = (n + OH_TILE - 1) / OH_TILE; prm.W = W;
+    fill_table(prm.ta, table, W, A);
+    return launch<A, false, true>(prm, (cudaStream_t)stream);
+}
+
+extern "C" int rs_scores_dense_seq(const uint8_t *d_codes, int64_t n, const double *table, int W, float *d_out,
+                                   void *stream)
+{
+    return dense_impl<4>(d_codes, n, table, W, d_out, stream);
+}
+extern "C" int rs_scores_dense_struct(const uint8_t *d_codes, int64_t n, const double *table, int W,
+                                      double *d_out, void *stream)
+{
+    return dense_impl<7>(d_codes, n, table, W, d_out, stream);
+}
+
+template <int A, bool PAIR>
+static int scan_impl(const uint8_t *ca, const uint8_t *cb, int64_t n, const double *ta, const double *tb, int W,
+                     double threshold, int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
+                     uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_args(ca, n, ta, W);
+    if (rc) return rc;
+    if (PAIR && (rc = check_args(cb, n, tb, W))) return rc;
+    if (!d_counters2 || cap < 0 || (cap > 0 && !d_hit_pos)) { rs_set_error("bad hit buffers"); return RS_ERR_INVALID; }
+    if (cap > 0 && ((A == 4 && !d_hit_seq) || ((A == 7 || PAIR) && !d_hit_str))) {
+        rs_set_error("missing score buffer"); return RS_ERR_INVALID;
+    }
+    if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    if (n < W) return RS_OK;
+    WorkLayout wl = rs_work_layout(n, cap);
+    if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+    OneHotParams prm = {};
+    prm.codes_a = ca; prm.codes_b = cb; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.n_tiles = (n + OH_TILE - 1) / OH_TILE; prm.W = W; prm.threshold = threshold;
+    uint8_t *wk = (uint8_t *)d_work;
+    prm.st.pos = (int64_t *)(wk + wl.off_pos);
+    prm.st.seq = d_hit_seq ? (float *)(wk + wl.off_seq) : nullptr;
+    prm.st.str = d_hit_str ? (double *)(wk + wl.off_str) : nullptr;
+    prm.st.tile_seg = (ulonglong2 *)(wk + wl.off_seg);
+    prm.st.counters = (unsigned long long *)d_counters2;
+    prm.st.capacity = cap;
+    fill_table(prm.ta, ta, W, A);
+    if (PAIR) fill_table(prm.tb, tb, W, 7);
+    rc = launch<A, PAIR, false>(prm, st);
+    if (rc) return rc;
+    return rs_order_hits(prm.st, prm.n_tiles, d_hit_pos, d_hit_seq, d_hit_str, wk + wl.off_scan, st);
+}
+
+extern "C" int rs_scan_seq(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
+                           int64_t cap, int64_t *d_hit_pos, float *d_hit_score, uint64_t *d_counters2,
+                           void *d_work, int64_t work_bytes, void *stream)
+{
+    return scan_impl<4, false>(d_codes, nullptr, n, table, nullptr, W, threshold, cap, d_hit_pos, d_hit_score,
+                               nullptr, d_counters2, d_work, work_bytes, stream);
+}
+extern "C" int rs_scan_struct_onehot(const uint8_t *d_codes, int64_t n, const double *table, int W,
+                                     double threshold, int64_t cap, int64_t *d_hit_pos, double *d_hit_score,
+                                     uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    return scan_impl<7, false>(d_codes, nullptr, n, table, nullptr, W, threshold, cap, d_hit_pos, nullptr,
+                               d_hit_score, d_counters2, d_work, work_bytes, stream);
+}
+extern "C" int rs_scan_pair_onehot(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes, int64_t n,
+                                   const double *seq_table, const double *struct_table, int W, double threshold,
+                                   int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                                   uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    return scan_impl<4, true>(d_seq_codes, d_struct_codes, n, seq_table, struct_table, W, threshold, cap,
+                              d_hit_pos, d_hit_seq, d_hit_struct, d_counters2, d_work, work_bytes, stream);
+}

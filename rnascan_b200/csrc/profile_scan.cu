@@ -1,0 +1,562 @@
+// Averaged-structure (7-channel profile) scans, fused with the sequence PSSM.
+//
+// Replaces the pandas double loop of /root/reference/rnascan/rnascan.py:293-315
+// (scan_averaged_structure) and, in RS_MODE_AND, the sequence scan + inner join of
+// rnascan.py:258-275,416-434 for the combined mode.
+//
+// Two kernels:
+//   fused_filter_kernel<W>   float32 profiles, W <= RS_FAST_W.  Persistent CTAs stream
+//       tiles of (TILE+W-1) profile rows (28 B each) + symbol codes into a 3-stage shared
+//       memory ring with 1-D bulk async copies (TMA engine) completing on mbarriers.  Each
+//       thread correlates 9 consecutive windows from registers: every profile row is
+//       loaded from shared memory once per thread and reused by up to W windows; the W x 7
+//       table sits in the constant bank (kernel parameters), so the inner loop is pure
+//       FFMA with a constant operand.  The fp32 result is only a FILTER: windows whose
+//       fp32 score is within the guard band of the threshold are re-scored in fp64 in the
+//       reference's exact operation order, and only those decide/emit hits.
+//   profile_exact_kernel<PT> any profile dtype, any W <= RS_MAX_W, dense output or hits,
+//       non-finite PSSM entries: everything in fp64 in the reference's order.
+#include "common.cuh"
+
+#define RS_FAST_W   24
+#define FT_THREADS  128
+#define FT_P        9                       // windows per thread; odd => 7*P-word stride is bank-conflict free
+#define FT_TILE     (FT_THREADS * FT_P)     // 1152 positions, 1152*28 B is a multiple of 16
+#define FT_STAGES   3
+
+#define EX_THREADS  128
+#define EX_TILE     1024
+#define EX_STAGES   2
+
+struct ProfileParams {
+    const uint8_t *codes;        // may be NULL in the exact kernel (no separators)
+    const void    *profile;
+    double        *dense_out;    // exact kernel, dense mode
+    int64_t        n;            // rows == symbols
+    int64_t        padded;       // rs_padded_count(n)
+    int64_t        n_tiles;
+    double         threshold;
+    float          filt_thr;     // threshold - guard band (fp32, rounded down)
+    int            mode;         // RS_MODE_*
+    int            W;
+    int            dense;
+    HitStage       st;
+    float          sf[RS_MAX_W * RS_CHANNELS];   // filter table: fp32, rounded up
+    double         sd[RS_MAX_W * RS_CHANNELS];   // exact structure table
+    double         qd[RS_MAX_W * 4];             // exact sequence table (A,C,G,U)
+};
+
+__host__ __device__ constexpr uint32_t ru16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// Exact evaluation of window `i` (tile-relative) from the staged tile; returns whether it
+// is a hit and its scores.  Shared by the filter kernel's rare path and the exact kernel.
+template <typename PT>
+__device__ __forceinline__ bool exact_window(const ProfileParams &prm, const PT *prof, const uint8_t *codes,
+                                             int i, int64_t gpos, float &seq_out, double &str_out)
+{
+    const int W = prm.W;
+    if (gpos + W > prm.n) return false;
+    double s = rs_exact_profile_window<PT>(prof + (size_t)i * RS_CHANNELS, prm.sd, W);
+    str_out = s;
+    if (!(s > prm.threshold)) return false;
+    if (prm.mode == RS_MODE_AND) {
+        double q;
+        if (!rs_exact_onehot_window<4, 4>(codes + i, prm.qd, W, q)) return false;
+        float qf = (float)q;                     // _pwm.c:65
+        seq_out = qf;
+        return (double)qf > prm.threshold;       // SURVEY.md note N1
+    }
+    seq_out = 0.f;
+    return codes == nullptr || rs_no_separator(codes + i, W);
+}
+
+// Append this tile's hits (bit i of `mask` = window i of this thread, consecutive windows
+// per thread) to the staging area in position order.  All threads of the CTA call it.
+template <int THREADS, typename RECOMPUTE>
+__device__ __forceinline__ void emit_tile_hits(const HitStage &st, int64_t tile, unsigned mask, int nbits,
+                                               RECOMPUTE recompute)
+{
+    __shared__ unsigned s_warp[THREADS / 32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned cnt = __popc(mask);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        unsigned v = s_warp[w];
+        if (w < warp) before += v;
+        total += v;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long base = atomicAdd(st.counters, (unsigned long long)total);   // one atomic per tile
+        s_base = base;
+        st.tile_seg[tile] = make_ulonglong2(base, (unsigned long long)total);
+    }
+    __syncthreads();
+    unsigned long long k = s_base + before + (incl - cnt);
+    for (int i = 0; i < nbits; i++) {
+        if (mask & (1u << i)) {
+            if ((int64_t)k < st.capacity) recompute(i, (int64_t)k);
+            k++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __grid_constant__ ProfileParams prm)
+{
+    constexpr int ROWS = FT_TILE + W - 1;
+    constexpr uint32_t PROF_BYTES = ru16(ROWS * RS_CHANNELS * 4);
+    constexpr uint32_t CODE_BYTES = ru16(ROWS);
+    constexpr uint32_t STAGE_BYTES = PROF_BYTES + CODE_BYTES;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *stages = smem + 128;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < FT_STAGES; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t stride = gridDim.x;
+    const int64_t first = blockIdx.x;
+    const int64_t my_tiles = first < prm.n_tiles ? (prm.n_tiles - first + stride - 1) / stride : 0;
+    const int64_t prof_end = prm.padded * (RS_CHANNELS * 4);
+
+    auto issue = [&](int64_t it) {
+        const int s = (int)(it % FT_STAGES);
+        const int64_t t0 = (first + it * stride) * FT_TILE;
+        uint8_t *dst = stages + (size_t)s * STAGE_BYTES;
+        const int64_t pstart = t0 * (RS_CHANNELS * 4);
+        const uint32_t pbytes = (uint32_t)min((int64_t)PROF_BYTES, prof_end - pstart);
+        const uint32_t cbytes = (uint32_t)min((int64_t)CODE_BYTES, prm.padded - t0);
+        mbar_expect_tx(&bars[s], pbytes + cbytes);
+        bulk_g2s(dst, reinterpret_cast<const uint8_t *>(prm.profile) + pstart, pbytes, &bars[s]);
+        bulk_g2s(dst + PROF_BYTES, prm.codes + t0, cbytes, &bars[s]);
+    };
+
+    if (tid == 0)
+        for (int64_t it = 0; it < FT_STAGES - 1 && it < my_tiles; it++) issue(it);
+
+    for (int64_t it = 0; it < my_tiles; it++) {
+        const int s = (int)(it % FT_STAGES);
+        if (tid == 0 && it + FT_STAGES - 1 < my_tiles) issue(it + FT_STAGES - 1);
+        mbar_wait(&bars[s], (uint32_t)((it / FT_STAGES) & 1));
+
+        const int64_t tile = first + it * stride;
+        const int64_t t0 = tile * FT_TILE;
+        const float *prof = reinterpret_cast<const float *>(stages + (size_t)s * STAGE_BYTES);
+        const uint8_t *codes = stages + (size_t)s * STAGE_BYTES + PROF_BYTES;
+        const float *rows = prof + tid * (FT_P * RS_CHANNELS);
+
+        // ---- dense fp32 filter: 9 windows x W rows x 7 channels, rows reused from registers
+        float acc[FT_P];
+#pragma unroll
+        for (int i = 0; i < FT_P; i++) acc[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < FT_P + W - 1; r++) {
+            float x[RS_CHANNELS];
+#pragma unroll
+            for (int c = 0; c < RS_CHANNELS; c++) x[c] = rows[r * RS_CHANNELS + c];
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                const int i = r - j;
+                if (i >= 0 && i < FT_P) {
+#pragma unroll
+                    for (int c = 0; c < RS_CHANNELS; c++)
+                        acc[i] = fmaf(x[c], prm.sf[j * RS_CHANNELS + c], acc[i]);
+                }
+            }
+        }
+
+        // ---- guard band: anything not provably below the threshold is re-scored exactly
+        unsigned hitmask = 0;
+        unsigned nexact = 0;
+#pragma unroll
+        for (int i = 0; i < FT_P; i++) {
+            if (!(acc[i] <= prm.filt_thr)) {
+                float sq; double st;
+                nexact++;
+                if (exact_window<float>(prm, prof, codes, tid * FT_P + i, t0 + tid * FT_P + i, sq, st))
+                    hitmask |= 1u << i;
+            }
+        }
+        if (nexact) atomicAdd(prm.st.counters + 1, (unsigned long long)nexact);
+
+        const int any = __syncthreads_or(hitmask != 0);
+        if (any) {
+            emit_tile_hits<FT_THREADS>(prm.st, tile, hitmask, FT_P, [&](int i, int64_t k) {
+                float sq; double st;
+                const int w = tid * FT_P + i;
+                exact_window<float>(prm, prof, codes, w, t0 + w, sq, st);
+                prm.st.pos[k] = t0 + w;
+                prm.st.str[k] = st;
+                if (prm.st.seq) prm.st.seq[k] = sq;
+            });
+            __syncthreads();          // staged tile still in use until every hit is written
+        } else if (tid == 0) {
+            prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(EX_THREADS) profile_exact_kernel(const __grid_constant__ ProfileParams prm)
+{
+    const int W = prm.W;
+    const int rows_max = EX_TILE + RS_MAX_W - 1;
+    const uint32_t PROF_BYTES = ru16(rows_max * RS_CHANNELS * (uint32_t)sizeof(PT));
+    const uint32_t CODE_BYTES = ru16(rows_max);
+    const uint32_t STAGE_BYTES = PROF_BYTES + CODE_BYTES;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *stages = smem + 128;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < EX_STAGES; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t stride = gridDim.x, first = blockIdx.x;
+    const int64_t my_tiles = first < prm.n_tiles ? (prm.n_tiles - first + stride - 1) / stride : 0;
+    const int64_t prof_end = prm.padded * (int64_t)(RS_CHANNELS * sizeof(PT));
+    const uint32_t need_prof = ru16((EX_TILE + W - 1) * RS_CHANNELS * (uint32_t)sizeof(PT));
+    const uint32_t need_code = ru16(EX_TILE + W - 1);
+
+    auto issue = [&](int64_t it) {
+        const int s = (int)(it % EX_STAGES);
+        const int64_t t0 = (first + it * stride) * EX_TILE;
+        uint8_t *dst = stages + (size_t)s * STAGE_BYTES;
+        const int64_t pstart = t0 * (int64_t)(RS_CHANNELS * sizeof(PT));
+        const uint32_t pbytes = (uint32_t)min((int64_t)need_prof, prof_end - pstart);
+        const uint32_t cbytes = prm.codes ? (uint32_t)min((int64_t)need_code, prm.padded - t0) : 0u;
+        mbar_expect_tx(&bars[s], pbytes + cbytes);
+        bulk_g2s(dst, reinterpret_cast<const uint8_t *>(prm.profile) + pstart, pbytes, &bars[s]);
+        if (cbytes) bulk_g2s(dst + PROF_BYTES, prm.codes + t0, cbytes, &bars[s]);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < EX_STAGES - 1 && it < my_tiles; it++) issue(it);
+
+    constexpr int PER = EX_TILE / EX_THREADS;       // 8 windows per thread, lane-contiguous
+    for (int64_t it = 0; it < my_tiles; it++) {
+        const int s = (int)(it % EX_STAGES);
+        if (tid == 0 && it + EX_STAGES - 1 < my_tiles) issue(it + EX_STAGES - 1);
+        mbar_wait(&bars[s], (uint32_t)((it / EX_STAGES) & 1));
+
+        const int64_t tile = first + it * stride;
+        const int64_t t0 = tile * EX_TILE;
+        const PT *prof = reinterpret_cast<const PT *>(stages + (size_t)s * STAGE_BYTES);
+        const uint8_t *codes = prm.codes ? stages + (size_t)s * STAGE_BYTES + PROF_BYTES : nullptr;
+
+        unsigned hitmask = 0;
+        for (int k = 0; k < PER; k++) {
+            const int w = warp * (32 * PER) + k * 32 + lane;
+            const int64_t gpos = t0 + w;
+            if (prm.dense) {
+                if (gpos + W <= prm.n) {
+                    double sc = rs_exact_profile_window<PT>(prof + (size_t)w * RS_CHANNELS, prm.sd, W);
+                    if (codes && !rs_no_separator(codes + w, W)) sc = nan("");
+                    prm.dense_out[gpos] = sc;
+                }
+            } else {
+                float sq; double st;
+                if (exact_window<PT>(prm, prof, codes, w, gpos, sq, st)) hitmask |= 1u << k;
+            }
+        }
+        if (prm.dense) {
+            __syncthreads();
+            continue;
+        }
+        const int any = __syncthreads_or(hitmask != 0);
+        if (any) {
+            // lane-contiguous mapping: order inside a warp is (k, lane); emit k by k
+            __shared__ unsigned s_cnt[EX_THREADS / 32][PER];
+            __shared__ unsigned long long s_base2;
+            for (int k = 0; k < PER; k++) {
+                unsigned b = __ballot_sync(0xffffffffu, (hitmask >> k) & 1u);
+                if (lane == 0) s_cnt[warp][k] = __popc(b);
+            }
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (int ww = 0; ww < EX_THREADS / 32; ww++)
+                for (int k = 0; k < PER; k++) {
+                    unsigned v = s_cnt[ww][k];
+                    if (ww < warp) before += v;
+                    total += v;
+                }
+            if (tid == 0) {
+                unsigned long long base = atomicAdd(prm.st.counters, (unsigned long long)total);
+                s_base2 = base;
+                prm.st.tile_seg[tile] = make_ulonglong2(base, (unsigned long long)total);
+            }
+            __syncthreads();
+            unsigned long long kk = s_base2 + before;
+            for (int k = 0; k < PER; k++) {
+                unsigned b = __ballot_sync(0xffffffffu, (hitmask >> k) & 1u);
+                if ((hitmask >> k) & 1u) {
+                    unsigned long long dst = kk + __popc(b & ((1u << lane) - 1u));
+                    if ((int64_t)dst < prm.st.capacity) {
+                        const int w = warp * (32 * PER) + k * 32 + lane;
+                        float sq; double st;
+                        exact_window<PT>(prm, prof, codes, w, t0 + w, sq, st);
+                        prm.st.pos[dst] = t0 + w;
+                        prm.st.str[dst] = st;
+                        if (prm.st.seq) prm.st.seq[dst] = sq;
+                    }
+                }
+                kk += __popc(b);
+            }
+            __syncthreads();
+        } else if (tid == 0) {
+            prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// profile statistics: [0] max_r sum_c |p[r][c]|, [1] non-finite entries, [2] negative entries
+template <typename PT>
+__global__ void profile_stats_kernel(const PT *p, int64_t n_rows, double *stats)
+{
+    double mx = 0.0;
+    unsigned long long bad = 0, neg = 0;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < RS_CHANNELS; c++) {
+            double v = (double)p[r * RS_CHANNELS + c];
+            if (!isfinite(v)) bad++;
+            else { s += fabs(v); if (v < 0) neg++; }
+        }
+        mx = fmax(mx, s);
+    }
+    for (int d = 16; d; d >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        bad += __shfl_xor_sync(0xffffffffu, bad, d);
+        neg += __shfl_xor_sync(0xffffffffu, neg, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long *>(stats), (unsigned long long)__double_as_longlong(mx));
+        if (bad) atomicAdd(reinterpret_cast<unsigned long long *>(stats + 1), bad);
+        if (neg) atomicAdd(reinterpret_cast<unsigned long long *>(stats + 2), neg);
+    }
+}
+__global__ void stats_finish_kernel(double *stats)
+{
+    stats[1] = (double)(*reinterpret_cast<unsigned long long *>(stats + 1));
+    stats[2] = (double)(*reinterpret_cast<unsigned long long *>(stats + 2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+static float f32_round_up(double v)
+{
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
+}
+static float f32_round_down(double v)
+{
+    float f = (float)v;
+    if ((double)f > v) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+template <int W>
+static int launch_filter(const ProfileParams &prm, cudaStream_t stream)
+{
+    constexpr int ROWS = FT_TILE + W - 1;
+    constexpr uint32_t STAGE_BYTES = ru16(ROWS * RS_CHANNELS * 4) + ru16(ROWS);
+    const size_t smem = 128 + (size_t)FT_STAGES * STAGE_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        RS_CUDA(cudaFuncSetAttribute(fused_filter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t grid = (int64_t)rs_sm_count() * 2;
+    if (grid > prm.n_tiles) grid = prm.n_tiles;
+    fused_filter_kernel<W><<<(unsigned)grid, FT_THREADS, smem, stream>>>(prm);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+template <int W>
+struct FilterDispatch {
+    static int run(int w, const ProfileParams &prm, cudaStream_t stream)
+    {
+        if (w == W) return launch_filter<W>(prm, stream);
+        return FilterDispatch<W - 1>::run(w, prm, stream);
+    }
+};
+template <>
+struct FilterDispatch<0> {
+    static int run(int, const ProfileParams &, cudaStream_t)
+    {
+        rs_set_error("internal: no filter kernel for this W");
+        return RS_ERR_INVALID;
+    }
+};
+
+template <typename PT>
+static int launch_exact(const ProfileParams &prm, cudaStream_t stream)
+{
+    const int rows_max = EX_TILE + RS_MAX_W - 1;
+    const size_t stage = ru16(rows_max * RS_CHANNELS * (uint32_t)sizeof(PT)) + ru16(rows_max);
+    const size_t smem = 128 + (size_t)EX_STAGES * stage;
+    static bool configured = false;
+    if (!configured) {
+        RS_CUDA(cudaFuncSetAttribute(profile_exact_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t grid = (int64_t)rs_sm_count() * (sizeof(PT) == 4 ? 3 : 1);
+    if (grid > prm.n_tiles) grid = prm.n_tiles;
+    profile_exact_kernel<PT><<<(unsigned)grid, EX_THREADS, smem, stream>>>(prm);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+static int check_common(const void *d_profile, int dtype, int64_t n, const double *struct_table, int W)
+{
+    if (!d_profile || !struct_table) { rs_set_error("null profile or table"); return RS_ERR_INVALID; }
+    if (dtype != RS_F32 && dtype != RS_F64) { rs_set_error("profile_dtype must be RS_F32 or RS_F64"); return RS_ERR_INVALID; }
+    if (W < 1 || W > RS_MAX_W) { rs_set_error("motif width %d outside [1, %d]", W, RS_MAX_W); return RS_ERR_INVALID; }
+    if (n < 0) { rs_set_error("negative length"); return RS_ERR_INVALID; }
+    if ((uintptr_t)d_profile & 15) { rs_set_error("profile pointer must be 16-byte aligned"); return RS_ERR_INVALID; }
+    return RS_OK;
+}
+
+extern "C" int rs_profile_stats(const void *d_profile, int profile_dtype, int64_t n_rows, double *d_stats3,
+                                void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_profile || !d_stats3 || n_rows < 0) { rs_set_error("rs_profile_stats: bad argument"); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_stats3, 0, 3 * sizeof(double), st));
+    if (n_rows > 0) {
+        int grid = rs_sm_count() * 8;
+        if (profile_dtype == RS_F32)
+            profile_stats_kernel<float><<<grid, 256, 0, st>>>((const float *)d_profile, n_rows, d_stats3);
+        else if (profile_dtype == RS_F64)
+            profile_stats_kernel<double><<<grid, 256, 0, st>>>((const double *)d_profile, n_rows, d_stats3);
+        else { rs_set_error("bad profile_dtype"); return RS_ERR_INVALID; }
+        RS_CUDA(cudaGetLastError());
+    }
+    stats_finish_kernel<<<1, 1, 0, st>>>(d_stats3);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+extern "C" int rs_scores_dense_profile(const void *d_profile, int profile_dtype, int64_t n_rows,
+                                       const uint8_t *d_codes, const double *table, int W, double *d_out,
+                                       void *stream)
+{
+    int rc = check_common(d_profile, profile_dtype, n_rows, table, W);
+    if (rc) return rc;
+    if (n_rows < W) return RS_OK;
+    if (!d_out) { rs_set_error("null output"); return RS_ERR_INVALID; }
+    if (d_codes && ((uintptr_t)d_codes & 15)) { rs_set_error("codes pointer must be 16-byte aligned"); return RS_ERR_INVALID; }
+    ProfileParams prm = {};
+    prm.codes = d_codes; prm.profile = d_profile; prm.dense_out = d_out;
+    prm.n = n_rows; prm.padded = rs_padded_count(n_rows);
+    prm.n_tiles = (n_rows + EX_TILE - 1) / EX_TILE;
+    prm.W = W; prm.dense = 1; prm.mode = RS_MODE_STRUCT; prm.threshold = 0;
+    for (int k = 0; k < W * RS_CHANNELS; k++) prm.sd[k] = table[k];
+    return profile_dtype == RS_F32 ? launch_exact<float>(prm, (cudaStream_t)stream)
+                                   : launch_exact<double>(prm, (cudaStream_t)stream);
+}
+
+extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                             const double *seq_table, const double *struct_table, int W, double threshold,
+                             double profile_absrow_max, int mode, int64_t hit_capacity, int64_t *d_hit_pos,
+                             float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
+                             int64_t work_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_common(d_profile, profile_dtype, n, struct_table, W);
+    if (rc) return rc;
+    if (!d_codes || ((uintptr_t)d_codes & 15)) { rs_set_error("codes pointer null or not 16-byte aligned"); return RS_ERR_INVALID; }
+    if (mode != RS_MODE_STRUCT && mode != RS_MODE_AND) { rs_set_error("bad mode"); return RS_ERR_INVALID; }
+    if (mode == RS_MODE_AND && (!seq_table || !d_hit_seq)) { rs_set_error("RS_MODE_AND needs a sequence table and d_hit_seq"); return RS_ERR_INVALID; }
+    if (!d_counters2 || hit_capacity < 0 || (hit_capacity > 0 && (!d_hit_pos || !d_hit_struct))) {
+        rs_set_error("bad hit buffers"); return RS_ERR_INVALID;
+    }
+    if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    if (n < W) return RS_OK;
+    WorkLayout wl = rs_work_layout(n, hit_capacity);
+    if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+
+    ProfileParams prm = {};
+    prm.codes = d_codes; prm.profile = d_profile; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.threshold = threshold; prm.mode = mode; prm.W = W; prm.dense = 0;
+    uint8_t *wk = (uint8_t *)d_work;
+    prm.st.pos = (int64_t *)(wk + wl.off_pos);
+    prm.st.seq = d_hit_seq ? (float *)(wk + wl.off_seq) : nullptr;
+    prm.st.str = (double *)(wk + wl.off_str);
+    prm.st.tile_seg = (ulonglong2 *)(wk + wl.off_seg);
+    prm.st.counters = (unsigned long long *)d_counters2;
+    prm.st.capacity = hit_capacity;
+
+    // Can the fp32 filter be used?  It needs float profiles, W <= RS_FAST_W, a finite
+    // threshold and a finite guard band; rows of the table that hold -inf (zero-probability
+    // letters with pseudocount 0) are replaced by a non-negative upper bound
+    // (nan_to_num makes such a row contribute 0 or -DBL_MAX, never more than max(0, finite part)).
+    bool fast = profile_dtype == RS_F32 && W <= RS_FAST_W && isfinite(threshold) &&
+                isfinite(profile_absrow_max) && profile_absrow_max >= 0;
+    double S = 0.0;
+    for (int j = 0; j < W && fast; j++) {
+        bool row_nonfinite = false;
+        double rowmax = 0.0;
+        for (int c = 0; c < RS_CHANNELS; c++) {
+            double v = struct_table[j * RS_CHANNELS + c];
+            if (v != v || v == INFINITY) fast = false;           // NaN / +inf: exact kernel only
+            else if (v == -INFINITY) row_nonfinite = true;
+        }
+        for (int c = 0; c < RS_CHANNELS; c++) {
+            double v = struct_table[j * RS_CHANNELS + c];
+            double f = row_nonfinite ? ((isfinite(v) && v > 0) ? v : 0.0) : v;
+            prm.sf[j * RS_CHANNELS + c] = f32_round_up(f);
+            if (!isfinite((double)prm.sf[j * RS_CHANNELS + c])) fast = false;
+            rowmax = fmax(rowmax, fabs(f));
+        }
+        S += rowmax;
+    }
+    for (int k = 0; k < W * RS_CHANNELS; k++) prm.sd[k] = struct_table[k];
+    if (seq_table) for (int k = 0; k < W * 4; k++) prm.qd[k] = seq_table[k];
+
+    int64_t n_tiles;
+    if (fast) {
+        // |fp32 result - real value of sum(p * sf)| <= gamma * sum|p*sf| <= gamma * R * S, and sf >= table
+        // entry wise for p >= 0; negative p are covered by the +2 ulp term.  Generous constant.
+        const double R = fmax(profile_absrow_max, 1.0);
+        const double tol = ldexp(1.0, -23) * (double)(RS_CHANNELS * W + 8) * S * R;
+        prm.filt_thr = f32_round_down(threshold - tol);
+        if (!isfinite((double)prm.filt_thr)) fast = false;
+    }
+    if (fast) {
+        n_tiles = (n + FT_TILE - 1) / FT_TILE;
+        prm.n_tiles = n_tiles;
+        rc = FilterDispatch<RS_FAST_W>::run(W, prm, st);
+    } else {
+        n_tiles = (n + EX_TILE - 1) / EX_TILE;
+        prm.n_tiles = n_tiles;
+        rc = profile_dtype == RS_F32 ? launch_exact<float>(prm, st) : launch_exact<double>(prm, st);
+    }
+    if (rc) return rc;
+    return rs_order_hits(prm.st, n_tiles, d_hit_pos, d_hit_seq, d_hit_struct, wk + wl.off_scan, st);
+}

@@ -1,0 +1,325 @@
+"""Device-buffer plumbing between the Python host API and the C ABI.
+
+PyTorch is used for exactly three things: allocating device / pinned-host memory, host<->
+device copies and CUDA streams.  All arithmetic happens in librnascan_b200.so.
+
+Layout in HBM:
+  symbol stream   uint8[rs_padded_count(n)]      records concatenated, one 0xFF separator
+                                                  after every record, padding = 0xFF
+  profile stream  float32|float64[padded][7]      rows aligned 1:1 with the symbol stream
+                                                  (separator rows are zeros), channels
+                                                  B,E,H,L,M,R,T
+  hits            int64 pos[], float32 seq[], float64 struct[]   (structure of arrays)
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, RnascanCudaError
+
+CHANNELS = "BEHLMRT"        # device channel order == profile file column order
+RNA_COLUMNS = "ACGU"        # device column order of sequence tables (matrix.py:57 sorts)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RnascanCudaError(
+            "rnascan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def padded_count(n):
+    return int(lib.rs_padded_count(int(n)))
+
+
+# --------------------------------------------------------------------------- packing (host)
+def pack_texts(texts, kind):
+    """Encode a list of record strings into one symbol stream (host, numpy).
+
+    Returns (codes uint8[n_total], offsets int64[R], lengths int64[R]); record r occupies
+    codes[offsets[r] : offsets[r]+lengths[r]] and is followed by one separator.
+    """
+    enc = lib.rs_host_encode_rna if kind == "rna" else lib.rs_host_encode_struct
+    lengths = np.fromiter((len(t) for t in texts), dtype=np.int64, count=len(texts))
+    offsets = np.zeros(len(texts), dtype=np.int64)
+    if len(texts) > 1:
+        np.cumsum(lengths[:-1] + 1, out=offsets[1:])
+    total = int(lengths.sum() + len(texts))
+    raw = "\n".join(texts).encode("latin-1", "replace") + b"\n" if texts else b""
+    assert len(raw) == total
+    src = np.frombuffer(raw, dtype=np.uint8)
+    codes = np.empty(total, dtype=np.uint8)
+    if total:
+        check(enc(src.ctypes.data, total, codes.ctypes.data))
+        codes[offsets + lengths] = _lib.RS_SEP
+    return codes, offsets, lengths
+
+
+def pack_profiles(profiles, dtype=np.float64):
+    """Concatenate (L_r, 7) arrays with one zero separator row after each."""
+    lengths = np.fromiter((p.shape[0] for p in profiles), dtype=np.int64, count=len(profiles))
+    total = int(lengths.sum() + len(profiles))
+    out = np.zeros((total, len(CHANNELS)), dtype=dtype)
+    off = 0
+    for p in profiles:
+        out[off:off + p.shape[0]] = p
+        off += p.shape[0] + 1
+    return out
+
+
+class SymbolStream(object):
+    """A symbol stream resident in HBM."""
+
+    def __init__(self, codes, offsets=None, lengths=None, device=None):
+        require_cuda()
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.n = int(codes.shape[0])
+        self.offsets = np.zeros(1, np.int64) if offsets is None else np.asarray(offsets, np.int64)
+        self.lengths = np.array([self.n], np.int64) if lengths is None else np.asarray(lengths, np.int64)
+        npad = padded_count(self.n)
+        host = torch.empty(npad, dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        hv[:self.n] = codes
+        hv[self.n:] = _lib.RS_SEP
+        self.codes = host.to(device or "cuda", non_blocking=True)
+        self._host = host            # keep the pinned buffer alive until the copy is done
+
+    @classmethod
+    def from_texts(cls, texts, kind, device=None):
+        codes, offsets, lengths = pack_texts(texts, kind)
+        return cls(codes, offsets, lengths, device)
+
+    def locate(self, pos):
+        """stream position -> (record index, 0-based start within the record)."""
+        pos = np.asarray(pos, dtype=np.int64)
+        rec = np.searchsorted(self.offsets, pos, side="right") - 1
+        return rec, pos - self.offsets[rec]
+
+
+class ProfileStream(object):
+    """A 7-channel profile stream resident in HBM, row-aligned with a SymbolStream."""
+
+    def __init__(self, rows, device=None):
+        require_cuda()
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype not in (np.float32, np.float64):
+            rows = rows.astype(np.float64)
+        if rows.ndim != 2 or rows.shape[1] != len(CHANNELS):
+            raise ValueError("profile must have shape (L, 7) in channel order %s" % CHANNELS)
+        self.n = int(rows.shape[0])
+        self.dtype = _lib.RS_F32 if rows.dtype == np.float32 else _lib.RS_F64
+        npad = padded_count(self.n)
+        tdt = torch.float32 if rows.dtype == np.float32 else torch.float64
+        host = torch.zeros((npad, len(CHANNELS)), dtype=tdt, pin_memory=True)
+        host.numpy()[:self.n] = rows
+        self.rows = host.to(device or "cuda", non_blocking=True)
+        self._host = host
+        self._stats = None
+
+    @classmethod
+    def from_device(cls, tensor, n):
+        """Wrap an already-resident (padded, 7) tensor (used by bench.py)."""
+        self = cls.__new__(cls)
+        self.n = int(n)
+        self.dtype = _lib.RS_F32 if tensor.dtype == torch.float32 else _lib.RS_F64
+        self.rows = tensor
+        self._host = None
+        self._stats = None
+        return self
+
+    def stats(self):
+        """(max abs row sum, #non-finite, #negative) -- computed once on the device."""
+        if self._stats is None:
+            st = torch.empty(3, dtype=torch.float64, device=self.rows.device)
+            check(lib.rs_profile_stats(_ptr(self.rows), self.dtype, self.n, _ptr(st), _stream()))
+            self._stats = tuple(float(v) for v in st.cpu().numpy())
+        return self._stats
+
+    def absrow_max(self):
+        mx, bad, neg = self.stats()
+        return float("nan") if (bad or neg) else mx
+
+
+# --------------------------------------------------------------------------- kernels
+def _table(table, cols):
+    t = np.ascontiguousarray(table, dtype=np.float64)
+    if t.ndim != 2:
+        raise ValueError("position-weight matrix has incorrect rank (%d expected 2)" % t.ndim)
+    if t.shape[1] != cols:
+        raise ValueError("position-weight matrix should have %d columns (%d columns found)"
+                         % (cols, t.shape[1]))
+    if not 1 <= t.shape[0] <= _lib.RS_MAX_W:
+        raise ValueError("motif width %d outside [1, %d]" % (t.shape[0], _lib.RS_MAX_W))
+    return t
+
+
+def histogram(stream):
+    """int64[8] exact counts of symbols 0..7 whose 'not counted' bit is clear."""
+    counts = torch.zeros(8, dtype=torch.int64, device=stream.codes.device)
+    check(lib.rs_hist(_ptr(stream.codes), stream.n, _ptr(counts), _stream()))
+    return counts
+
+
+def dense_seq(stream, table):
+    t = _table(table, 4)
+    W = t.shape[0]
+    nout = max(0, stream.n - W + 1)
+    out = torch.empty(max(nout, 1), dtype=torch.float32, device=stream.codes.device)
+    check(lib.rs_scores_dense_seq(_ptr(stream.codes), stream.n, t.ctypes.data, W, _ptr(out), _stream()))
+    return out[:nout]
+
+
+def dense_struct(stream, table):
+    t = _table(table, 7)
+    W = t.shape[0]
+    nout = max(0, stream.n - W + 1)
+    out = torch.empty(max(nout, 1), dtype=torch.float64, device=stream.codes.device)
+    check(lib.rs_scores_dense_struct(_ptr(stream.codes), stream.n, t.ctypes.data, W, _ptr(out), _stream()))
+    return out[:nout]
+
+
+def dense_profile(profile, table, stream=None):
+    t = _table(table, 7)
+    W = t.shape[0]
+    nout = max(0, profile.n - W + 1)
+    out = torch.empty(max(nout, 1), dtype=torch.float64, device=profile.rows.device)
+    codes = None if stream is None else stream.codes
+    check(lib.rs_scores_dense_profile(_ptr(profile.rows), profile.dtype, profile.n, _ptr(codes),
+                                      t.ctypes.data, W, _ptr(out), _stream()))
+    return out[:nout]
+
+
+class HitBuffers(object):
+    """Caller-owned output + workspace for one thresholded scan (reusable)."""
+
+    def __init__(self, n, capacity, device, want_seq=True, want_struct=True):
+        self.capacity = int(capacity)
+        cap = max(self.capacity, 1)
+        self.pos = torch.empty(cap, dtype=torch.int64, device=device)
+        self.seq = torch.empty(cap, dtype=torch.float32, device=device) if want_seq else None
+        self.struct = torch.empty(cap, dtype=torch.float64, device=device) if want_struct else None
+        self.counters = torch.zeros(2, dtype=torch.int64, device=device)
+        self.work_bytes = int(lib.rs_scan_workspace_bytes(int(n), self.capacity))
+        self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
+
+
+def _run_thresholded(n, device, launch, want_seq, want_struct, capacity=None):
+    """Run `launch(buffers)`; grow the hit buffers and re-run if they overflowed."""
+    cap = int(capacity) if capacity else max(4096, n // 256)
+    while True:
+        hb = HitBuffers(n, cap, device, want_seq, want_struct)
+        launch(hb)
+        found, rescored = (int(v) for v in hb.counters.cpu().numpy())
+        if found <= cap:
+            pos = hb.pos[:found].cpu().numpy()
+            seq = hb.seq[:found].cpu().numpy() if want_seq else None
+            st = hb.struct[:found].cpu().numpy() if want_struct else None
+            return pos, seq, st, rescored
+        cap = found
+
+
+def scan_seq(stream, table, threshold, capacity=None):
+    """Ordered (pos int64[], score float32[]) of windows with score > threshold."""
+    t = _table(table, 4)
+    W = t.shape[0]
+    threshold = float(threshold)
+    if threshold == float("-inf"):
+        sc = dense_seq(stream, t).cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            pos = np.nonzero(sc.astype(np.float64) > threshold)[0].astype(np.int64)
+        return pos, sc[pos]
+
+    def launch(hb):
+        check(lib.rs_scan_seq(_ptr(stream.codes), stream.n, t.ctypes.data, W, threshold, hb.capacity,
+                              _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work),
+                              hb.work_bytes, _stream()))
+    pos, seq, _, _ = _run_thresholded(stream.n, stream.codes.device, launch, True, False, capacity)
+    return pos, seq
+
+
+def scan_struct_onehot(stream, table, threshold, capacity=None):
+    t = _table(table, 7)
+    W = t.shape[0]
+    threshold = float(threshold)
+    if threshold == float("-inf"):
+        sc = dense_struct(stream, t).cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            pos = np.nonzero(sc > threshold)[0].astype(np.int64)
+        return pos, sc[pos]
+
+    def launch(hb):
+        check(lib.rs_scan_struct_onehot(_ptr(stream.codes), stream.n, t.ctypes.data, W, threshold,
+                                        hb.capacity, _ptr(hb.pos), _ptr(hb.struct), _ptr(hb.counters),
+                                        _ptr(hb.work), hb.work_bytes, _stream()))
+    pos, _, st, _ = _run_thresholded(stream.n, stream.codes.device, launch, False, True, capacity)
+    return pos, st
+
+
+def scan_pair_onehot(seq_stream, struct_stream, seq_table, struct_table, threshold, capacity=None):
+    """Windows where the sequence score AND the structure score exceed the threshold."""
+    ts, tq = _table(seq_table, 4), _table(struct_table, 7)
+    if ts.shape[0] != tq.shape[0]:
+        raise ValueError("sequence and structure motifs must have the same width")
+    if seq_stream.n != struct_stream.n:
+        raise ValueError("sequence and structure streams differ in length")
+    W = ts.shape[0]
+    threshold = float(threshold)
+    if threshold == float("-inf"):
+        a = dense_seq(seq_stream, ts).cpu().numpy()
+        b = dense_struct(struct_stream, tq).cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            pos = np.nonzero((a.astype(np.float64) > threshold) & (b > threshold))[0].astype(np.int64)
+        return pos, a[pos], b[pos]
+
+    def launch(hb):
+        check(lib.rs_scan_pair_onehot(_ptr(seq_stream.codes), _ptr(struct_stream.codes), seq_stream.n,
+                                      ts.ctypes.data, tq.ctypes.data, W, threshold, hb.capacity,
+                                      _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct), _ptr(hb.counters),
+                                      _ptr(hb.work), hb.work_bytes, _stream()))
+    pos, sq, st, _ = _run_thresholded(seq_stream.n, seq_stream.codes.device, launch, True, True, capacity)
+    return pos, sq, st
+
+
+def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=None, return_stats=False):
+    """Sequence PSSM + averaged profile in one pass.
+
+    seq_table=None  -> RS_MODE_STRUCT: hits where the profile score > threshold
+    seq_table given -> RS_MODE_AND:    hits where both scores > threshold
+    Returns (pos, seq_scores|None, struct_scores[, n_rescored]).
+    """
+    tq = _table(struct_table, 7)
+    W = tq.shape[0]
+    mode = _lib.RS_MODE_STRUCT if seq_table is None else _lib.RS_MODE_AND
+    ts = None if seq_table is None else _table(seq_table, 4)
+    if ts is not None and ts.shape[0] != W:
+        raise ValueError("sequence and structure motifs must have the same width")
+    if stream.n != profile.n:
+        raise ValueError("symbol stream and profile stream differ in length")
+    threshold = float(threshold)
+    if threshold == float("-inf"):
+        b = dense_profile(profile, tq, stream).cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            keep = b > threshold
+            if ts is not None:
+                a = dense_seq(stream, ts).cpu().numpy()
+                keep &= a.astype(np.float64) > threshold
+        pos = np.nonzero(keep)[0].astype(np.int64)
+        out = (pos, a[pos] if ts is not None else None, b[pos])
+        return out + (0,) if return_stats else out
+    absmax = profile.absrow_max()
+
+    def launch(hb):
+        check(lib.rs_scan_fused(_ptr(stream.codes), _ptr(profile.rows), profile.dtype, stream.n,
+                                0 if ts is None else ts.ctypes.data, tq.ctypes.data, W, threshold,
+                                absmax, mode, hb.capacity, _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct),
+                                _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, _stream()))
+    pos, sq, st, resc = _run_thresholded(stream.n, stream.codes.device, launch, ts is not None, True,
+                                         capacity)
+    return (pos, sq, st, resc) if return_stats else (pos, sq, st)
