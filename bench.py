@@ -1,0 +1,475 @@
+#!/usr/bin/env python
+"""Benchmark of the rnascan_b200 hot path (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3              # this framework (default)
+    python bench.py --impl reference --gpus 1 --steps 3 ...     # the reference's CPU path
+    torchrun ... bench.py --gpus N ...                          # one rank per GPU, weak scaling
+
+Workload (default "c4", BASELINE.json configs[3] -- the configuration the north-star's
+HBM-fraction target is quoted on): combined sequence-PSSM + averaged 7-channel structure
+profile scan, 125 Mnt per GPU (= 1 Gnt on 8 GPUs), W = 7, m = 6, sequence background
+computed from the data (histogram -> all-reduce of the integer counts -> log-odds on the
+host), structure background = the reference's example 3'UTR table.  A step is ONE pass of
+the whole path over the rank's shard:   histogram -> [all-reduce] -> PSSM -> fused scan ->
+ordered hit compaction.  `--workload c2` / `c3` time the sequence-only and one-hot
+structure scans (BASELINE.json configs[1], configs[2]) the same way.
+
+All positions/s figures count scored positions = sum over records of max(0, L - W + 1).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+W_MOTIF = 7
+THRESHOLD = 6.0
+SS_BG = {"B": 0.0163181097311479, "E": 0.272087789050946, "H": 0.153012079123538,
+         "L": 0.204624685341275, "M": 0.0196001330531237, "R": 0.196989713257981,
+         "T": 0.137367490441988}       # example/3p_UTR_background_structural_context.txt
+ALGO_BYTES = {"c4": 29.0, "c2": 1.0, "c3": 5.0}     # SURVEY.md section 8(d), per scored position
+
+
+# ----------------------------------------------------------------------------- helpers
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- synthetic shard
+def record_layout(n_symbols, seed):
+    """Record lengths (lognormal) filling ~n_symbols stream slots incl. separators."""
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(seed)
+    n_records = max(1, int(round(n_symbols / 3334.0)))
+    lengths = synth.record_lengths(n_symbols - n_records, n_records, rng)
+    offsets, total = synth.layout(lengths)
+    return lengths, offsets, total
+
+
+def scored_positions(lengths, W):
+    return int(np.maximum(lengths - W + 1, 0).sum())
+
+
+def make_device_shard(n_symbols, seed, workload, device):
+    """Synthetic shard generated on the device with torch (plumbing only): symbol codes with
+    separators + N runs, and (c4) float32 profile rows = Dirichlet(0.2) smoothed by a
+    length-5 box filter, re-normalised, separator rows zero."""
+    import torch
+    from rnascan_b200 import device as dev
+    lengths, offsets, n = record_layout(n_symbols, seed)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    npad = dev.padded_count(n)
+    sep_idx = torch.from_numpy(offsets + lengths).to(device)
+    if workload == "c3":
+        p = torch.tensor([SS_BG[c] for c in "BEHLMRT"], device=device, dtype=torch.float64)
+        change = torch.rand(n, device=device, generator=g) >= 0.8
+        change[0] = True
+        draws = torch.multinomial(p.float(), int(change.sum().item()), replacement=True, generator=g)
+        codes = draws[torch.cumsum(change, 0) - 1].to(torch.uint8)
+    else:
+        cdf = torch.tensor([0.27, 0.49, 0.71], device=device)
+        codes = torch.bucketize(torch.rand(n, device=device, generator=g), cdf).to(torch.uint8)
+        n_runs = int(n * 0.001 / 25.5)
+        if n_runs:
+            starts = torch.randint(0, n, (n_runs,), device=device, generator=g)
+            runlen = torch.randint(1, 51, (n_runs,), device=device, generator=g)
+            mark = torch.zeros(n + 64, device=device, dtype=torch.int32)
+            mark.index_add_(0, starts, torch.ones_like(starts, dtype=torch.int32))
+            mark.index_add_(0, torch.clamp(starts + runlen, max=n + 63), -torch.ones_like(starts, dtype=torch.int32))
+            codes[torch.cumsum(mark[:n], 0) > 0] = 0x0C
+            del mark
+    full = torch.full((npad,), 0xFF, dtype=torch.uint8, device=device)
+    full[:n] = codes
+    full[sep_idx] = 0xFF
+    del codes
+    prof = None
+    if workload == "c4":
+        prof = torch.zeros((npad, 7), dtype=torch.float32, device=device)
+        step = 1 << 24
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            lo, hi = max(0, a - 2), min(n, b + 2)
+            gam = torch._standard_gamma(torch.full((hi - lo, 7), 0.2, device=device), generator=g)
+            gam = gam / gam.sum(1, keepdim=True).clamp_min(1e-30)
+            sm = torch.nn.functional.avg_pool1d(gam.t().unsqueeze(0), 5, stride=1, padding=2,
+                                                count_include_pad=False)[0].t()
+            sm = sm / sm.sum(1, keepdim=True).clamp_min(1e-30)
+            prof[a:b] = sm[a - lo:a - lo + (b - a)]
+            del gam, sm
+        prof[sep_idx] = 0.0
+    torch.cuda.synchronize()
+    return {"codes": full, "prof": prof, "n": n, "lengths": lengths, "offsets": offsets}
+
+
+def make_tables_fn(workload, seed=102):
+    """PFMs (Dirichlet(0.3) rows, pseudocount 0.01) and the counts -> log-odds tables step,
+    done with the product's own PFM preprocessing (rnascan_b200.motifs)."""
+    from rnascan_b200 import motifs, synth
+    rng = np.random.default_rng(seed)
+    pfm_seq = synth.pfm_rows(W_MOTIF, 4, rng)               # columns A,C,G,U
+    pfm_str = synth.pfm_rows(W_MOTIF, 7, np.random.default_rng(seed + 1))   # columns B,E,H,L,M,R,T
+    rna, chan = "GAUC", "EHTBLRM"                           # alphabet.letters orders
+    seq_counts = {l: pfm_seq[:, "ACGU".index(l)].tolist() for l in rna}
+    str_counts = {l: pfm_str[:, "BEHLMRT".index(l)].tolist() for l in chan}
+    str_pssm = motifs.log_odds(motifs.normalize_counts(str_counts, chan, 0.01), chan,
+                               {l: SS_BG[l] for l in chan})
+    tq = np.array([str_pssm[l] for l in "BEHLMRT"], np.float64).T.copy()
+    seq_prob = motifs.normalize_counts(seq_counts, rna, 0.01)
+    str_prob_uniform = motifs.normalize_counts(str_counts, chan, 0.01)
+
+    def seq_table(counts8):
+        # rnascan.py:445-457: p = (count + 1) / (sum(count) + |A|), keys in "GAUC" order
+        c = {"A": int(counts8[0]), "C": int(counts8[1]), "G": int(counts8[2]), "U": int(counts8[3])}
+        total = 4 + sum(c[l] for l in rna)
+        bg = {l: (float(c[l]) + 1) / total for l in rna}
+        pssm = motifs.log_odds(seq_prob, rna, bg)
+        return np.array([pssm[l] for l in "ACGU"], np.float64).T.copy()
+
+    def struct_table_computed(counts8):
+        c = {l: int(counts8["BEHLMRT".index(l)]) for l in chan}
+        total = 7 + sum(c.values())
+        bg = {l: (float(c[l]) + 1) / total for l in chan}
+        pssm = motifs.log_odds(str_prob_uniform, chan, bg)
+        return np.array([pssm[l] for l in "BEHLMRT"], np.float64).T.copy()
+
+    if workload == "c4":
+        return lambda counts8: (seq_table(counts8), tq)
+    if workload == "c2":
+        return lambda counts8: (seq_table(counts8), None)
+    return lambda counts8: (None, struct_table_computed(counts8))
+
+
+# ----------------------------------------------------------------------------- this framework
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from rnascan_b200 import device as dev, _lib
+    from rnascan_b200.device import lib, check, _ptr
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    dev.require_cuda()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    wl = args.workload
+    n_target = args.n_per_gpu
+    shard = make_device_shard(n_target, 4000 + rank, wl, device)
+    n, codes, prof = shard["n"], shard["codes"], shard["prof"]
+    positions = scored_positions(shard["lengths"], W_MOTIF)
+    tables = make_tables_fn(wl)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    counts = torch.zeros(8, dtype=torch.int64, device=device)
+    counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+    hb = dev.HitBuffers(n, max(1 << 16, n // 256), device)
+    dense_out = torch.empty(n, dtype=torch.float64, device=device) if wl == "c3" else None
+    absmax = 1.0
+    if wl == "c4":
+        absmax = dev.ProfileStream.from_device(prof, n).absrow_max()
+    launches = [0]
+
+    def all_reduce(t):
+        if world > 1:
+            dist.all_reduce(t)
+
+    def step():
+        counts.zero_()
+        check(lib.rs_hist(_ptr(codes), n, _ptr(counts), sptr)); launches[0] += 1
+        all_reduce(counts)                                  # the path's only collective
+        counts_host.copy_(counts, non_blocking=True)
+        stream.synchronize()
+        ts, tq = tables(counts_host.numpy())
+        if wl == "c4":
+            check(lib.rs_scan_fused(_ptr(codes), _ptr(prof), _lib.RS_F32, n, ts.ctypes.data, tq.ctypes.data,
+                                    W_MOTIF, THRESHOLD, absmax, _lib.RS_MODE_AND, hb.capacity, _ptr(hb.pos),
+                                    _ptr(hb.seq), _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work),
+                                    hb.work_bytes, sptr))
+            launches[0] += 3
+        elif wl == "c2":
+            check(lib.rs_scan_seq(_ptr(codes), n, ts.ctypes.data, W_MOTIF, THRESHOLD, hb.capacity, _ptr(hb.pos),
+                                  _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, sptr))
+            launches[0] += 3
+        else:
+            check(lib.rs_scores_dense_struct(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
+            launches[0] += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches[0] = 0
+    check(lib.rs_prof_begin(max(args.steps, 1)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kms = np.zeros(max(args.steps, 1), np.float32)
+    nrec = np.zeros(1, np.int32)
+    check(lib.rs_prof_end(kms.ctypes.data, len(kms), nrec.ctypes.data))
+    kernel_ms = float(kms[:int(nrec[0])].mean()) if nrec[0] else float("nan")
+    n_launch = launches[0]
+    hits = int(hb.counters[0].item()) if wl != "c3" else None
+
+    # ---- end to end: host buffers -> device -> hits back on the host, every step
+    e2e = None
+    if wl == "c4":
+        h_codes = torch.empty(codes.shape, dtype=torch.uint8).pin_memory()
+        h_codes.copy_(codes)
+        h_prof = torch.empty(prof.shape, dtype=torch.float32).pin_memory()
+        h_prof.copy_(prof)
+        torch.cuda.synchronize()
+        pipe = dev.HostFusedScanner(n, W_MOTIF, device=device)
+        res = None
+        for _ in range(2):
+            res = pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax, all_reduce=all_reduce)
+        barrier()
+        k2 = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(k2):
+            res = pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax, all_reduce=all_reduce)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k2
+        e2e = {"ms": ms_e2e, "h2d": pipe.h2d_bytes, "d2h": pipe.d2h_bytes, "hits": int(len(res[0]))}
+        if hits is not None and e2e["hits"] != hits:
+            raise SystemExit("e2e hit count %d != device-resident hit count %d" % (e2e["hits"], hits))
+        del h_prof, pipe
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- max over ranks, totals
+    stats = torch.tensor([ms_total, kernel_ms, e2e["ms"] if e2e else 0.0], device=device, dtype=torch.float64)
+    tot = torch.tensor([positions, n], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms_total, kernel_ms, ms_e2e = (float(v) for v in stats.cpu())
+    all_positions, all_n = (int(v) for v in tot.cpu())
+    ms_step = ms_total / args.steps
+    peak, peak_src = measured_peaks()
+    achieved = ALGO_BYTES[wl] * positions / (kernel_ms * 1e-3) / 1e9
+    out = {
+        "metric": "scored positions/sec", "value": all_positions / (ms_step * 1e-3) / 1e9, "unit": "Gpos/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 filter + f64 exact re-score (sequence: f64 accumulate -> f32)" if wl == "c4" else
+                 ("f64 accumulate -> f32" if wl == "c2" else "f64"),
+        "data": "synthetic (SURVEY.md 8d shapes; generated on device, seed 4000+rank)",
+        "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile, fused AND scan",
+                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, dense f64 output"}[wl],
+                   "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
+                   "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
+                   "background": "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step",
+                   "l2_policy": "inputs (%.2f GB per GPU) exceed the 126 MB L2" %
+                                (n * (29 if wl == "c4" else 1) / 1e9),
+                   "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
+        "gpu_launches": n_launch,
+        "roofline": {"bound": "hbm", "kernel": {"c4": "fused_filter_kernel<7>", "c2": "onehot_kernel<4>",
+                                               "c3": "onehot_kernel<7,dense>"}[wl],
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],
+                     "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step, "traffic": None},
+        "clocks": clocks,
+    }
+    if hits is not None:
+        out["hits_rank0"] = hits
+    if e2e:
+        out["e2e"] = {"value": all_positions / (ms_e2e * 1e-3) / 1e9, "unit": "Gpos/s",
+                      "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                      "ms_per_step": ms_e2e,
+                      "api": "rnascan_b200.device.HostFusedScanner.run (pinned host streams in, host hit arrays out)"}
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_port_baseline(wl)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def host_sample(n_symbols, workload, seed=4999, min_records=1):
+    """A bounded host-side sample of the same synthetic workload (numpy generator)."""
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(seed)
+    n_records = max(1, min_records, int(round(n_symbols / 3334.0)))
+    lengths = synth.record_lengths(n_symbols - n_records, n_records, rng)
+    if workload == "c3":
+        codes, offsets = synth.struct_codes(lengths, rng)
+        return lengths, offsets, codes, None
+    codes, offsets = synth.rna_codes(lengths, rng)
+    rows = synth.profile_rows(len(codes), rng, lengths=lengths) if workload == "c4" else None
+    return lengths, offsets, codes, rows
+
+
+def cpu_port_baseline(workload, n_symbols=16_000_000):
+    """The C oracle (oracle/pwm_oracle.c, a port of the reference's loops) over whole records
+    with all host threads: the most the reference's C kernel could do if it were driven per
+    record instead of per window.  Reported, not the target."""
+    from oracle import oracle as orc
+    from rnascan_b200 import synth
+    L = orc.lib()
+    cores = int(L.orc_get_threads())
+    lengths, offsets, codes, rows = host_sample(n_symbols, workload)
+    positions = scored_positions(lengths, W_MOTIF)
+    tables = make_tables_fn(workload)
+    t0 = time.perf_counter()
+    if workload == "c3":
+        counts = np.array([(codes == k).sum() for k in range(8)], np.int64)
+        _, tq = tables(counts)
+        sc = orc.alpha_scores(synth.to_text(codes, "struct"), tq, "BEHLMRT")
+        nh = int(np.isfinite(sc).sum())
+    else:
+        text = synth.to_text(codes, "rna")
+        counts = np.zeros(8, np.int64)
+        cnt = np.zeros(4, np.int64)
+        L.orc_count_letters(text, len(text), b"ACGU", 4, cnt.ctypes.data)
+        counts[:4] = cnt
+        ts, tq = tables(counts)
+        a = orc.seq_scores(text, ts, threads=True)
+        keep = a.astype(np.float64) > THRESHOLD
+        if workload == "c4":
+            b = orc.profile_scores(rows, tq)
+            keep &= b > THRESHOLD
+        nh = int(keep.sum())
+    dt = time.perf_counter() - t0
+    return {"value": positions / dt / 1e9, "unit": "Gpos/s", "cores": cores, "kind": "port",
+            "sample": "%d symbols (%d scored positions) of the same synthetic workload, whole-record C loops "
+                      "on %d threads, %.2f s, %d hits" % (len(codes), positions, cores, dt, nh)}
+
+
+def run_reference(args):
+    """The reference's own CPU path, driven the way the reference drives it (oracle/ref_driver.py):
+    one _pwm.calculate call per window from Biopython-style search(), the pandas .iloc loop of
+    scan_averaged_structure, multiprocessing.Pool over records."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import ref_driver
+    wl = args.workload
+    cores = os.cpu_count() or 1
+    tables = make_tables_fn(wl)
+    rate = ref_driver.calibrate(wl, tables, W_MOTIF, THRESHOLD)          # windows/s on one core
+    target_s = float(os.environ.get("RNASCAN_REF_STEP_SECONDS", "8"))
+    n_symbols = int(max(2000, min(50_000_000, rate * cores * target_s)))
+    # the reference parallelises over records only: keep >= 2 records per core in the sample
+    lengths, offsets, codes, rows = host_sample(n_symbols, wl, seed=5999, min_records=2 * cores)
+    positions = scored_positions(lengths, W_MOTIF)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        nh = ref_driver.run_step(wl, lengths, offsets, codes, rows, tables, W_MOTIF, THRESHOLD, cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms_step = 1e3 * sum(times) / len(times)
+    value = positions / (ms_step * 1e-3) / 1e9
+    sample = ("%d symbols / %d records / %d scored positions per step of the same synthetic workload; "
+              "%s; Pool(%d); %d hits" % (len(codes), len(lengths), positions, ref_driver.describe(wl), cores, nh))
+    out = {"impl": "reference", "metric": "scored positions/sec", "value": value, "unit": "Gpos/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64 accumulate -> f32 (sequence), f64 (structure)", "data": "synthetic (bounded sample)",
+           "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile",
+                                   "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan"}[wl],
+                      "W": W_MOTIF, "minscore": THRESHOLD, "sample_symbols": len(codes)},
+           "gpu_launches": 0,
+           "cpu_baseline": {"value": value, "unit": "Gpos/s", "cores": cores,
+                            "kind": ref_driver.kind(), "sample": sample},
+           "e2e": {"value": value, "unit": "Gpos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3"])
+    ap.add_argument("--n-per-gpu", type=int, default=125_000_000, dest="n_per_gpu")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

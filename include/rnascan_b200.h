@@ -68,6 +68,13 @@ int         rs_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int64_t     rs_padded_count(int64_t n);                /* elements/rows to allocate     */
 int64_t     rs_scan_workspace_bytes(int64_t n, int64_t hit_capacity);
 
+/* ---- measurement hook (bench.py; no reference counterpart) --------------------------
+ * Between rs_prof_begin and rs_prof_end every scan entry point records a CUDA event pair
+ * tightly around its main kernel on the caller's stream (at most max_records pairs);
+ * rs_prof_end waits for them and returns the per-launch durations in milliseconds.     */
+int rs_prof_begin(int max_records);
+int rs_prof_end(float *ms_out, int capacity, int *n_records);
+
 /* ---- host-side encoding (CPU threads; replaces str.upper()/transcribe() + the char
  *      switch of _pwm.c:41-63 and the dict lookup of matrix.py:36-41) ---------------- */
 int rs_host_encode_rna(const uint8_t *text, int64_t n, uint8_t *codes);

@@ -37,6 +37,8 @@ _SIGS = {
     "rs_device_info": ([_vp, _vp, _vp], _int),
     "rs_padded_count": ([_i64], _i64),
     "rs_scan_workspace_bytes": ([_i64, _i64], _i64),
+    "rs_prof_begin": ([_int], _int),
+    "rs_prof_end": ([_vp, _int, _vp], _int),
     "rs_host_encode_rna": ([_vp, _i64, _vp], _int),
     "rs_host_encode_struct": ([_vp, _i64, _vp], _int),
     "rs_hist": ([_vp, _i64, _vp, _vp], _int),

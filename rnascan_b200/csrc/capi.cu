@@ -34,6 +34,53 @@ int rs_sm_count()
     return cached;
 }
 
+// --------------------------------------------------------------------------- profiling hook
+// A ring of CUDA event pairs recorded tightly around the main scan kernel of each entry
+// point, on the caller's stream, so bench.py can report that kernel's own duration inside
+// a longer timed step without synchronising between steps.
+#include <vector>
+static std::vector<cudaEvent_t> g_prof_ev;     // 2 * max_records
+static int g_prof_n = 0, g_prof_cap = 0;
+static bool g_prof_on = false, g_prof_open = false;
+
+void rs_prof_start(cudaStream_t s)
+{
+    if (!g_prof_on || g_prof_n >= g_prof_cap) return;
+    cudaEventRecord(g_prof_ev[2 * g_prof_n], s);
+    g_prof_open = true;
+}
+void rs_prof_stop(cudaStream_t s)
+{
+    if (!g_prof_on || !g_prof_open) return;
+    cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], s);
+    g_prof_open = false;
+    g_prof_n++;
+}
+
+extern "C" int rs_prof_begin(int max_records)
+{
+    if (max_records < 1 || max_records > 65536) { rs_set_error("rs_prof_begin: bad max_records"); return RS_ERR_INVALID; }
+    while ((int)g_prof_ev.size() < 2 * max_records) {
+        cudaEvent_t e;
+        RS_CUDA(cudaEventCreate(&e));
+        g_prof_ev.push_back(e);
+    }
+    g_prof_cap = max_records; g_prof_n = 0; g_prof_on = true; g_prof_open = false;
+    return RS_OK;
+}
+
+extern "C" int rs_prof_end(float *ms_out, int capacity, int *n_records)
+{
+    g_prof_on = false;
+    int n = g_prof_n < capacity ? g_prof_n : capacity;
+    for (int k = 0; k < n; k++) {
+        RS_CUDA(cudaEventSynchronize(g_prof_ev[2 * k + 1]));
+        RS_CUDA(cudaEventElapsedTime(&ms_out[k], g_prof_ev[2 * k], g_prof_ev[2 * k + 1]));
+    }
+    if (n_records) *n_records = n;
+    return RS_OK;
+}
+
 extern "C" int rs_version(void) { return 100; }            // 0.1.0
 
 extern "C" const char *rs_last_error(void) { return g_err; }

@@ -20,6 +20,8 @@ int  rs_cuda_fail(cudaError_t e, const char *what);
 
 static inline int64_t rs_roundup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 int rs_sm_count();               // SMs of the current device (cached)
+void rs_prof_start(cudaStream_t s);   // profiling hook (capi.cu): event pair around the main kernel
+void rs_prof_stop(cudaStream_t s);
 
 // --------------------------------------------------------------------------- PTX: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

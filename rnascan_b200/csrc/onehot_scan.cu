@@ -191,7 +191,9 @@ static int launch(const OneHotParams &prm, cudaStream_t stream)
 {
     int64_t grid = (int64_t)rs_sm_count() * (2048 / OH_THREADS);
     if (grid > prm.n_tiles) grid = prm.n_tiles;
+    rs_prof_start(stream);
     onehot_kernel<A, PAIR, DENSE><<<(unsigned)grid, OH_THREADS, 0, stream>>>(prm);
+    rs_prof_stop(stream);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

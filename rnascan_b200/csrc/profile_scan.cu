@@ -391,7 +391,9 @@ static int launch_filter(const ProfileParams &prm, cudaStream_t stream)
     }
     int64_t grid = (int64_t)rs_sm_count() * 2;
     if (grid > prm.n_tiles) grid = prm.n_tiles;
+    rs_prof_start(stream);
     fused_filter_kernel<W><<<(unsigned)grid, FT_THREADS, smem, stream>>>(prm);
+    rs_prof_stop(stream);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }
@@ -426,7 +428,9 @@ static int launch_exact(const ProfileParams &prm, cudaStream_t stream)
     }
     int64_t grid = (int64_t)rs_sm_count() * (sizeof(PT) == 4 ? 3 : 1);
     if (grid > prm.n_tiles) grid = prm.n_tiles;
+    rs_prof_start(stream);
     profile_exact_kernel<PT><<<(unsigned)grid, EX_THREADS, smem, stream>>>(prm);
+    rs_prof_stop(stream);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

@@ -323,3 +323,113 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     pos, sq, st, resc = _run_thresholded(stream.n, stream.codes.device, launch, ts is not None, True,
                                          capacity)
     return (pos, sq, st, resc) if return_stats else (pos, sq, st)
+
+
+# --------------------------------------------------------------------------- host-buffer pipeline
+class HostFusedScanner(object):
+    """Combined sequence + averaged-profile scan of HOST-resident streams.
+
+    The reference-facing call for data that lives in host memory (what the CLI has after
+    parsing): the symbol stream (1 B/symbol) goes to the device first so the background
+    histogram -- which the log-odds tables depend on -- is known early; the profile stream
+    (28 B/row) follows in chunks on a copy stream while the previous chunk is being scanned
+    on the compute stream (double buffering).  Chunks overlap by W-1 rows so every window
+    is scored exactly once.  All device buffers are allocated once and reused.
+    """
+
+    def __init__(self, n, W, chunk_rows=1 << 23, device=None, hits_per_row=1.0 / 64):
+        require_cuda()
+        self.device = torch.device(device or "cuda")
+        self.n, self.W = int(n), int(W)
+        self.chunk = max(256, int(chunk_rows) // 256 * 256)
+        self.starts = list(range(0, max(self.n - self.W + 1, 1), self.chunk)) if self.n >= self.W else []
+        rows = padded_count(min(self.chunk + self.W - 1, max(self.n, 1))) + 256
+        self.codes = torch.empty(padded_count(self.n) + 1024, dtype=torch.uint8, device=self.device)
+        self.prof = [torch.empty((rows, len(CHANNELS)), dtype=torch.float32, device=self.device)
+                     for _ in range(2)]
+        self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.loaded = [torch.cuda.Event() for _ in range(2)]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+        cap = max(4096, int(self.chunk * hits_per_row))
+        self.hb = [HitBuffers(self.chunk + self.W, cap, self.device) for _ in self.starts]
+        if self.hb:                      # one workspace serves all chunks (they run in order)
+            for hb in self.hb[1:]:
+                hb.work = self.hb[0].work
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, h_codes, h_prof, make_tables, threshold, mode=_lib.RS_MODE_AND, absrow_max=1.0,
+            all_reduce=None):
+        """h_codes: pinned uint8[>= n]; h_prof: pinned float32[>= n, 7];
+        make_tables(counts int64[8]) -> (seq_table | None, struct_table).
+        Returns (pos, seq_scores, struct_scores) as numpy arrays, positions ascending."""
+        n, W = self.n, self.W
+        comp = torch.cuda.current_stream(self.device)
+        self.h2d_bytes = self.d2h_bytes = 0
+        # -- pass 1: symbols -> device, exact background counts
+        self.codes[:n].copy_(h_codes[:n], non_blocking=True)
+        self.codes[n:].fill_(_lib.RS_SEP)
+        self.h2d_bytes += n
+        self.copy_stream.wait_stream(comp)
+        # profile chunks start flowing while the histogram runs
+        order = self.starts
+        def load(k):
+            c0 = order[k]
+            rows = min(self.chunk + W - 1, n - c0)
+            slot = k & 1
+            with torch.cuda.stream(self.copy_stream):
+                if k >= 2:
+                    self.copy_stream.wait_event(self.freed[slot])
+                self.prof[slot][:rows].copy_(h_prof[c0:c0 + rows], non_blocking=True)
+                self.loaded[slot].record(self.copy_stream)
+            self.h2d_bytes += rows * 28
+            return rows
+        pending = {}
+        for k in range(min(2, len(order))):
+            pending[k] = load(k)
+        self.counts.zero_()
+        check(lib.rs_hist(_ptr(self.codes), n, _ptr(self.counts), comp.cuda_stream))
+        if all_reduce is not None:
+            all_reduce(self.counts)
+        self.counts_host.copy_(self.counts, non_blocking=True)
+        comp.synchronize()
+        self.d2h_bytes += 64
+        ts, tq = make_tables(self.counts_host.numpy())
+        tq = _table(tq, 7)
+        ts = None if ts is None else _table(ts, 4)
+        # -- pass 2: scan chunk k while chunk k+1 is in flight
+        for k, c0 in enumerate(order):
+            rows = pending.pop(k)
+            slot = k & 1
+            comp.wait_event(self.loaded[slot])
+            hb = self.hb[k]
+            check(lib.rs_scan_fused(_ptr(self.codes) + c0, _ptr(self.prof[slot]), _lib.RS_F32, rows,
+                                    0 if ts is None else ts.ctypes.data, tq.ctypes.data, W, float(threshold),
+                                    float(absrow_max), mode, hb.capacity, _ptr(hb.pos), _ptr(hb.seq),
+                                    _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes,
+                                    comp.cuda_stream))
+            self.freed[slot].record(comp)
+            if k + 2 < len(order):
+                pending[k + 2] = load(k + 2)
+        comp.synchronize()
+        # -- results back to the host
+        pos_l, seq_l, str_l = [], [], []
+        for k, c0 in enumerate(order):
+            hb = self.hb[k]
+            found = int(hb.counters[0].item())
+            self.d2h_bytes += 16
+            if found > hb.capacity:
+                raise MemoryError("hit buffer of chunk %d overflowed (%d > %d): raise hits_per_row"
+                                  % (k, found, hb.capacity))
+            if found:
+                pos_l.append(hb.pos[:found].cpu().numpy() + c0)
+                str_l.append(hb.struct[:found].cpu().numpy())
+                if ts is not None:
+                    seq_l.append(hb.seq[:found].cpu().numpy())
+                self.d2h_bytes += found * (20 if ts is not None else 16)
+        pos = np.concatenate(pos_l) if pos_l else np.zeros(0, np.int64)
+        st = np.concatenate(str_l) if str_l else np.zeros(0, np.float64)
+        sq = (np.concatenate(seq_l) if seq_l else np.zeros(0, np.float32)) if ts is not None else None
+        return pos, sq, st

@@ -1,0 +1,262 @@
+"""GPU parity: every C-ABI scan entry point against the CPU oracle on the same seeded inputs.
+
+Bit-exact for positions, counts and one-hot scores (integer / sequential-double work);
+the averaged-profile scores are compared bit-exactly too, because the device re-scores
+every reported window in fp64 in the reference's operation order (rnascan.py:302-307).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from rnascan_b200 import device
+    device.require_cuda()
+    return device
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def assert_same_float(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b)
+    assert np.array_equal(_bits(a[~nan_a]), _bits(b[~nan_b]))
+
+
+def make_stream(dev, total, n_records, seed, kind="rna", n_frac=0.01):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(seed)
+    lengths = synth.record_lengths(total, n_records, rng)
+    if kind == "rna":
+        codes, offsets = synth.rna_codes(lengths, rng, n_frac=n_frac)
+    else:
+        codes, offsets = synth.struct_codes(lengths, rng)
+        # sprinkle lower-case (scored, not counted) and unknown symbols
+        k = rng.integers(0, len(codes), size=max(1, len(codes) // 200))
+        keep = codes[k] != 0xFF
+        codes[k[keep]] |= 8
+        k = rng.integers(0, len(codes), size=max(1, len(codes) // 500))
+        keep = codes[k] != 0xFF
+        codes[k[keep]] = 0x0F
+    return dev.SymbolStream(codes, offsets, lengths), codes, lengths
+
+
+def pick_threshold(scores, q):
+    """A threshold given as a quantile of the finite oracle scores ('q0.99'), or a number."""
+    if isinstance(q, str):
+        s = np.asarray(scores, np.float64)
+        s = s[np.isfinite(s) & (s > -1e300)]
+        assert len(s) > 100, "test input has (almost) no finite scores"
+        return float(np.quantile(s, float(q[1:])))
+    return float(q)
+
+
+def window_has_sep(codes, W):
+    sep = (codes == 0xFF).astype(np.int32)
+    c = np.concatenate([[0], np.cumsum(sep)])
+    n = len(codes) - W + 1
+    return (c[W:W + n] - c[:n]) > 0
+
+
+# ----------------------------------------------------------------------------- histogram
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4095, 100003, 3_000_000])
+def test_hist_exact(dev, n):
+    rng = np.random.default_rng(n + 1)
+    codes = rng.choice(np.array([0, 1, 2, 3, 4, 5, 6, 8, 9, 0x0C, 0x0F, 0xFF], np.uint8), size=n)
+    st = dev.SymbolStream(codes)
+    got = dev.histogram(st).cpu().numpy()
+    want = np.array([(codes == k).sum() for k in range(8)], np.int64)
+    assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------- sequence
+@pytest.mark.parametrize("W", [1, 4, 7, 12, 18, 33, 64])
+def test_dense_seq_bit_exact(dev, oracle, W):
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 200_000, 40, seed=W)
+    rng = np.random.default_rng(100 + W)
+    tab = synth.pssm_table(synth.pfm_rows(W, 4, rng), pseudocount=0.01)
+    got = dev.dense_seq(st, tab).cpu().numpy()
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+    assert_same_float(got, want)
+
+
+def test_dense_seq_nonfinite_table(dev, oracle):
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 50_000, 10, seed=5)
+    rng = np.random.default_rng(6)
+    pfm = synth.pfm_rows(9, 4, rng)
+    pfm[pfm < 0.05] = 0.0
+    tab = synth.pssm_table(pfm, pseudocount=0.0)            # holds -inf
+    assert np.isinf(tab).any()
+    got = dev.dense_seq(st, tab).cpu().numpy()
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+    assert_same_float(got, want)
+
+
+@pytest.mark.parametrize("n", [0, 3, 7, 8, 4095, 4096, 4097, 4102, 4103, 8192 + 6])
+def test_scan_seq_tile_edges(dev, oracle, n):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(n)
+    codes = rng.integers(0, 4, size=n).astype(np.uint8)
+    st = dev.SymbolStream(codes)
+    tab = synth.pssm_table(synth.pfm_rows(7, 4, rng))
+    pos, sc = dev.scan_seq(st, tab, 0.0)
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+    wpos = oracle.search_hits(want, 0.0)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+
+
+@pytest.mark.parametrize("thr", [6.0, 0.0, -3.5, float("-inf"), 1e9])
+def test_scan_seq_hits(dev, oracle, thr):
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 1_000_000, 300, seed=2)
+    rng = np.random.default_rng(102)
+    tab = synth.pssm_table(synth.pfm_rows(7, 4, rng))
+    pos, sc = dev.scan_seq(st, tab, thr, capacity=64)       # tiny capacity -> exercises regrow
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+    wpos = oracle.search_hits(want, thr)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+    assert np.all(np.diff(pos) > 0)
+
+
+# ----------------------------------------------------------------------------- structure one-hot
+@pytest.mark.parametrize("W", [1, 7, 18, 64])
+def test_dense_struct_bit_exact(dev, oracle, W):
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 150_000, 30, seed=W, kind="struct")
+    rng = np.random.default_rng(200 + W)
+    tab = synth.pssm_table(synth.pfm_rows(W, 7, rng))
+    got = dev.dense_struct(st, tab).cpu().numpy()
+    want = oracle.alpha_scores(synth.to_text(codes, "struct"), tab, "BEHLMRT")
+    assert_same_float(got, want)
+
+
+@pytest.mark.parametrize("thr", [3.0, float("-inf")])
+def test_scan_struct_hits(dev, oracle, thr):
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 700_000, 200, seed=3, kind="struct")
+    rng = np.random.default_rng(103)
+    tab = synth.pssm_table(synth.pfm_rows(7, 7, rng))
+    pos, sc = dev.scan_struct_onehot(st, tab, thr)
+    want = oracle.alpha_scores(synth.to_text(codes, "struct"), tab, "BEHLMRT")
+    wpos = oracle.search_hits(want, thr)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+
+
+def test_scan_pair_onehot(dev, oracle):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(77)
+    lengths = synth.record_lengths(400_000, 100, rng)
+    ca, off = synth.rna_codes(lengths, rng, n_frac=0.01)
+    cb, _ = synth.struct_codes(lengths, rng)
+    sa, sb = dev.SymbolStream(ca, off, lengths), dev.SymbolStream(cb, off, lengths)
+    ta = synth.pssm_table(synth.pfm_rows(6, 4, rng))
+    tb = synth.pssm_table(synth.pfm_rows(6, 7, rng))
+    a = oracle.seq_scores(synth.to_text(ca, "rna"), ta)
+    b = oracle.alpha_scores(synth.to_text(cb, "struct"), tb, "BEHLMRT")
+    for thr in (0.0, float("-inf")):
+        pos, qa, qb = dev.scan_pair_onehot(sa, sb, ta, tb, thr)
+        with np.errstate(invalid="ignore"):
+            wpos = np.nonzero((a.astype(np.float64) > thr) & (b > thr))[0]
+        assert np.array_equal(pos, wpos)
+        assert_same_float(qa, a[wpos])
+        assert_same_float(qb, b[wpos])
+
+
+# ----------------------------------------------------------------------------- averaged profiles
+def _profile_case(dev, total, n_records, seed, dtype, W, zero_frac=0.0, pseudocount=0.01):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(seed)
+    lengths = synth.record_lengths(total, n_records, rng)
+    codes, off = synth.rna_codes(lengths, rng, n_frac=0.005)
+    rows = synth.profile_rows(len(codes), rng, lengths=lengths)
+    pfm = synth.pfm_rows(W, 7, rng)
+    if zero_frac:
+        # -inf log-odds (zero-probability letters) meet exact zeros in the profile, as in the
+        # reference's example data: 0 * -inf = NaN -> 0, w * -inf -> -DBL_MAX
+        pfm[pfm < zero_frac] = 0.0
+        rows = rows.astype(np.float64)
+        rows[rows < 0.08] = 0.0
+        rows /= np.maximum(rows.sum(axis=1, keepdims=True), 1e-300)
+    rows = rows.astype(np.float32).astype(dtype)
+    tq = synth.pssm_table(pfm, background=[synth.SS_P[c] for c in "BEHLMRT"], pseudocount=pseudocount)
+    ts = synth.pssm_table(synth.pfm_rows(W, 4, rng))
+    return (dev.SymbolStream(codes, off, lengths), dev.ProfileStream(rows), codes, rows, ts, tq)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("W,zero", [(7, 0.0), (18, 0.05), (30, 0.0)])
+def test_dense_profile_bit_exact(dev, oracle, dtype, W, zero):
+    st, pf, codes, rows, ts, tq = _profile_case(dev, 120_000, 25, 11 + W, dtype, W, zero,
+                                                pseudocount=0.0 if zero else 0.01)
+    got = dev.dense_profile(pf, tq, st).cpu().numpy()
+    with np.errstate(all="ignore"):
+        want = oracle.profile_scores(rows, tq)
+    want[window_has_sep(codes, W)] = np.nan
+    assert_same_float(got, want)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("W,zero,thr", [(7, 0.0, "q0.999"), (7, 0.0, "q0.5"), (12, 0.05, "q0.99"),
+                                        (18, 0.0, "q0.9999"), (24, 0.0, "q0.99"), (25, 0.0, "q0.99"),
+                                        (7, 0.0, 6.0), (7, 0.05, float("-inf"))])
+def test_scan_fused_struct_mode(dev, oracle, dtype, W, zero, thr):
+    st, pf, codes, rows, ts, tq = _profile_case(dev, 600_000, 150, 21 + W, dtype, W, zero,
+                                                pseudocount=0.0 if zero else 0.01)
+    with np.errstate(all="ignore"):
+        want = oracle.profile_scores(rows, tq)
+    want[window_has_sep(codes, W)] = np.nan
+    thr = pick_threshold(want, thr)
+    pos, sq, sc, resc = dev.scan_fused(st, pf, None, tq, thr, return_stats=True)
+    wpos = oracle.search_hits(want, thr)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+    assert sq is None
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("W,thr", [(7, 0.0), (7, 1.0), (10, -2.0), (7, float("-inf"))])
+def test_scan_fused_and_mode(dev, oracle, dtype, W, thr):
+    from rnascan_b200 import synth
+    st, pf, codes, rows, ts, tq = _profile_case(dev, 800_000, 200, 31 + W, dtype, W)
+    with np.errstate(all="ignore"):
+        b = oracle.profile_scores(rows, tq)
+    a = oracle.seq_scores(synth.to_text(codes, "rna"), ts)
+    pos, sq, sc = dev.scan_fused(st, pf, ts, tq, thr)
+    with np.errstate(invalid="ignore"):
+        wpos = np.nonzero((a.astype(np.float64) > thr) & (b > thr))[0]
+    assert len(wpos) > 0
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sq, a[wpos])
+    assert_same_float(sc, b[wpos])
+
+
+def test_fused_filter_is_used_and_rare(dev):
+    """The fp32 filter must leave only a small fraction of windows for exact re-scoring."""
+    st, pf, codes, rows, ts, tq = _profile_case(dev, 2_000_000, 500, 99, np.float32, 7)
+    pos, sq, sc, resc = dev.scan_fused(st, pf, ts, tq, 6.0, return_stats=True)
+    assert resc < 0.02 * len(codes)
+
+
+# ----------------------------------------------------------------------------- error behaviour
+def test_bad_arguments(dev):
+    st = dev.SymbolStream(np.zeros(100, np.uint8))
+    with pytest.raises(ValueError):
+        dev.dense_seq(st, np.zeros((7, 5)))
+    with pytest.raises(ValueError):
+        dev.dense_seq(st, np.zeros((65, 4)))
+    with pytest.raises(ValueError):
+        dev.scan_seq(st, np.zeros((7, 4)), float("nan"))
