@@ -96,6 +96,10 @@ class SymbolStream(object):
         codes, offsets, lengths = pack_texts(texts, kind)
         return cls(codes, offsets, lengths, device)
 
+    def host_codes(self):
+        """The encoded symbols as a host uint8 array (the pinned upload buffer)."""
+        return self._host.numpy()[:self.n]
+
     def locate(self, pos):
         """stream position -> (record index, 0-based start within the record)."""
         pos = np.asarray(pos, dtype=np.int64)

@@ -1,0 +1,718 @@
+"""The reference's scan API and CLI (rnascan/rnascan.py) on the B200 kernels.
+
+Same function names, arguments, stderr messages and hits.tab output as the reference; the
+per-window Python loops (Biopython ``search`` -> ``_pwm.calculate``, ``_py_calculate``, the
+pandas double loop of ``scan_averaged_structure``) and the ``multiprocessing.Pool`` fan-out
+are replaced by one kernel launch over ALL records of a file: records are packed into a
+single symbol stream (include/rnascan_b200.h), scanned in one pass, and the ordered hit list
+is mapped back to (record, start) on the host.  Each function cites the reference lines it
+mirrors.  There is no CPU fallback: without the CUDA library / a device the scans raise.
+
+Result frames reproduce the reference's dtypes (float32 sequence scores rounded in float32,
+Python-float structure scores, object columns when a record has no hit, ...) because the
+TSV text written by ``to_csv`` depends on them.
+"""
+from __future__ import print_function
+
+import argparse
+import ast
+import glob
+import os
+import os.path
+import re
+import sys
+import time
+import warnings
+from collections import defaultdict
+
+import numpy as np
+import pandas as pd
+
+from . import motifs
+from . import seq as _seq
+from .BioAddons.Alphabet import ContextualSecondaryStructure
+from .BioAddons.motifs import matrix
+from .seq import IUPAC, RNAAlphabet, Seq, SeqRecord  # noqa: F401  (re-exported names)
+from .version import __version__
+
+HIT_COLUMNS = ["Motif_ID", "Start", "End", "Sequence", "LogOdds"]
+MAX_BATCH_SYMBOLS = 1 << 30          # symbols per device batch when scanning a FASTA file
+
+
+def getoptions(argv=None):
+    """argparse definition of rnascan.py:44-105 (same flags, defaults and checks)."""
+    desc = "Scan sequence for motif binding sites. Results sent to STDOUT."
+    parser = argparse.ArgumentParser(description=desc)
+    parser.add_argument("fastafiles", metavar="FASTA", nargs="*",
+                        help="Input sequence and structure FASTA files")
+    pfm_grp = parser.add_argument_group("PFM options")
+    pfm_grp.add_argument("-p", "--pfm_seq", dest="pfm_seq", type=str, help="Sequence PFM")
+    pfm_grp.add_argument("-q", "--pfm_struct", dest="pfm_struct", type=str, help="Structure PFM")
+    parser.add_argument("-C", "--pseudocount", type=float, dest="pseudocount", default=0,
+                        help="Pseudocount for normalizing PFM. [%(default)s]")
+    parser.add_argument("-m", "--minscore", type=float, dest="minscore", default=6,
+                        help="Minimum score for motif hits. [%(default)s]")
+    parser.add_argument("-t", "--testseq", dest="testseq", default=None,
+                        help=("Supply a test sequence to scan. FASTA files will be ignored. Can "
+                              "supply sequence and structure as single string separated by  comma."))
+    parser.add_argument("-c", "--cores", type=int, default=8, dest="cores",
+                        help="Accepted for compatibility; the scan runs on the GPU and the result "
+                             "does not depend on it [%(default)s]")
+    bg_grp = parser.add_argument_group("Background frequency options")
+    bg_grp.add_argument("-u", "--uniformbg", action="store_true", default=False,
+                        dest="uniform_background",
+                        help=("Use uniform background for calculating log-odds [%(default)s]. "
+                              "Default is to compute background from input sequences. This option "
+                              "is mutually exclusive with -B."))
+    bg_grp.add_argument("-g", "--bgonly", action="store_true", default=False, dest="bgonly",
+                        help=("Compute background probabilities from input sequences (STDOUT) and "
+                              "exit. Useful for getting background probabilities from a superset of "
+                              "sequences. Then, these values can be subsequently supplied using -b. "
+                              "[%(default)s]"))
+    bg_grp.add_argument("-b", "--bg_seq", default=None, dest="bg_seq",
+                        help="Load file of pre-computed background probabilities for nucleotide sequences")
+    bg_grp.add_argument("-B", "--bg_struct", default=None, dest="bg_struct",
+                        help="Load file of pre-computed background probabilities for structure contexts")
+    parser.add_argument("-v", "--version", action="version", version="%(prog)s " + __version__)
+    parser.add_argument("-x", "--debug", action="store_true", default=False, dest="debug",
+                        help="Reference debug mode (no process pool there; here it only changes the "
+                             "Sequence_ID of averaged-structure hits as in the reference) [%(default)s]")
+    args = parser.parse_args(argv)
+    if not (args.pfm_seq or args.pfm_struct):
+        parser.error("Must specify PFMs with -p and/or -q")
+    if args.uniform_background and (args.bg_seq or args.bg_struct):
+        parser.error("You cannot set uniform and custom background options at the same time\n")
+    return args
+
+
+def eprint(*args, **kwargs):
+    print(*args, file=sys.stderr, **kwargs)
+
+
+###############################################################################
+# Sequence functions
+###############################################################################
+def _guess_seq_type(args):
+    """RNA, SS or RNASS from the number of inputs and PFMs (rnascan.py:114-137)."""
+    if len(args.fastafiles) == 2:
+        if not (args.pfm_seq or args.pfm_struct):
+            eprint("Missing PFMs")
+            sys.exit(1)
+        return "RNASS"
+    if args.pfm_seq and args.pfm_struct and not args.testseq:
+        eprint("Can't specify two PFMs with one input file")
+        sys.exit(1)
+    if args.pfm_seq and args.pfm_struct and args.testseq:
+        return "RNASS"
+    if args.pfm_seq:
+        return "RNA"
+    if args.pfm_struct:
+        return "SS"
+    eprint("Must specify PFMs with -p and/or -q")
+    sys.exit(1)
+
+
+def batch_iterator(iterator, batch_size):
+    """Lists of up to `batch_size` entries of `iterator` (rnascan.py:140-167); a None entry
+    ends the iteration like exhaustion does."""
+    iterator = iter(iterator)
+    done = False
+    while not done:
+        batch = []
+        while len(batch) < batch_size:
+            entry = next(iterator, None)
+            if entry is None:
+                done = True
+                break
+            batch.append(entry)
+        if batch:
+            yield batch
+
+
+def parse_sequences(fasta_file):
+    """SeqRecord iterator over one FASTA path or a list of paths; .gz/.bz2 transparently
+    (rnascan.py:170-174)."""
+    return _seq.parse_fasta(fasta_file)
+
+
+def preprocess_seq(seqrec, alphabet):
+    """RNA target alphabet + non-RNA input -> transcribe (T->U, t->u) and upper-case;
+    anything else passes through (rnascan.py:177-204).  Returns a Seq."""
+    if not _seq.is_seqrecord(seqrec):
+        raise TypeError("SeqRecord object must be supplied")
+    if _seq.is_ambiguous_rna_alphabet(alphabet) and not _seq.is_rna_alphabet(seqrec.seq.alphabet):
+        out = seqrec.seq.transcribe()
+        out.alphabet = alphabet
+        return out.upper()
+    return seqrec.seq
+
+
+###############################################################################
+# PFM functions
+###############################################################################
+def load_motif(pfm_file, *args):
+    """{motif_id: PSSM} for one PFM file; motif_id = file name without extension
+    (rnascan.py:210-235, messages included)."""
+    motifs_set = {}
+    eprint("Loading PFM %s" % pfm_file, end="")
+    tic = time.time()
+    try:
+        motif_id = os.path.splitext(os.path.basename(pfm_file))[0]
+        motifs_set[motif_id] = pfm2pssm(pfm_file, *args)
+    except ValueError:
+        eprint("\nFailed to load motif %s" % pfm_file)
+    except KeyError:
+        eprint("\nFailed to load motif %s" % pfm_file)
+        eprint("Check that you are using the correct --type")
+        raise
+    except Exception:
+        eprint("Unexpected error: %s" % sys.exc_info()[0])
+        raise
+    eprint("\b.", end="")
+    sys.stderr.flush()
+    eprint("done in %0.2f seconds!" % (float(time.time() - tic)))
+    eprint("Found %d motifs" % len(motifs_set))
+    if len(motifs_set) == 0:
+        raise ValueError("No motifs found.")
+    return motifs_set
+
+
+def pfm2pssm(pfm_file, pseudocount, alphabet, background=None):
+    """PFM file -> normalize(pseudocount) -> log_odds(background) -> PSSM
+    (rnascan.py:238-252).  The first column is dropped; header letters may come in any order."""
+    table = pd.read_csv(pfm_file, sep="\t")
+    counts = table.drop(columns=table.columns[0]).to_dict(orient="list")
+    values = motifs.Motif(alphabet=alphabet, counts=counts).pssm(pseudocount, background)
+    return matrix.ExtendedPositionSpecificScoringMatrix(alphabet, values)
+
+
+###############################################################################
+# Packed record batches (host side of the device layout)
+###############################################################################
+class _Batch(object):
+    """Records of one input packed into a symbol stream resident in HBM."""
+
+    def __init__(self, ids, descriptions, texts, kind):
+        from . import device
+        self.ids, self.descriptions, self.texts, self.kind = ids, descriptions, texts, kind
+        self.stream = device.SymbolStream.from_texts(texts, kind)
+        self._raw = None
+
+    def __len__(self):
+        return len(self.texts)
+
+    def raw(self):
+        """The record texts joined by newlines as a uint8 array: byte i is the letter of
+        stream position i (used to cut hit fragments without a Python loop)."""
+        if self._raw is None:
+            joined = ("\n".join(self.texts) + "\n") if self.texts else ""
+            self._raw = np.frombuffer(joined.encode("latin-1", "replace"), dtype=np.uint8)
+        return self._raw
+
+
+def _kind_of(alphabet):
+    return "rna" if _seq.is_nucleotide_alphabet(alphabet) else "struct"
+
+
+def _record_batches(fasta_file, alphabet, max_symbols=None):
+    """Parse + preprocess a FASTA input and yield _Batch objects of bounded size."""
+    max_symbols = max_symbols or MAX_BATCH_SYMBOLS
+    ids, descs, texts, size = [], [], [], 0
+    for rec in parse_sequences(fasta_file):
+        text = str(preprocess_seq(rec, alphabet))
+        if texts and size + len(text) + 1 > max_symbols:
+            yield _Batch(ids, descs, texts, _kind_of(alphabet))
+            ids, descs, texts, size = [], [], [], 0
+        ids.append(rec.id)
+        descs.append(rec.description)
+        texts.append(text)
+        size += len(text) + 1
+    if texts:
+        yield _Batch(ids, descs, texts, _kind_of(alphabet))
+
+
+def _table_for(pm, kind):
+    from . import device
+    return pm.table(device.RNA_COLUMNS if kind == "rna" else device.CHANNELS)
+
+
+def _first_motif(pssm):
+    return list(pssm.items())[0]
+
+
+def _fragments(raw, pos, width):
+    """Python str of the `width` letters starting at each stream position."""
+    if len(pos) == 0:
+        return []
+    windows = np.lib.stride_tricks.sliding_window_view(raw, width)[pos]
+    return np.ascontiguousarray(windows).view("S%d" % width).ravel().astype("U%d" % width).tolist()
+
+
+def _round3_f32(scores):
+    """round(numpy.float32, 3) elementwise: float32 arithmetic, as rnascan.py:273 gets it."""
+    return np.round(np.asarray(scores, dtype=np.float32), 3)
+
+
+def _round3_f64(scores):
+    """round(float, 3) elementwise with Python's exact decimal rounding."""
+    return [round(v, 3) for v in np.asarray(scores, dtype=np.float64).tolist()]
+
+
+###############################################################################
+# Motif scan functions
+###############################################################################
+def scan(pssm, seq, alphabet, minscore):
+    """[motif_id, Start (1-based), End, fragment, round(score, 3)] for every window of `seq`
+    whose score is > minscore (rnascan.py:258-275)."""
+    motif_id, pm = _first_motif(pssm)
+    width = len(pm.consensus)
+    results = []
+    for position, score in pm.search(seq, threshold=minscore, both=False):
+        end_position = position + width
+        results.append([motif_id, position + 1, end_position, str(seq[position:end_position]),
+                        round(score, 3)])
+    return results
+
+
+def scan_all(seqrecord, pssm, alphabet, *args):
+    """DataFrame of the hits of one record (rnascan.py:278-286)."""
+    sequence = preprocess_seq(seqrecord, alphabet)
+    final = pd.DataFrame(scan(pssm, sequence, alphabet, *args), columns=HIT_COLUMNS)
+    return final.sort_values(["Start", "Motif_ID"])
+
+
+def _scan_all(a_b):
+    return scan_all(*a_b)
+
+
+def _read_profile(struct_file):
+    """(L, 7) float64 rows in B,E,H,L,M,R,T order from a ``structure.<id>.txt`` profile
+    (pfmutil.format_pfm layout).  Channels are matched BY LABEL."""
+    from . import device
+    table = pd.read_csv(struct_file, sep="\t")
+    del table["PO"]
+    return np.ascontiguousarray(table[list(device.CHANNELS)].to_numpy(dtype=np.float64))
+
+
+def _averaged_frame(motif_id, starts, width, scores):
+    """Frame built the way pd.DataFrame(list of Series) builds it in the reference
+    (rnascan.py:311-315): object columns; no columns at all when there is no hit."""
+    if len(starts) == 0:
+        return pd.DataFrame([])
+    starts = np.asarray(starts, dtype=np.int64)
+    data = {
+        "Motif_ID": np.array([motif_id] * len(starts), dtype=object),
+        "Start": (starts + 1).astype(object),
+        "End": (starts + width).astype(object),
+        "Sequence": np.array(["."] * len(starts), dtype=object),
+        "LogOdds": np.asarray(scores, dtype=np.float64).astype(object),
+    }
+    return pd.DataFrame(data, columns=HIT_COLUMNS)
+
+
+def scan_averaged_structure(struct_file, pssm, minscore):
+    """Hits of a structure PSSM on one averaged 7-channel profile (rnascan.py:293-315):
+    score_i = sum_j nan_to_num(dot(profile[i+j], pssm[j])) in float64, unrounded, > minscore."""
+    from . import device
+    motif_id, pm = _first_motif(pssm)
+    rows = _read_profile(struct_file)
+    tq = _structure_table(pm)
+    width = tq.shape[0]
+    if rows.shape[0] < width:
+        return pd.DataFrame([])
+    profile = device.ProfileStream(rows)
+    stream = device.SymbolStream(np.zeros(rows.shape[0], np.uint8))
+    pos, _, scores = device.scan_fused(stream, profile, None, tq, minscore)
+    return _averaged_frame(motif_id, pos, width, scores)
+
+
+def _scan_averaged_structure(a_b):
+    return scan_averaged_structure(*a_b)
+
+
+def _structure_table(pm):
+    """(W, 7) table in device channel order from a PSSM object or a plain {letter: values}."""
+    from . import device
+    return np.array([list(pm[c]) for c in device.CHANNELS], dtype=np.float64).T.copy()
+
+
+def _add_sequence_id(df, seq_id, description):
+    df["Sequence_ID"] = seq_id
+    df["Description"] = description
+
+
+def _add_match_id(df):
+    df["Match_ID"] = list(range(1, df.shape[0] + 1))
+
+
+def _assemble_fasta_frame(n_records, rec, ids, descriptions, motif_id, start0, width, fragments,
+                          logodds):
+    """The frame pd.concat() of the reference's per-record frames would give
+    (rnascan.py:284-286,401-408): typed columns when every record has a hit, object columns
+    (Python ints / Python floats widened from the column dtype) as soon as one record has
+    none, because an empty per-record frame has object columns."""
+    n = len(rec)
+    rec = np.asarray(rec, dtype=np.int64)
+    per_record = np.bincount(rec, minlength=n_records) if n_records else np.zeros(0, np.int64)
+    any_empty = bool((per_record == 0).any())
+    start = np.asarray(start0, dtype=np.int64) + 1
+    end = np.asarray(start0, dtype=np.int64) + width
+    ids_arr = np.array(ids, dtype=object)[rec] if n else np.array([], dtype=object)
+    desc_arr = np.array(descriptions, dtype=object)[rec] if n else np.array([], dtype=object)
+    first = np.concatenate([[0], np.cumsum(per_record)[:-1]]) if n_records else np.zeros(0, np.int64)
+    index = np.arange(n, dtype=np.int64) - first[rec] if n else np.zeros(0, np.int64)
+    if any_empty:
+        start, end = start.astype(object), end.astype(object)
+        logodds = np.asarray(logodds).astype(object) if not isinstance(logodds, list) \
+            else np.array(logodds, dtype=object)
+    elif isinstance(logodds, list):
+        logodds = np.array(logodds, dtype=np.float64)
+    frame = pd.DataFrame({
+        "Sequence_ID": ids_arr, "Description": desc_arr,
+        "Motif_ID": np.array([motif_id] * n, dtype=object),
+        "Start": start, "End": end,
+        "Sequence": np.array(fragments, dtype=object) if n else np.array([], dtype=object),
+        "LogOdds": logodds,
+    }, index=index)
+    return frame
+
+
+def _scan_batch(batch, pm, kind, minscore):
+    """(record index, 0-based start, scores) of all hits in a packed batch."""
+    from . import device
+    table = _table_for(pm, kind)
+    if kind == "rna":
+        pos, scores = device.scan_seq(batch.stream, table, minscore)
+    else:
+        pos, scores = device.scan_struct_onehot(batch.stream, table, minscore)
+    rec, start0 = batch.stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    return pos, rec, start0, scores
+
+
+def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
+    """All records of a FASTA input in one (or a few) kernel launches; returns the assembled
+    frame and the number of records.  `restrict(batch_index, batch, pos)` may drop hits."""
+    motif_id, pm = _first_motif(pssm)
+    kind = _kind_of(alphabet)
+    if kind == "struct" and not pm._is_structure():
+        raise NotImplementedError("GPU scoring supports the nucleotide and BEHLMRT structure alphabets")
+    width = pm.length
+    parts, n_records = [], 0
+    for b, batch in enumerate(_cached_batches(fasta_file, alphabet)):
+        pos, rec, start0, scores = _scan_batch(batch, pm, kind, minscore)
+        if restrict is not None:
+            keep = restrict(b, batch, pos)
+            pos, rec, start0, scores = pos[keep], rec[keep], start0[keep], scores[keep]
+        parts.append((rec + n_records, start0, scores, _fragments(batch.raw(), pos, width),
+                      batch.ids, batch.descriptions))
+        n_records += len(batch)
+    if n_records == 0:
+        return pd.DataFrame(), 0
+    rec = np.concatenate([p[0] for p in parts])
+    start0 = np.concatenate([p[1] for p in parts])
+    scores = np.concatenate([p[2] for p in parts])
+    fragments = [f for p in parts for f in p[3]]
+    ids = [i for p in parts for i in p[4]]
+    descs = [d for p in parts for d in p[5]]
+    logodds = _round3_f32(scores) if kind == "rna" else _round3_f64(scores)
+    return _assemble_fasta_frame(n_records, rec, ids, descs, motif_id, start0, width, fragments,
+                                 logodds), n_records
+
+
+# one parsed + uploaded input is reused by compute_background and the scan that follows it
+_BATCH_CACHE = {}
+
+
+def _cache_key(fasta_file, alphabet):
+    paths = [fasta_file] if isinstance(fasta_file, str) else list(fasta_file)
+    try:
+        stamp = tuple((os.path.abspath(p), os.path.getmtime(p), os.path.getsize(p)) for p in paths)
+    except OSError:
+        return None
+    return (stamp, _kind_of(alphabet), _seq.is_ambiguous_rna_alphabet(alphabet))
+
+
+def _cached_batches(fasta_file, alphabet):
+    key = _cache_key(fasta_file, alphabet)
+    if key is not None and key in _BATCH_CACHE:
+        return _BATCH_CACHE[key]
+    batches = list(_record_batches(fasta_file, alphabet))
+    if key is not None:
+        _BATCH_CACHE.clear()
+        if sum(b.stream.n for b in batches) <= MAX_BATCH_SYMBOLS:
+            _BATCH_CACHE[key] = batches
+    return batches
+
+
+def _profile_files(directory):
+    structures = glob.glob(directory + "/structure.*.txt")
+    if len(structures) == 0:
+        raise IOError("No averaged structure files found")
+    return structures
+
+
+def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None):
+    """All ``structure.<id>.txt`` profiles of a directory in one launch (rnascan.py:348-375).
+    With `seq_batches`/`seq_pm` (combined mode) the sequence PSSM is evaluated in the same
+    kernel and only windows passing BOTH thresholds come back."""
+    from . import device
+    motif_id, pm = _first_motif(pssm)
+    tq = _structure_table(pm)
+    width = tq.shape[0]
+    files = _profile_files(directory)
+    names = []
+    for path in files:
+        match = re.search(r"^structure\.(.*)\.txt$", os.path.basename(path))
+        names.append(path if debug else match.group(1))
+    profiles = [_read_profile(path) for path in files]
+    lengths = np.array([p.shape[0] for p in profiles], dtype=np.int64)
+    offsets = np.zeros(len(profiles), np.int64)
+    if len(profiles) > 1:
+        np.cumsum(lengths[:-1] + 1, out=offsets[1:])
+    codes = np.zeros(int(lengths.sum() + len(profiles)), np.uint8)
+    seq_table = None
+    if seq_batches is not None:
+        # sequence symbols of the record with the same id, aligned row by row
+        by_id = {}
+        for batch in seq_batches:
+            host = batch.stream.host_codes()
+            for k, rid in enumerate(batch.ids):
+                by_id.setdefault(rid, host[batch.stream.offsets[k]:batch.stream.offsets[k] + batch.stream.lengths[k]])
+        seq_table = _table_for(seq_pm, "rna")
+        for k, name in enumerate(names):
+            sym = by_id.get(name)
+            if sym is None or len(sym) != lengths[k]:
+                codes[offsets[k]:offsets[k] + lengths[k]] = device._lib.RS_RNA_OTHER   # no joint hit possible
+            else:
+                codes[offsets[k]:offsets[k] + lengths[k]] = sym
+    codes[offsets + lengths] = device._lib.RS_SEP
+    stream = device.SymbolStream(codes, offsets, lengths)
+    profile = device.ProfileStream(device.pack_profiles(profiles, dtype=np.float64))
+    pos, _, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
+    rec, start0 = stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    n = len(pos)
+    frame = pd.DataFrame({
+        "Sequence_ID": np.array(names, dtype=object)[rec] if n else np.array([], dtype=object),
+        "Description": np.array([""] * n, dtype=object),
+        "Motif_ID": np.array([motif_id] * n, dtype=object),
+        "Start": (start0 + 1).astype(object), "End": (start0 + width).astype(object),
+        "Sequence": np.array(["."] * n, dtype=object),
+        "LogOdds": np.asarray(scores, dtype=np.float64).astype(object),
+    })
+    return frame, len(files)
+
+
+def scan_main(fasta_file, pssm, alphabet, bg, args):
+    """Scan one input -- a SeqRecord, a directory of averaged profiles or a FASTA file -- and
+    return the hit frame with Sequence_ID and Description in front (rnascan.py:335-413)."""
+    count = 0
+    if _seq.is_seqrecord(fasta_file):
+        final = scan_all(fasta_file, pssm, alphabet, args.minscore)
+        _add_sequence_id(final, "testseq", "")
+        count += 1
+        cols = final.columns.tolist()
+        final = final[cols[-2:] + cols[:-2]]
+    elif os.path.isdir(fasta_file):
+        eprint("Scanning averaged secondary structures ")
+        final, count = _scan_profile_dir(fasta_file, pssm, args.minscore, args.debug)
+    else:
+        eprint("Scanning sequences ")
+        final, count = _scan_fasta(fasta_file, pssm, alphabet, args.minscore)
+    eprint("Processed %d sequences" % count)
+    return final
+
+
+def combine(seq_results, struct_results):
+    """Inner join of the two hit sets on Sequence_ID, Start, End; the combined score is the
+    sum of the two (rnascan.py:416-434).  A hit exists only where BOTH scans reported one."""
+    keys = ["Sequence_ID", "Start", "End"]
+    left, right = seq_results, struct_results
+    for key in keys[1:]:                     # pandas >= 2 refuses int64-vs-object merge keys
+        if key in left and key in right and left[key].dtype != right[key].dtype:
+            left, right = left.copy(), right.copy()
+            left[key], right[key] = left[key].astype(object), right[key].astype(object)
+    result = pd.merge(left, right, on=keys)
+    result.rename(columns={"Description_x": "Description.Seq", "Description_y": "Description.Struct",
+                           "Sequence_x": "Sequence.Seq", "Sequence_y": "Sequence.Struct",
+                           "Motif_ID_x": "Motif_ID.Seq", "Motif_ID_y": "Motif_ID.Struct",
+                           "LogOdds_x": "LogOdds.Seq", "LogOdds_y": "LogOdds.Struct"}, inplace=True)
+    result["LogOdds.SeqStruct"] = result["LogOdds.Seq"] + result["LogOdds.Struct"]
+    return result
+
+
+###############################################################################
+# Background functions
+###############################################################################
+def compute_background(fastas, alphabet, verbose=True):
+    """p(letter) = (count + 1) / (sum(counts) + |alphabet|) over all records, counted on the
+    device (exact integers), keys in ``alphabet.letters`` order (rnascan.py:440-465).
+    Counting is case-sensitive on the pre-processed sequence: lower-case structure letters
+    are scored but not counted."""
+    from . import device
+    eprint("Calculating background probabilities...")
+    kind = _kind_of(alphabet)
+    columns = device.RNA_COLUMNS if kind == "rna" else device.CHANNELS
+    if any(letter not in columns for letter in alphabet.letters):
+        raise NotImplementedError("GPU background counting supports GAUC and EHTBLRM alphabets")
+    counts = np.zeros(8, dtype=np.int64)
+    n_records = 0
+    for batch in _cached_batches(fastas, alphabet):
+        counts += device.histogram(batch.stream).cpu().numpy()
+        n_records += len(batch)
+    counts = _allreduce_counts(counts)
+    content = defaultdict(int)
+    total = len(alphabet.letters)
+    if n_records:
+        for letter in alphabet.letters:
+            amount = int(counts[columns.index(letter)])
+            content[letter] += amount
+            total += amount
+    pct_sum = 0
+    for letter, count in content.items():
+        content[letter] = (float(count) + 1) / total
+        if content[letter] <= 0.05:
+            warnings.warn("Letter %s has low content: %0.2f" % (letter, content[letter]), Warning)
+        pct_sum += content[letter]
+    if verbose:
+        eprint(dict(content))
+    assert abs(1.0 - pct_sum) < 0.0001, "Background sums to %f" % pct_sum
+    return content
+
+
+def _allreduce_counts(counts):
+    """Sum the integer background counts over all ranks when running under torchrun (the
+    path's only collective); identity in a single process."""
+    from . import shard
+    return shard.allreduce_counts(counts)
+
+
+def load_background(bg_file, uniform, *args):
+    """Dict-literal background file, else computed from the input, else None = uniform
+    (rnascan.py:468-484)."""
+    if bg_file:
+        eprint("Reading custom background probabilities from %s" % bg_file)
+        with open(bg_file, "r") as fin:
+            bg = ast.literal_eval(fin.read())
+            eprint(dict(bg))
+    elif not uniform:
+        bg = compute_background(*args)
+    else:
+        bg = None
+    return bg
+
+
+###############################################################################
+# Main
+###############################################################################
+def _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, args):
+    """Structure side of the combined mode, restricted on the device to windows whose
+    SEQUENCE score also passes (the inner join of rnascan.py:422 keeps nothing else).
+    Returns None when the restriction cannot be applied (then the caller scans the structure
+    input on its own)."""
+    from . import device
+    _, seq_pm = _first_motif(seq_pssm)
+    motif_id, pm = _first_motif(struct_pssm)
+    if seq_pm.length != pm.length:
+        return None
+    rna = IUPAC.IUPACUnambiguousRNA()
+    seq_batches = _cached_batches(seq_file, rna)
+    ids = [i for b in seq_batches for i in b.ids]
+    if len(set(ids)) != len(ids):
+        return None                       # duplicate ids join across records: keep the plain path
+    if os.path.isdir(struct_file):
+        eprint("Scanning averaged secondary structures ")
+        frame, count = _scan_profile_dir(struct_file, struct_pssm, args.minscore, args.debug,
+                                         seq_batches=seq_batches, seq_pm=seq_pm)
+        eprint("Processed %d sequences" % count)
+        return frame
+    alphabet = ContextualSecondaryStructure()
+    struct_batches = _cached_batches(struct_file, alphabet)
+    if len(struct_batches) != len(seq_batches) or any(
+            a.ids != b.ids or not np.array_equal(a.stream.lengths, b.stream.lengths)
+            for a, b in zip(seq_batches, struct_batches)):
+        return None
+    eprint("Scanning sequences ")
+    ts, tq = _table_for(seq_pm, "rna"), _table_for(pm, "struct")
+    width = pm.length
+    parts, n_records = [], 0
+    for sb, qb in zip(seq_batches, struct_batches):
+        pos, _, scores = device.scan_pair_onehot(sb.stream, qb.stream, ts, tq, args.minscore)
+        rec, start0 = qb.stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+        parts.append((rec + n_records, start0, scores, _fragments(qb.raw(), pos, width)))
+        n_records += len(qb)
+    eprint("Processed %d sequences" % n_records)
+    if n_records == 0:
+        return pd.DataFrame()
+    rec = np.concatenate([p[0] for p in parts])
+    ids = [i for b in struct_batches for i in b.ids]
+    descs = [d for b in struct_batches for d in b.descriptions]
+    frame = _assemble_fasta_frame(n_records, rec, ids, descs, motif_id,
+                                  np.concatenate([p[1] for p in parts]), width,
+                                  [f for p in parts for f in p[3]],
+                                  _round3_f64(np.concatenate([p[2] for p in parts])))
+    return frame
+
+
+def main(argv=None):
+    tic = time.time()
+    args = getoptions(argv)
+    seq_type = _guess_seq_type(args)
+    bg = None
+    seq_file = struct_file = None
+    seq_pssm = None
+
+    if args.testseq:
+        testseq_stack = args.testseq.split(",")[::-1]
+
+    if seq_type in ["RNA", "RNASS"]:
+        rna = IUPAC.IUPACUnambiguousRNA()
+        if args.testseq:
+            seq_file = SeqRecord(Seq(testseq_stack.pop()))
+        else:
+            seq_file = args.fastafiles[0]
+            bg = load_background(args.bg_seq, args.uniform_background, seq_file, rna, not args.bgonly)
+        if args.bgonly:
+            print(dict(bg))
+            sys.exit()
+        seq_pssm = load_motif(args.pfm_seq, args.pseudocount, rna, bg)
+        seq_results = scan_main(seq_file, seq_pssm, rna, bg, args)
+
+    if seq_type in ["SS", "RNASS"]:
+        structure = ContextualSecondaryStructure()
+        if args.testseq:
+            struct_file = SeqRecord(Seq(testseq_stack.pop()))
+        elif seq_type == "SS":
+            struct_file = args.fastafiles[0]
+        else:
+            struct_file = args.fastafiles[1]
+        if not args.testseq:
+            bg = load_background(args.bg_struct, args.uniform_background, struct_file, structure,
+                                 not args.bgonly)
+        if args.bgonly:
+            print(dict(bg))
+            sys.exit()
+        struct_pssm = load_motif(args.pfm_struct, args.pseudocount, structure, bg)
+        struct_results = None
+        if seq_type == "RNASS" and not args.testseq:
+            struct_results = _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, args)
+        if struct_results is None:
+            struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
+
+    if seq_type == "RNASS":
+        final = combine(seq_results, struct_results)
+    elif seq_type == "RNA":
+        final = seq_results
+    else:
+        final = struct_results
+    _add_match_id(final)
+    final.to_csv(sys.stdout, sep="\t", index=False)
+
+    runtime = float(time.time() - tic)
+    if runtime > 60:
+        eprint("Done in %0.4f minutes!" % (runtime / 60))
+    else:
+        eprint("Done in %0.4f seconds!" % (runtime))
+
+
+if __name__ == "__main__":
+    main()
