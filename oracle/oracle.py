@@ -110,18 +110,22 @@ def profile_scores(profile, table):
     assert M.shape[1] == C
     out = np.empty(max(0, L_ - N + 1), dtype=np.float64)
     if P.dtype == np.float32:
-        lib().orc_profile_scores_f32(P.ctypes.data, L_, M.ctypes.data, N, C, out.ctypes.data)
+        rc = lib().orc_profile_scores_f32(P.ctypes.data, L_, M.ctypes.data, N, C, out.ctypes.data)
     else:
-        P = P.astype(np.float64, copy=False)
-        lib().orc_profile_scores(P.ctypes.data, L_, M.ctypes.data, N, C, out.ctypes.data)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        rc = lib().orc_profile_scores(P.ctypes.data, L_, M.ctypes.data, N, C, out.ctypes.data)
+    if rc < 0:
+        raise ValueError("profile_scores: exactly 7 channels are supported")
     return out
 
 
 def profile_scores_py(profile, table):
     """Pure-numpy-per-window restatement of rnascan.py:302-307 for tiny inputs; used to
-    check the C loop (np.dot here goes through the same BLAS ddot the reference uses)."""
-    P = np.asarray(profile, dtype=np.float64)
-    M = np.asarray(table, dtype=np.float64)
+    check the C loop.  The reference's operands are rows of single-block pandas frames =
+    STRIDED views, which sends np.dot to BLAS ddot's non-unit-stride loop; Fortran-ordered
+    arrays reproduce that here."""
+    P = np.asfortranarray(np.asarray(profile, dtype=np.float64))
+    M = np.asfortranarray(np.asarray(table, dtype=np.float64))
     N = M.shape[0]
     out = []
     for i in range(0, P.shape[0] - N + 1):

@@ -79,17 +79,33 @@ __device__ __forceinline__ double rs_nan_to_num(double d)
 }
 
 // One window of the averaged-profile score, exactly rnascan.py:302-307:
-//   sum_j nan_to_num( sum_c p[i+j][c] * m[j][c] ), separate multiply and add, c then j.
+//   sum_j nan_to_num( np.dot(profile row i+j, pssm row j) ).
+// Both operands of that np.dot are strided pandas row views, so it runs OpenBLAS ddot's
+// non-unit-stride loop; for 7 channels its compiled arithmetic is (oracle/pwm_oracle.c
+// documents how this was established and pinned against the reference's own outputs):
+//   m3 = x2*y2; m4 = x3*y3; t1 = fma(x0,y0,m3); t2 = fma(x1,y1,m4);
+//   t1 = fma(x4,y4,t1); t1 = fma(x5,y5,t1); t1 = fma(x6,y6,t1); dot = t1 + t2
+__device__ __forceinline__ double rs_ddot7(double x0, double x1, double x2, double x3, double x4, double x5,
+                                           double x6, const double *y)
+{
+    const double m3 = __dmul_rn(x2, y[2]), m4 = __dmul_rn(x3, y[3]);
+    double t1 = __fma_rn(x0, y[0], m3);
+    const double t2 = __fma_rn(x1, y[1], m4);
+    t1 = __fma_rn(x4, y[4], t1);
+    t1 = __fma_rn(x5, y[5], t1);
+    t1 = __fma_rn(x6, y[6], t1);
+    return __dadd_rn(t1, t2);
+}
+
 template <typename PT>
 __device__ __forceinline__ double rs_exact_profile_window(const PT *rows /* first row of window */,
                                                           const double *tab /* [W][7] */, int W)
 {
     double score = 0.0;
     for (int j = 0; j < W; j++) {
-        double d = 0.0;
-#pragma unroll
-        for (int c = 0; c < RS_CHANNELS; c++)
-            d = __dadd_rn(d, __dmul_rn((double)rows[j * RS_CHANNELS + c], tab[j * RS_CHANNELS + c]));
+        const PT *r = rows + j * RS_CHANNELS;
+        const double d = rs_ddot7((double)r[0], (double)r[1], (double)r[2], (double)r[3], (double)r[4],
+                                  (double)r[5], (double)r[6], tab + j * RS_CHANNELS);
         score = __dadd_rn(score, rs_nan_to_num(d));
     }
     return score;

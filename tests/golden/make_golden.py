@@ -292,7 +292,38 @@ def api_vectors():
     buf = io.StringIO()
     comb.to_csv(buf, sep="\t", index=False)
     A["combine_example_aligned_tsv"] = buf.getvalue()
+    A["pfmutil"] = pfmutil_vectors()
     return A
+
+
+def pfmutil_vectors():
+    """Outputs of the reference's rnascan/pfmutil.py (pure Python, imported as is)."""
+    import tempfile
+    from rnascan import pfmutil as pu
+    V = {}
+    struct = pu.read_pfm(P("SLBP_pfm_assembled_normalized_struct.txt"))
+    seq = pu.read_pfm(P("test_seq_pfm.txt"))
+    V["read_struct"] = struct
+    V["format_struct"] = pu.format_pfm(struct)
+    V["format_seq"] = pu.format_pfm(seq)
+    V["norm_seq"] = pu.norm_pfm(seq)
+    V["is_normalized"] = [pu.is_normalized(seq), pu.is_normalized(pu.norm_pfm(seq)),
+                          pu.is_normalized(struct)]
+    V["from_IUPAC"] = pu.pfm_from_IUPAC("ACGURYSWKMBDHVN")
+    V["from_string"] = pu.pfm_from_string("EHLLRT", pu.FULL_STRUCT_ALPHABET)
+    pwm = pu.pfm_to_pwm(pu.norm_pfm(seq), 20)
+    V["to_pwm_seq_20"] = pwm
+    V["scan_fwd_seq"] = {"seq": "UUUUGCUCUGUAUAUAGGCAUCG", "scores": pu.pwm_scan_fwd(pwm, "UUUUGCUCUGUAUAUAGGCAUCG")}
+    spwm = pu.pfm_to_pwm(pu.norm_pfm(pu.read_pfm(P("test_struct_pfm.txt"))), 7)
+    V["scan_fwd_struct"] = {"seq": "EEELLLHHHRRREEMMBBTT", "scores": pu.pwm_scan_fwd(spwm, "EEELLLHHHRRREEMMBBTT"),
+                            "pwm": spwm}
+    V["reduce_struct"] = pu.reduce_pfm_alphabet(struct)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "multi.txt")
+        pu.write_multi_pfm(["m1", "m2"], [seq, struct], f)
+        V["multi_text"] = open(f).read()
+        V["multi_iter"] = [[i, {k: list(v) for k, v in pfm.items()}] for i, pfm in pu.multi_pfm_iter(f)]
+    return V
 
 
 def main():

@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE: an oracle-backed stand-in for ``rnascan_b200.device`` so that the HOST
+logic of the product (record packing, hit -> (record, start) mapping, frame assembly, CLI flow,
+stderr messages, TSV text) can be exercised on a machine without a GPU.
+
+``install(monkeypatch)`` swaps the device entry points for functions that compute the same
+results with the CPU oracle on the same packed streams.  Nothing here is shipped or imported
+by the product; the GPU tests (-m gpu) run the same cases through the real kernels.
+"""
+import numpy as np
+import torch
+
+from oracle import oracle as orc
+from rnascan_b200 import device, synth, _lib
+
+
+class FakeSymbolStream(object):
+    def __init__(self, codes, offsets=None, lengths=None, device=None):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.n = int(codes.shape[0])
+        self.offsets = np.zeros(1, np.int64) if offsets is None else np.asarray(offsets, np.int64)
+        self.lengths = np.array([self.n], np.int64) if lengths is None else np.asarray(lengths, np.int64)
+        self._codes = codes
+        self.codes = torch.from_numpy(codes.copy())
+
+    @classmethod
+    def from_texts(cls, texts, kind, device=None):
+        codes, offsets, lengths = device_pack(texts, kind)
+        return cls(codes, offsets, lengths)
+
+    def host_codes(self):
+        return self._codes
+
+    locate = device.SymbolStream.locate
+
+
+def device_pack(texts, kind):
+    return device.pack_texts(texts, kind)
+
+
+class FakeProfileStream(object):
+    def __init__(self, rows, device=None):
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype not in (np.float32, np.float64):
+            rows = rows.astype(np.float64)
+        self.n = rows.shape[0]
+        self._rows = rows
+        self.dtype = _lib.RS_F32 if rows.dtype == np.float32 else _lib.RS_F64
+
+    def absrow_max(self):
+        return float(np.abs(self._rows).sum(axis=1).max()) if self.n else 0.0
+
+
+def _text(stream, kind):
+    return synth.to_text(stream._codes, kind)
+
+
+def _sep_mask(codes, W):
+    sep = (codes == 0xFF).astype(np.int64)
+    c = np.concatenate([[0], np.cumsum(sep)])
+    n = len(codes) - W + 1
+    return (c[W:W + n] - c[:n]) > 0 if n > 0 else np.zeros(0, bool)
+
+
+def histogram(stream):
+    c = stream._codes
+    return torch.from_numpy(np.array([(c == k).sum() for k in range(8)], np.int64))
+
+
+def dense_seq(stream, table):
+    t = device._table(table, 4)
+    return torch.from_numpy(orc.seq_scores(_text(stream, "rna"), t))
+
+
+def dense_struct(stream, table):
+    t = device._table(table, 7)
+    return torch.from_numpy(orc.alpha_scores(_text(stream, "struct"), t, "BEHLMRT"))
+
+
+def dense_profile(profile, table, stream=None):
+    t = device._table(table, 7)
+    with np.errstate(all="ignore"):
+        sc = orc.profile_scores(profile._rows, t)
+    if stream is not None and len(sc):
+        sc[_sep_mask(stream._codes, t.shape[0])] = np.nan
+    return torch.from_numpy(sc)
+
+
+def _gt(scores, thr):
+    with np.errstate(invalid="ignore"):
+        return np.asarray(scores, np.float64) > float(thr)
+
+
+def scan_seq(stream, table, threshold, capacity=None):
+    if float(threshold) != float(threshold):
+        raise ValueError("threshold is NaN")
+    sc = dense_seq(stream, table).numpy()
+    pos = np.nonzero(_gt(sc, threshold))[0].astype(np.int64)
+    return pos, sc[pos]
+
+
+def scan_struct_onehot(stream, table, threshold, capacity=None):
+    sc = dense_struct(stream, table).numpy()
+    pos = np.nonzero(_gt(sc, threshold))[0].astype(np.int64)
+    return pos, sc[pos]
+
+
+def scan_pair_onehot(seq_stream, struct_stream, seq_table, struct_table, threshold, capacity=None):
+    a = dense_seq(seq_stream, seq_table).numpy()
+    b = dense_struct(struct_stream, struct_table).numpy()
+    pos = np.nonzero(_gt(a, threshold) & _gt(b, threshold))[0].astype(np.int64)
+    return pos, a[pos], b[pos]
+
+
+def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=None, return_stats=False):
+    b = dense_profile(profile, struct_table, stream).numpy()
+    keep = _gt(b, threshold)
+    a = None
+    if seq_table is not None:
+        a = dense_seq(stream, seq_table).numpy()
+        keep &= _gt(a, threshold)
+    pos = np.nonzero(keep)[0].astype(np.int64)
+    out = (pos, a[pos] if a is not None else None, b[pos])
+    return out + (0,) if return_stats else out
+
+
+def install(monkeypatch):
+    for name, fn in (("SymbolStream", FakeSymbolStream), ("ProfileStream", FakeProfileStream),
+                     ("histogram", histogram), ("dense_seq", dense_seq), ("dense_struct", dense_struct),
+                     ("dense_profile", dense_profile), ("scan_seq", scan_seq),
+                     ("scan_struct_onehot", scan_struct_onehot), ("scan_pair_onehot", scan_pair_onehot),
+                     ("scan_fused", scan_fused)):
+        monkeypatch.setattr(device, name, fn)
+    from rnascan_b200 import rnascan as ms
+    ms._BATCH_CACHE.clear()

@@ -1,0 +1,195 @@
+"""Drop-in parity of the scan API and the CLI on the GPU: stdout of ``rnascan`` (hits.tab,
+--bgonly dicts) must be byte-identical to what the reference's own main() printed for the same
+arguments (tests/golden/cli/*.stdout, produced by tests/golden/make_golden.py), stderr
+messages included; API-level results must equal the golden vectors of the reference's
+functions."""
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(REPO, "tests", "golden", "cli")
+INP = os.path.join(REPO, "tests", "golden", "inputs")
+
+with open(os.path.join(CLI, "cases.json")) as _fh:
+    CASES = json.load(_fh)
+ALIGNED = sorted(k for k, v in CASES.items() if v["group"] != "misaligned")
+
+
+def run_cli(argv):
+    from rnascan_b200 import rnascan as ms
+    out, err = io.StringIO(), io.StringIO()
+    code = 0
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        try:
+            ms.main(list(argv))
+        except SystemExit as e:
+            code = e.code or 0
+    lines = [l for l in err.getvalue().splitlines() if "seconds" not in l and "minutes" not in l]
+    return out.getvalue(), lines, code
+
+
+def same(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and \
+        np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+@pytest.mark.parametrize("name", ALIGNED)
+def test_cli_output_is_byte_identical(name, in_repo):
+    case = CASES[name]
+    with open(os.path.join(CLI, name + ".stdout")) as fh:
+        want = fh.read()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out, err_lines, code = run_cli(case["argv"])
+    assert code == case["exit"]
+    assert out == want
+    assert err_lines == case["stderr_lines"]
+
+
+def test_cores_flag_does_not_change_the_result(in_repo):
+    base = CASES["rna_mixed_all"]["argv"]
+    a = run_cli(base)[0]
+    b = run_cli([x for x in base if x not in ("-c", "2")] + ["-c", "7"])[0]
+    assert a == b
+
+
+def test_averaged_cli_is_label_aligned_not_the_py3_misaligned_variant(in_repo):
+    """on python >= 3.6 the reference pairs profile columns B,E,H,L,M,R,T with PSSM
+    columns E,H,T,B,L,R,M positionally.  The canonical semantics here are label-aligned; the
+    misaligned output is kept as a golden file only to document the divergence."""
+    case = CASES["rnass_avg_example_misaligned"]
+    out, _, code = run_cli(case["argv"])
+    with open(os.path.join(CLI, "rnass_avg_example_misaligned.stdout")) as fh:
+        mis = fh.read()
+    assert code == 0 and out != mis
+    rows, mrows = out.splitlines(), mis.splitlines()
+    assert rows[0] == mrows[0] and len(rows) == len(mrows) == 220
+    cols = rows[0].split("\t")
+    i_seq, i_str, i_start = cols.index("LogOdds.Seq"), cols.index("LogOdds.Struct"), cols.index("Start")
+    best = max(rows[1:], key=lambda r: float(r.split("\t")[i_str])).split("\t")
+    assert best[i_start] == "213" and float(best[i_str]) > 10.0              # the SLBP stem-loop
+    # sequence column is unaffected by the alignment question
+    assert [r.split("\t")[i_seq] for r in rows[1:]] == [r.split("\t")[i_seq] for r in mrows[1:]]
+
+
+# ----------------------------------------------------------------------------- API level
+def _pssm(golden_api, name):
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.seq import IUPAC
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    g = golden_api["pssm"][name]
+    alpha = IUPAC.IUPACUnambiguousRNA() if g["alphabet"] == "GAUC" else ContextualSecondaryStructure()
+    bg = g["background"]
+    if bg is not None:
+        bg = {l: bg[l] for l in g["alphabet"]}
+    return ms.pfm2pssm(g["file"], g["pseudocount"], alpha, bg), alpha
+
+
+def test_calculate_matches_the_reference_class(golden_api, in_repo):
+    for key, g in golden_api["calculate"].items():
+        pm, _ = _pssm(golden_api, key.split("|")[0])
+        r = pm.calculate(g["seq"])
+        if len(g["scores"]) == 1:
+            assert np.ndim(r) == 0                       # scalar when there is one window
+        r = np.atleast_1d(np.asarray(r))
+        if g["dtype"] == "float32":
+            assert r.dtype == np.float32 or len(r) == 0
+        assert same(r, g["scores"]), key
+
+
+def test_pwm_module_signature_and_errors(in_repo):
+    from rnascan_b200.BioAddons.motifs import _pwm
+    out = _pwm.calculate("ACGUN", np.zeros((2, 4)))
+    assert out.dtype == np.float32 and out.shape == (4,) and np.isnan(out[3])
+    assert _pwm.calculate(sequence="AC", matrix=np.ones((2, 4)))[0] == 2.0
+    with pytest.raises(ValueError):
+        _pwm.calculate("ACGU", np.zeros((4, 4), np.float32))
+    with pytest.raises(ValueError):
+        _pwm.calculate("ACGU", np.zeros((4, 5)))
+    with pytest.raises(ValueError):
+        _pwm.calculate("ACGU", np.zeros(4))
+    with pytest.raises(TypeError):
+        _pwm.calculate(1234, np.zeros((4, 4)))
+
+
+def test_compute_background_matches_the_reference(golden_api, in_repo, capsys):
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.seq import IUPAC
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bg = ms.compute_background([os.path.join(INP, "test.fa")], IUPAC.IUPACUnambiguousRNA(), verbose=False)
+        assert dict(bg) == golden_api["bg_test_fa"] and list(bg) == list("GAUC")
+        # the reference's own known-answer test, tests/motif_scan_test.py:33-43
+        for k, v in {"A": 0.1944, "C": 0.1388, "U": 0.5277, "G": 0.1388}.items():
+            assert abs(bg[k] - v) < 1e-3
+        bg = ms.compute_background(os.path.join(INP, "mixed_struct.fa"), ContextualSecondaryStructure(), False)
+        assert dict(bg) == golden_api["bg_mixed_struct_fa"] and list(bg) == list("EHTBLRM")
+    capsys.readouterr()
+
+
+def test_scan_averaged_structure_matches_the_reference(golden_api, in_repo):
+    from rnascan_b200 import rnascan as ms
+    for key, g in golden_api["averaged"].items():
+        pm, _ = _pssm(golden_api, g["pssm"])
+        df = ms.scan_averaged_structure(g["profile"], {"m": pm}, g["threshold"])
+        rows = [] if df.shape[0] == 0 else [[int(r.Start), int(r.End), float(r.LogOdds)] for r in df.itertuples()]
+        assert [r[:2] for r in rows] == [r[:2] for r in g["rows"]], key
+        assert same([r[2] for r in rows], [r[2] for r in g["rows"]]), key
+        if rows:
+            assert list(df.columns) == ["Motif_ID", "Start", "End", "Sequence", "LogOdds"]
+            assert set(df["Sequence"]) == {"."} and set(df["Motif_ID"]) == {"m"}
+
+
+def test_combined_example_matches_the_reference(golden_api, in_repo, capsys):
+    """K5: combine() of the example's sequence hits (uniform background) and label-aligned
+    averaged-structure hits at m = 6 -- one row, Start 213."""
+    from rnascan_b200 import rnascan as ms
+    seq_pm, rna = _pssm(golden_api, "slbp_seq_uniform")
+    st_pm, _ = _pssm(golden_api, "slbp_struct_examplebg")
+
+    class Args(object):
+        minscore, debug, cores = 6.0, False, 1
+    seq_df = ms.scan_main(os.path.join(INP, "HIST2H3C_3p_end.fa"),
+                          {"SLBP_pfm_assembled_normalized_seq": seq_pm}, rna, None, Args())
+    st_df = ms.scan_main(os.path.join(INP, "profiles_example"),
+                         {"SLBP_pfm_assembled_normalized_struct": st_pm}, None, None, Args())
+    comb = ms.combine(seq_df, st_df)
+    ms._add_match_id(comb)
+    buf = io.StringIO()
+    comb.to_csv(buf, sep="\t", index=False)
+    assert buf.getvalue() == golden_api["combine_example_aligned_tsv"]
+    capsys.readouterr()
+
+
+def test_pwm_scan_fwd_matches_the_reference(golden_api):
+    from rnascan_b200 import pfmutil as pu
+    V = golden_api["pfmutil"]
+    got = pu.pwm_scan_fwd(V["to_pwm_seq_20"], V["scan_fwd_seq"]["seq"])
+    assert same(got, V["scan_fwd_seq"]["scores"]) and isinstance(got[0], float)
+    got = pu.pwm_scan_fwd(V["scan_fwd_struct"]["pwm"], V["scan_fwd_struct"]["seq"])
+    assert same(got, V["scan_fwd_struct"]["scores"])
+    with pytest.raises(KeyError):
+        pu.pwm_scan_fwd(V["to_pwm_seq_20"], "ACGUNACGU")
+    assert pu.pwm_scan_fwd(V["to_pwm_seq_20"], "AC") == []
+
+
+def test_search_generator_semantics(golden_api, in_repo):
+    pm, _ = _pssm(golden_api, "test_seq_uniform")
+    hits = list(pm.search("UUUUGCUCUGUAUAUA", threshold=0.0, both=False))
+    assert [p for p, _ in hits] == [1, 5, 6, 7]
+    assert all(isinstance(s, np.float32) for _, s in hits)
+    assert list(pm.search("ACG", threshold=-100.0, both=False)) == []
+    # NaN / -inf windows are never reported, even at -inf
+    hits = list(pm.search("ACGUNACGU", threshold=float("-inf"), both=False))
+    assert [p for p, _ in hits] == [0, 5]

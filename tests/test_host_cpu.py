@@ -1,0 +1,303 @@
+"""Host-side logic of the product (no GPU needed): PFM -> log-odds, sequence handling, argument
+parsing, pfmutil, shard planning, and that the C-ABI library loads and exports every symbol
+declared in include/rnascan_b200.h."""
+import copy
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INP = os.path.join(REPO, "tests", "golden", "inputs")
+
+
+def same(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and \
+        np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+# ----------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    from rnascan_b200 import _lib
+    header = open(os.path.join(REPO, "include", "rnascan_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(_lib.lib, name), "library lacks %s" % name
+    assert sorted(_lib.EXPORTS) == declared, "ctypes signatures and header differ"
+    assert _lib.lib.rs_version() >= 100
+    assert _lib.lib.rs_padded_count(0) == 256 and _lib.lib.rs_padded_count(257) == 768
+    assert _lib.lib.rs_scan_workspace_bytes(1 << 20, 1000) > 0
+
+
+def test_host_encoders_match_the_reference_switch():
+    from rnascan_b200 import device, _lib
+    codes, off, ln = device.pack_texts(["ACGUTacgutNn-x", "", "Rr"], "rna")
+    assert codes.tolist() == [0, 1, 2, 3, 3, 0, 1, 2, 3, 3, 12, 12, 12, 12, 255, 255, 12, 12, 255]
+    assert off.tolist() == [0, 15, 16] and ln.tolist() == [14, 0, 2]
+    codes, _, _ = device.pack_texts(["BEHLMRTbehlmrtXx."], "struct")
+    assert codes.tolist() == [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15, 15, 15, 255]
+    assert _lib.RS_SEP == 255
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rnascan_b200 import device, _lib
+    with pytest.raises(_lib.RnascanCudaError):
+        device.SymbolStream(np.zeros(8, np.uint8))
+    from rnascan_b200.BioAddons.motifs import _pwm
+    with pytest.raises(_lib.RnascanCudaError):
+        _pwm.calculate("ACGUACGU", np.zeros((4, 4)))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(REPO, "rnascan_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text, f
+
+
+# ----------------------------------------------------------------------------- PFM -> PSSM
+def test_pfm2pssm_matches_the_reference(golden_api, in_repo):
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.seq import IUPAC
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    for name, g in golden_api["pssm"].items():
+        alpha = IUPAC.IUPACUnambiguousRNA() if g["alphabet"] == "GAUC" else ContextualSecondaryStructure()
+        assert alpha.letters == g["alphabet"]
+        bg = g["background"]
+        if bg is not None:
+            bg = {l: bg[l] for l in g["alphabet"]}
+        pm = ms.pfm2pssm(g["file"], g["pseudocount"], alpha, bg)
+        assert list(pm.keys()) == list(g["alphabet"])
+        assert pm.length == len(g["values"][g["alphabet"][0]])
+        for letter in g["alphabet"]:
+            assert same(pm[letter], g["values"][letter]), (name, letter)
+
+
+def test_pssm_object(golden_api, in_repo):
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.seq import IUPAC
+    pm = ms.pfm2pssm(os.path.join(INP, "SLBP_pfm_assembled_normalized_seq.txt"), 0,
+                     IUPAC.IUPACUnambiguousRNA(), None)
+    assert pm.length == 18 and len(pm.consensus) == 18
+    assert str(pm.consensus)[5:9] == "CUCU" or len(str(pm.consensus)) == 18
+    t = pm.table("ACGU")
+    assert t.shape == (18, 4) and t[0, 3] == pm["U"][0]
+    loaded = ms.load_motif(os.path.join(INP, "test_seq_pfm.txt"), 0, IUPAC.IUPACUnambiguousRNA(), None)
+    assert list(loaded) == ["test_seq_pfm"]
+
+
+def test_wrong_alphabet_pfm_raises_keyerror(in_repo):
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    with pytest.raises(KeyError):
+        ms.load_motif(os.path.join(INP, "test_seq_pfm.txt"), 0, ContextualSecondaryStructure(), None)
+
+
+# ----------------------------------------------------------------------------- sequences
+def test_preprocess_seq_cases_of_the_reference():
+    # /root/reference/tests/preprocess_seq_test.py:13-53
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.seq import Seq, SeqRecord, IUPAC, SingleLetterAlphabet
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    rna, dna = IUPAC.IUPACUnambiguousRNA(), IUPAC.IUPACUnambiguousDNA()
+    cases = [(Seq("GATTACA", dna), rna, "GAUUACA"), (Seq("GAUUACA", rna), rna, "GAUUACA"),
+             (Seq("GAUUACA", rna), dna, "GAUUACA"), (Seq("GATTACA", dna), dna, "GATTACA"),
+             (Seq("GAUUACA", SingleLetterAlphabet()), rna, "GAUUACA"),
+             (Seq("KHIL", ContextualSecondaryStructure()), rna, "KHIL"),
+             (Seq("gattaca", SingleLetterAlphabet()), rna, "GAUUACA")]
+    for s, alpha, want in cases:
+        assert str(ms.preprocess_seq(SeqRecord(s), alpha)) == want
+    with pytest.raises(TypeError):
+        ms.preprocess_seq("GATTACA", rna)
+
+
+def test_parse_sequences_and_batches():
+    # /root/reference/tests/motif_scan_test.py:18-25
+    from rnascan_b200 import rnascan as ms
+    recs = list(ms.parse_sequences([os.path.join(INP, "test.fa")]))
+    assert [r.id for r in recs] == ["read1", "read2"]
+    assert all(str(r.seq) == "UUUUGCUCUGUAUAUA" for r in recs)
+    recs = list(ms.parse_sequences(os.path.join(INP, "mixed.fa")))
+    assert [r.id for r in recs] == ["rec1", "rec2", "rec3", "rec4", "rec5", "rec6"]
+    assert recs[0].description == "rec1 first record, DNA letters" and len(recs[4].seq) == 0
+    assert len(recs[5].seq) == 400                       # wrapped lines are joined
+    assert [len(b) for b in ms.batch_iterator(iter(range(1, 8)), 3)] == [3, 3, 1]
+    assert list(ms.batch_iterator(iter([]), 3)) == []
+
+
+def test_gzip_fasta(tmp_path):
+    import gzip
+    from rnascan_b200 import rnascan as ms
+    p = tmp_path / "x.fa.gz"
+    with gzip.open(p, "wt") as fh:
+        fh.write(">a desc\nACGT\nAC\n>b\n\n")
+    recs = list(ms.parse_sequences(str(p)))
+    assert [(r.id, r.description, str(r.seq)) for r in recs] == [("a", "a desc", "ACGTAC"), ("b", "b", "")]
+
+
+# ----------------------------------------------------------------------------- CLI arguments
+def test_getoptions_and_mode_guess(capsys):
+    from rnascan_b200 import rnascan as ms
+    a = ms.getoptions(["-p", "x.pfm", "in.fa"])
+    assert (a.minscore, a.cores, a.pseudocount, a.uniform_background, a.bgonly, a.debug) == \
+        (6, 8, 0, False, False, False)
+    assert ms._guess_seq_type(a) == "RNA"
+    assert ms._guess_seq_type(ms.getoptions(["-q", "x.pfm", "in.fa"])) == "SS"
+    assert ms._guess_seq_type(ms.getoptions(["-p", "a", "-q", "b", "s.fa", "t.fa"])) == "RNASS"
+    assert ms._guess_seq_type(ms.getoptions(["-p", "a", "-q", "b", "-t", "ACGU,EEEE"])) == "RNASS"
+    assert ms.getoptions(["-p", "a", "-m", " -inf", "x.fa"]).minscore == float("-inf")
+    with pytest.raises(SystemExit):
+        ms.getoptions(["in.fa"])
+    with pytest.raises(SystemExit):
+        ms.getoptions(["-p", "a", "-u", "-b", "bg.txt", "x.fa"])
+    with pytest.raises(SystemExit):
+        ms._guess_seq_type(ms.getoptions(["-p", "a", "-q", "b", "only_one.fa"]))
+    capsys.readouterr()
+
+
+def test_load_background_file_and_uniform(in_repo, capsys):
+    from rnascan_b200 import rnascan as ms
+    bg = ms.load_background(os.path.join(INP, "bg_seq_custom.txt"), False)
+    assert bg == {"A": 0.3, "C": 0.2, "G": 0.2, "U": 0.3}
+    assert ms.load_background(None, True) is None
+    err = capsys.readouterr().err
+    assert "Reading custom background probabilities from" in err
+
+
+# ----------------------------------------------------------------------------- pfmutil
+def test_pfmutil_matches_the_reference(golden_api, tmp_path):
+    from rnascan_b200 import pfmutil as pu
+    V = golden_api["pfmutil"]
+    struct = pu.read_pfm(os.path.join(INP, "SLBP_pfm_assembled_normalized_struct.txt"))
+    seq = pu.read_pfm(os.path.join(INP, "test_seq_pfm.txt"))
+    assert struct == V["read_struct"]
+    assert pu.format_pfm(struct) == V["format_struct"] and pu.format_pfm(seq) == V["format_seq"]
+    assert pu.norm_pfm(seq) == V["norm_seq"]
+    assert [pu.is_normalized(seq), pu.is_normalized(pu.norm_pfm(seq)), pu.is_normalized(struct)] == V["is_normalized"]
+    assert pu.pfm_from_IUPAC("ACGURYSWKMBDHVN") == V["from_IUPAC"]
+    assert pu.pfm_from_string("EHLLRT", pu.FULL_STRUCT_ALPHABET) == V["from_string"]
+    with pytest.raises(Exception):
+        pu.pfm_from_string("EHX", pu.FULL_STRUCT_ALPHABET)
+    assert pu.pfm_to_pwm(pu.norm_pfm(seq), 20) == V["to_pwm_seq_20"]
+    assert pu.reduce_pfm_alphabet(struct) == V["reduce_struct"]
+    f = str(tmp_path / "multi.txt")
+    pu.write_multi_pfm(["m1", "m2"], [seq, struct], f)
+    assert open(f).read() == V["multi_text"]
+    got = [[i, copy.deepcopy(pfm)] for i, pfm in pu.multi_pfm_iter(f)]
+    assert got == V["multi_iter"]
+    g = str(tmp_path / "one.txt")
+    pu.write_pfm(struct, g)
+    assert pu.read_pfm(g) == struct
+
+
+# ----------------------------------------------------------------------------- sharding
+def _check_plan(lengths, R, W):
+    from rnascan_b200 import shard
+    plan = shard.plan_shards(lengths, R, W)
+    assert len(plan) == R
+    own = [np.zeros(max(L, 1), int) for L in lengths]
+    cnt = [np.zeros(max(L, 1), int) for L in lengths]
+    order = []
+    for pieces in plan:
+        for (r, a, b, o) in pieces:
+            order.append((r, a))
+            L = lengths[r]
+            last = o >= b
+            hi = (b - W + 1) if last else o
+            assert 0 <= a <= b <= L
+            if not last:
+                assert b == min(L, o + W - 1)
+            own[r][a:max(a, hi)] += 1
+            cnt[r][a:a + shard.owned_symbols((r, a, b, o))] += 1
+    assert order == sorted(order)
+    for r, L in enumerate(lengths):
+        nw = max(0, L - W + 1)
+        assert (own[r][:nw] == 1).all() and (own[r][nw:L] == 0).all()
+        assert (cnt[r][:L] == 1).all()
+    return plan
+
+
+def test_shard_plan_owns_every_window_once():
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        n = int(rng.integers(1, 30))
+        lengths = rng.integers(0, 200, size=n).tolist()
+        if trial % 5 == 0:
+            lengths[int(rng.integers(0, n))] = 5000
+        _check_plan(lengths, int(rng.integers(1, 9)), int(rng.integers(1, 20)))
+    _check_plan([], 4, 7)
+    _check_plan([0, 0, 0], 2, 7)
+    plan = _check_plan([1_000_000], 8, 7)                 # one long record is split 8 ways
+    loads = [sum(b - a for (_, a, b, _) in p) for p in plan]
+    assert max(loads) - min(loads) <= 16 and all(len(p) == 1 for p in plan)
+
+
+_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, %(repo)r)
+import numpy as np
+import torch.distributed as dist
+from rnascan_b200 import shard, synth
+rank, size = shard.init("gloo")
+rng = np.random.default_rng(5)
+lengths = synth.record_lengths(200000, 40, rng)
+codes, offsets = synth.rna_codes(lengths, rng, n_frac=0.01)
+W = 7
+plan = shard.plan_shards(lengths, size, W)
+counts = np.zeros(8, np.int64)
+starts = []
+for piece in plan[rank]:
+    r, a, b, o = piece
+    seg = codes[offsets[r] + a: offsets[r] + b]
+    k = shard.owned_symbols(piece)
+    counts += np.bincount(seg[:k][seg[:k] < 8], minlength=8)      # stand-in for rs_hist on this rank's shard
+    hi = (b - W + 1) if o >= b else o
+    starts.extend((r, i) for i in range(a, max(a, hi)))
+total = shard.allreduce_counts(counts)
+gathered = shard.gather_objects(starts)
+if rank == 0:
+    flat = [x for part in gathered for x in part]
+    want_counts = np.bincount(codes[codes < 8], minlength=8)
+    want = [(r, i) for r, L in enumerate(lengths.tolist()) for i in range(max(0, L - W + 1))]
+    print(json.dumps({"counts_ok": bool((total == want_counts).all()), "order_ok": flat == want,
+                      "n": len(flat), "size": size}))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_allreduce_and_ordered_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"repo": REPO})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res == {"counts_ok": True, "order_ok": True, "n": res["n"], "size": 2} and res["n"] > 100000
+
+
+def test_numpy_strided_dot_is_the_pinned_arithmetic(oracle):
+    """The averaged-profile oracle pins OpenBLAS' strided ddot arithmetic; check that numpy on
+    THIS machine still computes it that way (skip, not fail, on a different BLAS build)."""
+    rng = np.random.default_rng(3)
+    prof = np.asfortranarray(rng.random((200, 7)))
+    tab = np.asfortranarray(rng.normal(size=(5, 7)) * 3)
+    got = oracle.profile_scores(np.ascontiguousarray(prof), np.ascontiguousarray(tab))
+    want = oracle.profile_scores_py(prof, tab)
+    if not np.array_equal(got, want):
+        pytest.skip("this machine's BLAS uses a different ddot kernel than the one the golden vectors pin")
