@@ -36,7 +36,8 @@ THRESHOLD = 6.0
 SS_BG = {"B": 0.0163181097311479, "E": 0.272087789050946, "H": 0.153012079123538,
          "L": 0.204624685341275, "M": 0.0196001330531237, "R": 0.196989713257981,
          "T": 0.137367490441988}       # example/3p_UTR_background_structural_context.txt
-ALGO_BYTES = {"c4": 29.0, "c2": 1.0, "c3": 5.0}     # SURVEY.md section 8(d), per scored position
+ALGO_BYTES = {"c4": 29.0, "c2": 1.0, "c3": 5.0, "c5": 29.0}     # SURVEY.md section 8(d), per scored position
+N_MOTIFS_C5 = 256
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -145,7 +146,7 @@ def make_device_shard(n_symbols, seed, workload, device):
     full[sep_idx] = 0xFF
     del codes
     prof = None
-    if workload == "c4":
+    if workload in ("c4", "c5"):
         prof = torch.zeros((npad, 7), dtype=torch.float32, device=device)
         step = 1 << 24
         for a in range(0, n, step):
@@ -196,6 +197,29 @@ def make_tables_fn(workload, seed=102):
 
     if workload == "c4":
         return lambda counts8: (seq_table(counts8), tq)
+    if workload == "c5":
+        # 256 motif pairs, W ~ U{7..12} (same W for the two PFMs of a pair), Dirichlet(0.3) rows
+        r5 = np.random.default_rng(seed + 5)
+        widths = r5.integers(7, 13, size=N_MOTIFS_C5)
+        seq_probs, tqs = [], []
+        for w in widths:
+            ps = synth.pfm_rows(int(w), 4, r5)
+            pq = synth.pfm_rows(int(w), 7, r5)
+            seq_probs.append(motifs.normalize_counts({l: ps[:, "ACGU".index(l)].tolist() for l in rna}, rna, 0.01))
+            sp = motifs.log_odds(motifs.normalize_counts({l: pq[:, "BEHLMRT".index(l)].tolist() for l in chan},
+                                                         chan, 0.01), chan, {l: SS_BG[l] for l in chan})
+            tqs.append(np.array([sp[l] for l in "BEHLMRT"], np.float64).T.copy())
+
+        def batched(counts8):
+            c = {"A": int(counts8[0]), "C": int(counts8[1]), "G": int(counts8[2]), "U": int(counts8[3])}
+            total = 4 + sum(c[l] for l in rna)
+            bg = {l: (float(c[l]) + 1) / total for l in rna}
+            tss = []
+            for prob in seq_probs:
+                pssm = motifs.log_odds(prob, rna, bg)
+                tss.append(np.array([pssm[l] for l in "ACGU"], np.float64).T.copy())
+            return tss, tqs
+        return batched
     if workload == "c2":
         return lambda counts8: (seq_table(counts8), None)
     return lambda counts8: (None, struct_table_computed(counts8))
@@ -229,8 +253,14 @@ def run_b200(args):
     hb = dev.HitBuffers(n, max(1 << 16, n // 256), device)
     dense_out = torch.empty(n, dtype=torch.float64, device=device) if wl == "c3" else None
     absmax = 1.0
-    if wl == "c4":
+    if wl in ("c4", "c5"):
         absmax = dev.ProfileStream.from_device(prof, n).absrow_max()
+    if wl == "c5":
+        _, tq0 = tables(np.ones(8, np.int64))
+        c5_widths = np.array([t.shape[0] for t in tq0], np.int32)
+        c5_motif = torch.empty(hb.capacity, dtype=torch.int32, device=device)
+        c5_counters = torch.zeros(2 * N_MOTIFS_C5, dtype=torch.int64, device=device)
+        c5_bases = torch.zeros(N_MOTIFS_C5 + 1, dtype=torch.int64, device=device)
     launches = [0]
 
     def all_reduce(t):
@@ -250,6 +280,17 @@ def run_b200(args):
                                     _ptr(hb.seq), _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work),
                                     hb.work_bytes, sptr))
             launches[0] += 3
+        elif wl == "c5":
+            M = len(tq)
+            stride = max(t.shape[0] for t in tq)
+            qs = np.zeros((M, stride, 7)); ss = np.zeros((M, stride, 4))
+            for m in range(M):
+                qs[m, :tq[m].shape[0]] = tq[m]; ss[m, :ts[m].shape[0]] = ts[m]
+            check(lib.rs_scan_batched(_ptr(codes), _ptr(prof), _lib.RS_F32, n, M, c5_widths.ctypes.data,
+                                      ss.ctypes.data, qs.ctypes.data, stride, THRESHOLD, absmax, _lib.RS_MODE_AND,
+                                      hb.capacity, _ptr(c5_motif), _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct),
+                                      _ptr(c5_counters), _ptr(c5_bases), _ptr(hb.work), hb.work_bytes, sptr))
+            launches[0] += 4 * M
         elif wl == "c2":
             check(lib.rs_scan_seq(_ptr(codes), n, ts.ctypes.data, W_MOTIF, THRESHOLD, hb.capacity, _ptr(hb.pos),
                                   _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, sptr))
@@ -271,7 +312,8 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches[0] = 0
-    check(lib.rs_prof_begin(max(args.steps, 1)))
+    per_step = N_MOTIFS_C5 if wl == "c5" else 1
+    check(lib.rs_prof_begin(max(args.steps, 1) * per_step))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -279,12 +321,14 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    kms = np.zeros(max(args.steps, 1), np.float32)
+    kms = np.zeros(max(args.steps, 1) * per_step, np.float32)
     nrec = np.zeros(1, np.int32)
     check(lib.rs_prof_end(kms.ctypes.data, len(kms), nrec.ctypes.data))
-    kernel_ms = float(kms[:int(nrec[0])].mean()) if nrec[0] else float("nan")
+    kernel_ms = float(kms[:int(nrec[0])].sum()) / args.steps if nrec[0] else float("nan")
     n_launch = launches[0]
-    hits = int(hb.counters[0].item()) if wl != "c3" else None
+    hits = int(hb.counters[0].item()) if wl in ("c4", "c2") else None
+    if wl == "c5":
+        hits = int(c5_bases[-1].item())
 
     # ---- end to end: host buffers -> device -> hits back on the host, every step
     e2e = None
@@ -329,19 +373,23 @@ def run_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 filter + f64 exact re-score (sequence: f64 accumulate -> f32)" if wl == "c4" else
-                 ("f64 accumulate -> f32" if wl == "c2" else "f64"),
+                 ("f64 accumulate -> f32" if wl == "c2" else ("f64" if wl == "c3" else
+                                                              "f32 filter + f64 exact re-score, per motif")),
         "data": "synthetic (SURVEY.md 8d shapes; generated on device, seed 4000+rank)",
         "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile, fused AND scan",
-                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, dense f64 output"}[wl],
+                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, dense f64 output",
+                                "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure, CUDA-core path "
+                                      "(one fused scan per motif)" % N_MOTIFS_C5}[wl],
                    "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
                    "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
                    "background": "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step",
                    "l2_policy": "inputs (%.2f GB per GPU) exceed the 126 MB L2" %
-                                (n * (29 if wl == "c4" else 1) / 1e9),
+                                (n * (29 if wl in ("c4", "c5") else 1) / 1e9),
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
         "gpu_launches": n_launch,
-        "roofline": {"bound": "hbm", "kernel": {"c4": "fused_filter_kernel<7>", "c2": "onehot_kernel<4>",
-                                               "c3": "onehot_kernel<7,dense>"}[wl],
+        "roofline": {"bound": "hbm", "kernel": {"c4": "fused_filter_kernel<7>", "c2": "kmer_scan_kernel<7>",
+                                               "c3": "onehot_kernel<7,dense>",
+                                               "c5": "fused_filter_kernel<W> x %d motifs" % N_MOTIFS_C5}[wl],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],
                      "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step, "traffic": None},
@@ -349,6 +397,11 @@ def run_b200(args):
     }
     if hits is not None:
         out["hits_rank0"] = hits
+    if wl == "c5":
+        out["motif_positions_per_s"] = out["value"] * N_MOTIFS_C5
+        out["roofline"]["note"] = ("CUDA-core path re-reads the streams once per motif: physical traffic is %d x the "
+                                   "algorithmic 29 B/position; the tensor-core (windows x motifs GEMM) path is the "
+                                   "replacement" % N_MOTIFS_C5)
     if e2e:
         out["e2e"] = {"value": all_positions / (ms_e2e * 1e-3) / 1e9, "unit": "Gpos/s",
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -377,7 +430,7 @@ def host_sample(n_symbols, workload, seed=4999, min_records=1):
     return lengths, offsets, codes, rows
 
 
-def cpu_port_baseline(workload, n_symbols=16_000_000):
+def cpu_port_baseline(workload, n_symbols=None):
     """The C oracle (oracle/pwm_oracle.c, a port of the reference's loops) over whole records
     with all host threads: the most the reference's C kernel could do if it were driven per
     record instead of per window.  Reported, not the target."""
@@ -385,7 +438,9 @@ def cpu_port_baseline(workload, n_symbols=16_000_000):
     from rnascan_b200 import synth
     L = orc.lib()
     cores = int(L.orc_get_threads())
-    lengths, offsets, codes, rows = host_sample(n_symbols, workload)
+    if n_symbols is None:
+        n_symbols = 1_000_000 if workload == "c5" else 16_000_000
+    lengths, offsets, codes, rows = host_sample(n_symbols, "c4" if workload == "c5" else workload)
     positions = scored_positions(lengths, W_MOTIF)
     tables = make_tables_fn(workload)
     t0 = time.perf_counter()
@@ -401,12 +456,19 @@ def cpu_port_baseline(workload, n_symbols=16_000_000):
         L.orc_count_letters(text, len(text), b"ACGU", 4, cnt.ctypes.data)
         counts[:4] = cnt
         ts, tq = tables(counts)
-        a = orc.seq_scores(text, ts, threads=True)
-        keep = a.astype(np.float64) > THRESHOLD
-        if workload == "c4":
-            b = orc.profile_scores(rows, tq)
-            keep &= b > THRESHOLD
-        nh = int(keep.sum())
+        if workload == "c5":
+            nh = 0
+            for ts_m, tq_m in zip(ts, tq):
+                a = orc.seq_scores(text, ts_m, threads=True)
+                b = orc.profile_scores(rows, tq_m)
+                nh += int(((a.astype(np.float64) > THRESHOLD) & (b > THRESHOLD)).sum())
+        else:
+            a = orc.seq_scores(text, ts, threads=True)
+            keep = a.astype(np.float64) > THRESHOLD
+            if workload == "c4":
+                b = orc.profile_scores(rows, tq)
+                keep &= b > THRESHOLD
+            nh = int(keep.sum())
     dt = time.perf_counter() - t0
     return {"value": positions / dt / 1e9, "unit": "Gpos/s", "cores": cores, "kind": "port",
             "sample": "%d symbols (%d scored positions) of the same synthetic workload, whole-record C loops "
@@ -461,7 +523,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--n-per-gpu", type=int, default=125_000_000, dest="n_per_gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

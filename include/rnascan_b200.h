@@ -141,6 +141,26 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
                   int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
                   uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
 
+/* ---- batched many-PFM scan (BASELINE config 5: 256 RNAcompete-style motif pairs) -------
+ * The reference scans one PFM (pair) per process run; a motif collection means running
+ * rnascan.py:490-576 once per motif.  Here all motifs are scanned over the SAME resident
+ * streams in one call.  Motif m has width widths[m] <= table_stride_rows and tables
+ * seq_tables[m][table_stride_rows][4] (NULL in RS_MODE_STRUCT) and
+ * struct_tables[m][table_stride_rows][7] (rows >= widths[m] are ignored).
+ * Hits come back grouped by motif (ascending), sorted by position inside a motif:
+ * d_hit_motif[k], d_hit_pos[k], d_hit_seq[k], d_hit_struct[k].  After syncing the stream,
+ * d_bases[m] .. d_bases[m+1] is motif m's slice, d_bases[n_motifs] the total (if it exceeds
+ * hit_capacity the excess was dropped: re-run with a larger buffer); d_motif_counters2[2m]
+ * = hits of motif m, [2m+1] = windows re-scored exactly for motif m.
+ * Semantics per motif are exactly rs_scan_fused's.                                        */
+int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                    int n_motifs, const int *widths, const double *seq_tables,
+                    const double *struct_tables, int table_stride_rows, double threshold,
+                    double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
+                    int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                    uint64_t *d_motif_counters2 /* [2*n_motifs] */, uint64_t *d_bases /* [n_motifs+1] */,
+                    void *d_work, int64_t work_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

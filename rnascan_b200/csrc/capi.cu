@@ -112,13 +112,14 @@ WorkLayout rs_work_layout(int64_t n, int64_t capacity)
 {
     WorkLayout wl;
     const int64_t cap = capacity > 0 ? capacity : 0;
-    const int64_t tiles = (n > 0 ? n : 0) / RS_MIN_TILE + 2;
+    const int64_t tiles = (n > 0 ? n : 0) / RS_MIN_TILE + 16;
     int64_t off = 0;
     wl.off_pos = off;  off += rs_roundup(cap * 8, 256);
     wl.off_str = off;  off += rs_roundup(cap * 8, 256);
     wl.off_seq = off;  off += rs_roundup(cap * 4, 256);
     wl.off_seg = off;  off += rs_roundup(tiles * 16, 256);
     wl.off_scan = off; off += rs_roundup(16 + 8 * (tiles / 8192 + 2), 256);
+    wl.off_lut = off;  off += rs_kmer_work_bytes(n);      // k-mer scan: table, hit masks, segment scan
     wl.total = off;
     return wl;
 }

@@ -151,10 +151,23 @@ struct HitStage {
 };
 
 struct WorkLayout {
-    int64_t off_pos, off_seq, off_str, off_seg, off_scan, total;
+    int64_t off_pos, off_seq, off_str, off_seg, off_scan, off_lut, total;
 };
 WorkLayout rs_work_layout(int64_t n, int64_t capacity);
-int rs_order_hits(const HitStage &st, int64_t n_tiles, int64_t *d_hit_pos, float *d_hit_seq,
-                  double *d_hit_str, void *d_scan_tmp, cudaStream_t stream);
+// Batched scans append every motif's ordered hits behind the previous motif's: `out_base`
+// (device, may be NULL = 0) is added to the destination index, `out_motif` (may be NULL)
+// receives `motif_id` for every hit written.
+struct OrderDest {
+    int64_t *pos; float *seq; double *str;
+    const unsigned long long *out_base;
+    int32_t *out_motif;
+    int32_t  motif_id;
+};
+int rs_order_hits(const HitStage &st, int64_t n_tiles, const OrderDest &dst, void *d_scan_tmp,
+                  cudaStream_t stream);
 
-#define RS_MIN_TILE 1024         // smallest tile any scan kernel uses (sizes the segment table)
+#define RS_MIN_TILE 512          // no scan kernel orders segments shorter than this (sizes the segment table)
+int64_t rs_kmer_work_bytes(int64_t n);   // workspace of the W <= 8 sequence scan (kmer_scan.cu)
+
+int rs_scan_seq_kmer(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold, int64_t cap,
+                     int64_t *d_hit_pos, float *d_hit_score, uint64_t *d_counters2, void *d_work, cudaStream_t st);

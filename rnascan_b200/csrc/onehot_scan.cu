@@ -241,6 +241,8 @@ static int scan_impl(const uint8_t *ca, const uint8_t *cb, int64_t n, const doub
     if (n < W) return RS_OK;
     WorkLayout wl = rs_work_layout(n, cap);
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+    if (A == 4 && !PAIR && W <= 8)       // exact k-mer decision table: one lookup decides 9-W positions
+        return rs_scan_seq_kmer(ca, n, ta, W, threshold, cap, d_hit_pos, d_hit_seq, d_counters2, d_work, st);
     OneHotParams prm = {};
     prm.codes_a = ca; prm.codes_b = cb; prm.n = n; prm.padded = rs_padded_count(n);
     prm.n_tiles = (n + OH_TILE - 1) / OH_TILE; prm.W = W; prm.threshold = threshold;
@@ -255,7 +257,8 @@ static int scan_impl(const uint8_t *ca, const uint8_t *cb, int64_t n, const doub
     if (PAIR) fill_table(prm.tb, tb, W, 7);
     rc = launch<A, PAIR, false>(prm, st);
     if (rc) return rc;
-    return rs_order_hits(prm.st, prm.n_tiles, d_hit_pos, d_hit_seq, d_hit_str, wk + wl.off_scan, st);
+    OrderDest od = {d_hit_pos, d_hit_seq, d_hit_str, nullptr, nullptr, 0};
+    return rs_order_hits(prm.st, prm.n_tiles, od, wk + wl.off_scan, st);
 }
 
 extern "C" int rs_scan_seq(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,

@@ -81,10 +81,12 @@ __global__ void __launch_bounds__(OR_THREADS) order_sum_kernel(const ulonglong2 
 
 // pass 2: exclusive offsets per tile, then copy each non-empty segment to its final place
 __global__ void __launch_bounds__(OR_THREADS) order_copy_kernel(HitStage st, int64_t n_tiles, const OrderTmp *tmp,
-                                                                int64_t *__restrict__ out_pos,
-                                                                float *__restrict__ out_seq,
-                                                                double *__restrict__ out_str)
+                                                                OrderDest od)
 {
+    int64_t *__restrict__ out_pos = od.pos;
+    float *__restrict__ out_seq = od.seq;
+    double *__restrict__ out_str = od.str;
+    const unsigned long long out_base = od.out_base ? *od.out_base : 0ull;
     const int64_t base = (int64_t)blockIdx.x * OR_CHUNK + (int64_t)threadIdx.x * OR_PER;
     ulonglong2 sg[OR_PER];
     unsigned long long s = 0;
@@ -98,19 +100,19 @@ __global__ void __launch_bounds__(OR_THREADS) order_copy_kernel(HitStage st, int
 #pragma unroll
     for (int k = 0; k < OR_PER; k++) {
         for (unsigned long long h = 0; h < sg[k].y; h++) {
-            const unsigned long long from = sg[k].x + h, to = dst + h;
+            const unsigned long long from = sg[k].x + h, to = out_base + dst + h;
             if ((int64_t)from < st.capacity && (int64_t)to < st.capacity) {
                 out_pos[to] = st.pos[from];
                 if (out_seq && st.seq) out_seq[to] = st.seq[from];
                 if (out_str && st.str) out_str[to] = st.str[from];
+                if (od.out_motif) od.out_motif[to] = od.motif_id;
             }
         }
         dst += sg[k].y;
     }
 }
 
-int rs_order_hits(const HitStage &st, int64_t n_tiles, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
-                  void *d_scan_tmp, cudaStream_t stream)
+int rs_order_hits(const HitStage &st, int64_t n_tiles, const OrderDest &dst, void *d_scan_tmp, cudaStream_t stream)
 {
     if (n_tiles <= 0) return RS_OK;
     const int n_blocks = (int)((n_tiles + OR_CHUNK - 1) / OR_CHUNK);
@@ -119,7 +121,7 @@ int rs_order_hits(const HitStage &st, int64_t n_tiles, int64_t *d_hit_pos, float
     order_sum_kernel<<<n_blocks, OR_THREADS, 0, stream>>>(st.tile_seg, n_tiles, tmp, n_blocks);
     RS_CUDA(cudaGetLastError());
     if (st.capacity > 0) {
-        order_copy_kernel<<<n_blocks, OR_THREADS, 0, stream>>>(st, n_tiles, tmp, d_hit_pos, d_hit_seq, d_hit_str);
+        order_copy_kernel<<<n_blocks, OR_THREADS, 0, stream>>>(st, n_tiles, tmp, dst);
         RS_CUDA(cudaGetLastError());
     }
     return RS_OK;

@@ -484,11 +484,12 @@ extern "C" int rs_scores_dense_profile(const void *d_profile, int profile_dtype,
                                    : launch_exact<double>(prm, (cudaStream_t)stream);
 }
 
-extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
-                             const double *seq_table, const double *struct_table, int W, double threshold,
-                             double profile_absrow_max, int mode, int64_t hit_capacity, int64_t *d_hit_pos,
-                             float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
-                             int64_t work_bytes, void *stream)
+static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                           const double *seq_table, const double *struct_table, int W, double threshold,
+                           double profile_absrow_max, int mode, int64_t hit_capacity, int64_t *d_hit_pos,
+                           float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
+                           int64_t work_bytes, void *stream, const unsigned long long *d_out_base,
+                           int32_t *d_hit_motif, int32_t motif_id)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_common(d_profile, profile_dtype, n, struct_table, W);
@@ -562,5 +563,59 @@ extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int 
         rc = profile_dtype == RS_F32 ? launch_exact<float>(prm, st) : launch_exact<double>(prm, st);
     }
     if (rc) return rc;
-    return rs_order_hits(prm.st, n_tiles, d_hit_pos, d_hit_seq, d_hit_struct, wk + wl.off_scan, st);
+    OrderDest od = {d_hit_pos, d_hit_seq, d_hit_struct, d_out_base, d_hit_motif, motif_id};
+    return rs_order_hits(prm.st, n_tiles, od, wk + wl.off_scan, st);
+}
+
+extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                             const double *seq_table, const double *struct_table, int W, double threshold,
+                             double profile_absrow_max, int mode, int64_t hit_capacity, int64_t *d_hit_pos,
+                             float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
+                             int64_t work_bytes, void *stream)
+{
+    return scan_fused_impl(d_codes, d_profile, profile_dtype, n, seq_table, struct_table, W, threshold,
+                           profile_absrow_max, mode, hit_capacity, d_hit_pos, d_hit_seq, d_hit_struct, d_counters2,
+                           d_work, work_bytes, stream, nullptr, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched many-PFM scan, CUDA-core path: one fused scan per motif over the same resident
+// streams; every motif's ordered hits are appended behind the previous motif's.
+__global__ void batched_base_kernel(unsigned long long *bases, const unsigned long long *counters2, int m)
+{
+    bases[m + 1] = bases[m] + counters2[2 * m];
+}
+
+extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                               int n_motifs, const int *widths, const double *seq_tables,
+                               const double *struct_tables, int table_stride_rows, double threshold,
+                               double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
+                               int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                               uint64_t *d_motif_counters2, uint64_t *d_bases, void *d_work, int64_t work_bytes,
+                               void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_motifs < 1 || !widths || !struct_tables || !d_motif_counters2 || !d_bases) {
+        rs_set_error("rs_scan_batched: bad argument"); return RS_ERR_INVALID;
+    }
+    if (table_stride_rows < 1 || table_stride_rows > RS_MAX_W) { rs_set_error("bad table_stride_rows"); return RS_ERR_INVALID; }
+    if (mode == RS_MODE_AND && !seq_tables) { rs_set_error("RS_MODE_AND needs sequence tables"); return RS_ERR_INVALID; }
+    if (hit_capacity > 0 && !d_hit_motif) { rs_set_error("null d_hit_motif"); return RS_ERR_INVALID; }
+    for (int m = 0; m < n_motifs; m++)
+        if (widths[m] < 1 || widths[m] > table_stride_rows) { rs_set_error("motif %d: width outside [1, stride]", m); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_bases, 0, sizeof(uint64_t) * (size_t)(n_motifs + 1), st));
+    RS_CUDA(cudaMemsetAsync(d_motif_counters2, 0, sizeof(uint64_t) * 2 * (size_t)n_motifs, st));
+    for (int m = 0; m < n_motifs; m++) {
+        const double *ts = seq_tables ? seq_tables + (size_t)m * table_stride_rows * 4 : nullptr;
+        const double *tq = struct_tables + (size_t)m * table_stride_rows * RS_CHANNELS;
+        int rc = scan_fused_impl(d_codes, d_profile, profile_dtype, n, ts, tq, widths[m], threshold,
+                                 profile_absrow_max, mode, hit_capacity, d_hit_pos, d_hit_seq, d_hit_struct,
+                                 d_motif_counters2 + 2 * m, d_work, work_bytes, stream,
+                                 (const unsigned long long *)d_bases + m, d_hit_motif, m);
+        if (rc) return rc;
+        batched_base_kernel<<<1, 1, 0, st>>>((unsigned long long *)d_bases,
+                                             (const unsigned long long *)d_motif_counters2, m);
+        RS_CUDA(cudaGetLastError());
+    }
+    return RS_OK;
 }

@@ -329,6 +329,59 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     return (pos, sq, st, resc) if return_stats else (pos, sq, st)
 
 
+def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity=None):
+    """Many motif pairs over the same resident streams (BASELINE config 5).
+
+    seq_tables: list of (W_m, 4) arrays or None (structure-only); struct_tables: list of
+    (W_m, 7) arrays.  Returns (motif int32[], pos int64[], seq float32[]|None, struct
+    float64[], bases int64[M+1]) with hits grouped by motif, ordered by position."""
+    M = len(struct_tables)
+    if M == 0:
+        raise ValueError("no motifs")
+    if seq_tables is not None and len(seq_tables) != M:
+        raise ValueError("sequence and structure motif lists differ in length")
+    tq = [_table(t, 7) for t in struct_tables]
+    widths = np.array([t.shape[0] for t in tq], dtype=np.int32)
+    stride = int(widths.max())
+    qs = np.zeros((M, stride, 7), np.float64)
+    for m, t in enumerate(tq):
+        qs[m, :t.shape[0]] = t
+    ss = None
+    if seq_tables is not None:
+        ss = np.zeros((M, stride, 4), np.float64)
+        for m, t in enumerate(seq_tables):
+            t = _table(t, 4)
+            if t.shape[0] != widths[m]:
+                raise ValueError("motif %d: sequence and structure widths differ" % m)
+            ss[m, :t.shape[0]] = t
+    if stream.n != profile.n:
+        raise ValueError("symbol stream and profile stream differ in length")
+    threshold = float(threshold)
+    if threshold == float("-inf"):
+        raise ValueError("scan_batched needs a finite threshold (use the dense entry points for -inf)")
+    mode = _lib.RS_MODE_STRUCT if ss is None else _lib.RS_MODE_AND
+    absmax = profile.absrow_max()
+    dev = stream.codes.device
+    cap = int(capacity) if capacity else max(1 << 16, stream.n // 64)
+    counters = torch.zeros(2 * M, dtype=torch.int64, device=dev)
+    bases = torch.zeros(M + 1, dtype=torch.int64, device=dev)
+    while True:
+        hb = HitBuffers(stream.n, cap, dev)
+        motif = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        check(lib.rs_scan_batched(_ptr(stream.codes), _ptr(profile.rows), profile.dtype, stream.n, M,
+                                  widths.ctypes.data, 0 if ss is None else ss.ctypes.data, qs.ctypes.data,
+                                  stride, threshold, absmax, mode, cap, _ptr(motif), _ptr(hb.pos),
+                                  _ptr(hb.seq), _ptr(hb.struct), _ptr(counters), _ptr(bases), _ptr(hb.work),
+                                  hb.work_bytes, _stream()))
+        b = bases.cpu().numpy()
+        total = int(b[-1])
+        if total <= cap:
+            return (motif[:total].cpu().numpy(), hb.pos[:total].cpu().numpy(),
+                    hb.seq[:total].cpu().numpy() if ss is not None else None,
+                    hb.struct[:total].cpu().numpy(), b)
+        cap = total
+
+
 # --------------------------------------------------------------------------- host-buffer pipeline
 class HostFusedScanner(object):
     """Combined sequence + averaged-profile scan of HOST-resident streams.

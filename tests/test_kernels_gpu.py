@@ -260,3 +260,95 @@ def test_bad_arguments(dev):
         dev.dense_seq(st, np.zeros((65, 4)))
     with pytest.raises(ValueError):
         dev.scan_seq(st, np.zeros((7, 4)), float("nan"))
+
+
+# ----------------------------------------------------------------------------- batched many-PFM scan
+@pytest.mark.parametrize("with_seq", [True, False])
+def test_scan_batched_matches_per_motif_oracle(dev, oracle, with_seq):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(555)
+    lengths = synth.record_lengths(400_000, 100, rng)
+    codes, off = synth.rna_codes(lengths, rng, n_frac=0.005)
+    rows = synth.profile_rows(len(codes), rng, lengths=lengths)
+    st, pf = dev.SymbolStream(codes, off, lengths), dev.ProfileStream(rows)
+    bg = [synth.SS_P[c] for c in "BEHLMRT"]
+    M = 9
+    widths = rng.integers(7, 13, size=M)
+    tq = [synth.pssm_table(synth.pfm_rows(int(w), 7, rng), background=bg) for w in widths]
+    ts = [synth.pssm_table(synth.pfm_rows(int(w), 4, rng)) for w in widths]
+    text = synth.to_text(codes, "rna")
+    thr = 0.5 if with_seq else 3.0
+    motif, pos, sq, sc, bases = dev.scan_batched(st, pf, ts if with_seq else None, tq, thr, capacity=128)
+    assert bases[0] == 0 and bases[-1] == len(pos) and np.all(np.diff(bases) >= 0)
+    total = 0
+    for m in range(M):
+        W = int(widths[m])
+        with np.errstate(all="ignore"):
+            b = oracle.profile_scores(rows, tq[m])
+        b[window_has_sep(codes, W)] = np.nan
+        keep = b > thr
+        if with_seq:
+            a = oracle.seq_scores(text, ts[m])
+            with np.errstate(invalid="ignore"):
+                keep &= a.astype(np.float64) > thr
+        want = np.nonzero(keep)[0]
+        lo, hi = int(bases[m]), int(bases[m + 1])
+        assert np.array_equal(pos[lo:hi], want), m
+        assert np.all(motif[lo:hi] == m)
+        assert_same_float(sc[lo:hi], b[want])
+        if with_seq:
+            assert_same_float(sq[lo:hi], a[want])
+        total += len(want)
+    assert total == len(pos) and total > 0
+
+
+# ----------------------------------------------------------------------------- k-mer decision-table scan (W <= 8)
+@pytest.mark.parametrize("W", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12])
+@pytest.mark.parametrize("q", ["q0.5", "q0.99", "q0.9999"])
+def test_scan_seq_all_widths(dev, oracle, W, q):
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 1_500_000, 400, seed=40 + W, n_frac=0.02)
+    rng = np.random.default_rng(140 + W)
+    pfm = synth.pfm_rows(W, 4, rng)
+    if W % 3 == 0:
+        pfm[pfm < 0.03] = 0.0                                   # -inf entries
+    tab = synth.pssm_table(pfm, pseudocount=0.0 if W % 3 == 0 else 0.01)
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+    thr = pick_threshold(want, q)
+    pos, sc = dev.scan_seq(st, tab, thr)
+    wpos = oracle.search_hits(want, thr)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 27, 28, 29, 35, 36, 7167, 7168, 7169, 7175, 14336 + 3, 3 * 7168])
+def test_scan_seq_kmer_tile_edges(dev, oracle, n):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(n)
+    codes = rng.integers(0, 4, size=n).astype(np.uint8)
+    if n > 40:
+        codes[rng.integers(0, n, size=3)] = 0x0C
+        codes[n // 2] = 0xFF
+    st = dev.SymbolStream(codes)
+    for W in (4, 7, 8):
+        tab = synth.pssm_table(synth.pfm_rows(W, 4, rng))
+        want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+        for thr in (-50.0, 0.0):
+            pos, sc = dev.scan_seq(st, tab, thr)
+            wpos = oracle.search_hits(want, thr)
+            assert np.array_equal(pos, wpos), (W, thr)
+            assert_same_float(sc, want[wpos])
+
+
+def test_scan_seq_threshold_equal_to_a_score(dev, oracle):
+    """Strict `>`: a window whose float32 score equals the threshold is not a hit."""
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 300_000, 80, seed=9)
+    rng = np.random.default_rng(19)
+    tab = synth.pssm_table(synth.pfm_rows(7, 4, rng))
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), tab)
+    finite = want[np.isfinite(want)]
+    thr = float(np.sort(finite)[-50])                           # exactly a score that occurs
+    pos, sc = dev.scan_seq(st, tab, thr)
+    wpos = oracle.search_hits(want, thr)
+    assert np.array_equal(pos, wpos) and not np.any(sc.astype(np.float64) == thr)
