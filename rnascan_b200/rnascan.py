@@ -86,7 +86,18 @@ def getoptions(argv=None):
 
 
 def eprint(*args, **kwargs):
-    print(*args, file=sys.stderr, **kwargs)
+    if _rank() == 0:                      # under torchrun only rank 0 talks
+        print(*args, file=sys.stderr, **kwargs)
+
+
+def _rank():
+    from . import shard
+    return shard.world()[0]
+
+
+def _world_size():
+    from . import shard
+    return shard.world()[1]
 
 
 ###############################################################################
@@ -190,13 +201,46 @@ def pfm2pssm(pfm_file, pseudocount, alphabet, background=None):
 # Packed record batches (host side of the device layout)
 ###############################################################################
 class _Batch(object):
-    """Records of one input packed into a symbol stream resident in HBM."""
+    """Records (or, when the input is sharded over ranks, pieces of records) of one input
+    packed into a symbol stream resident in HBM.
 
-    def __init__(self, ids, descriptions, texts, kind):
+    ids/descriptions describe ALL records of the batch's input range; `record` maps each
+    packed text to its record, `piece_start` is its offset inside that record and `own`
+    the number of leading window starts / symbols this rank owns (shard.plan_shards)."""
+
+    def __init__(self, ids, descriptions, texts, kind, record=None, piece_start=None, own=None,
+                 full_texts=None):
         from . import device
         self.ids, self.descriptions, self.texts, self.kind = ids, descriptions, texts, kind
+        self.full_texts = texts if full_texts is None else full_texts     # one per record
+        n = len(texts)
+        self.record = np.arange(n, dtype=np.int64) if record is None else np.asarray(record, np.int64)
+        self.piece_start = np.zeros(n, np.int64) if piece_start is None else np.asarray(piece_start, np.int64)
+        self.own = None if own is None else np.asarray(own, np.int64)
         self.stream = device.SymbolStream.from_texts(texts, kind)
         self._raw = None
+
+    def overlap_counts(self):
+        """Counts (int64[8]) of the symbols this rank holds but does not own (the overlap
+        tails of split records); the device histogram minus these is the owned count."""
+        counts = np.zeros(8, np.int64)
+        if self.own is None:
+            return counts
+        host = self.stream.host_codes()
+        for k in np.nonzero(self.own < self.stream.lengths)[0]:
+            a = self.stream.offsets[k] + self.own[k]
+            tail = host[a:self.stream.offsets[k] + self.stream.lengths[k]]
+            counts += np.bincount(tail[tail < 8], minlength=8)[:8]
+        return counts
+
+    def locate(self, pos):
+        """stream positions -> (keep mask, record index, 0-based start in the record)."""
+        if len(pos) == 0:
+            z = np.zeros(0, np.int64)
+            return np.zeros(0, bool), z, z
+        piece, start = self.stream.locate(pos)
+        keep = np.ones(len(pos), bool) if self.own is None else start < self.own[piece]
+        return keep, self.record[piece], start + self.piece_start[piece]
 
     def __len__(self):
         return len(self.texts)
@@ -214,8 +258,29 @@ def _kind_of(alphabet):
     return "rna" if _seq.is_nucleotide_alphabet(alphabet) else "struct"
 
 
+def _sharded_batch(fasta_file, alphabet, rank, size):
+    """This rank's share of the input: contiguous pieces balanced by total length, split
+    records overlapping by RS_MAX_W - 1 symbols (enough for any motif width)."""
+    from . import shard, _lib
+    ids, descs, texts = [], [], []
+    for rec in parse_sequences(fasta_file):
+        ids.append(rec.id)
+        descs.append(rec.description)
+        texts.append(str(preprocess_seq(rec, alphabet)))
+    plan = shard.plan_shards([len(t) for t in texts], size, _lib.RS_MAX_W)
+    mine = plan[rank]
+    piece_texts = [texts[r][a:b] for (r, a, b, o) in mine]
+    own = [(b if o >= b else o) - a for (r, a, b, o) in mine]
+    return _Batch(ids, descs, piece_texts, _kind_of(alphabet), record=[p[0] for p in mine],
+                  piece_start=[p[1] for p in mine], own=own, full_texts=texts)
+
+
 def _record_batches(fasta_file, alphabet, max_symbols=None):
     """Parse + preprocess a FASTA input and yield _Batch objects of bounded size."""
+    size = _world_size()
+    if size > 1:
+        yield _sharded_batch(fasta_file, alphabet, _rank(), size)
+        return
     max_symbols = max_symbols or MAX_BATCH_SYMBOLS
     ids, descs, texts, size = [], [], [], 0
     for rec in parse_sequences(fasta_file):
@@ -385,8 +450,24 @@ def _scan_batch(batch, pm, kind, minscore):
         pos, scores = device.scan_seq(batch.stream, table, minscore)
     else:
         pos, scores = device.scan_struct_onehot(batch.stream, table, minscore)
-    rec, start0 = batch.stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
-    return pos, rec, start0, scores
+    keep, rec, start0 = batch.locate(pos)
+    return pos[keep], rec[keep], start0[keep], scores[keep]
+
+
+def _gather_parts(parts, n_records, ids, descs):
+    """Under torchrun: concatenate every rank's hit arrays on rank 0 in rank order (= record
+    order, shard.plan_shards); other ranks get None."""
+    from . import shard
+    if _world_size() == 1:
+        return parts
+    rec = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.int64)
+    start0 = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
+    scores = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0)
+    frags = [f for p in parts for f in p[3]]
+    gathered = shard.gather_objects((rec, start0, scores, frags))
+    if gathered is None:
+        return None
+    return [(g[0], g[1], g[2], g[3], ids, descs) for g in gathered]
 
 
 def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
@@ -405,7 +486,14 @@ def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
             pos, rec, start0, scores = pos[keep], rec[keep], start0[keep], scores[keep]
         parts.append((rec + n_records, start0, scores, _fragments(batch.raw(), pos, width),
                       batch.ids, batch.descriptions))
-        n_records += len(batch)
+        n_records += len(batch.ids)
+    if _world_size() > 1:
+        ids0 = parts[0][4] if parts else []
+        descs0 = parts[0][5] if parts else []
+        parts = _gather_parts(parts, n_records, ids0, descs0)
+        if parts is None:
+            return pd.DataFrame(), n_records          # not rank 0: nothing to assemble or print
+        parts = [parts[0]] + [(p[0], p[1], p[2], p[3], [], []) for p in parts[1:]]
     if n_records == 0:
         return pd.DataFrame(), 0
     rec = np.concatenate([p[0] for p in parts])
@@ -438,7 +526,8 @@ def _cached_batches(fasta_file, alphabet):
         return _BATCH_CACHE[key]
     batches = list(_record_batches(fasta_file, alphabet))
     if key is not None:
-        _BATCH_CACHE.clear()
+        while len(_BATCH_CACHE) >= 2:                      # sequence + structure input of one run
+            _BATCH_CACHE.pop(next(iter(_BATCH_CACHE)))
         if sum(b.stream.n for b in batches) <= MAX_BATCH_SYMBOLS:
             _BATCH_CACHE[key] = batches
     return batches
@@ -454,12 +543,19 @@ def _profile_files(directory):
 def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None):
     """All ``structure.<id>.txt`` profiles of a directory in one launch (rnascan.py:348-375).
     With `seq_batches`/`seq_pm` (combined mode) the sequence PSSM is evaluated in the same
-    kernel and only windows passing BOTH thresholds come back."""
-    from . import device
+    kernel and only windows passing BOTH thresholds come back.  Under torchrun every rank
+    takes a contiguous range of files balanced by size; rank 0 assembles the frame."""
+    from . import device, shard
     motif_id, pm = _first_motif(pssm)
     tq = _structure_table(pm)
     width = tq.shape[0]
     files = _profile_files(directory)
+    n_files = len(files)
+    rank, size = shard.world()
+    if size > 1:
+        sizes = [os.path.getsize(f) for f in files]
+        plan = shard.plan_shards(sizes, size, 1)[rank]     # W = 1: whole files only
+        files = [files[r] for (r, a, b, o) in plan if a == 0]
     names = []
     for path in files:
         match = re.search(r"^structure\.(.*)\.txt$", os.path.basename(path))
@@ -472,34 +568,49 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     codes = np.zeros(int(lengths.sum() + len(profiles)), np.uint8)
     seq_table = None
     if seq_batches is not None:
-        # sequence symbols of the record with the same id, aligned row by row
+        # sequence symbols of the record with the same id, aligned row by row; rows beyond the
+        # shorter of the two get an invalid symbol (no joint window exists there)
         by_id = {}
         for batch in seq_batches:
-            host = batch.stream.host_codes()
-            for k, rid in enumerate(batch.ids):
-                by_id.setdefault(rid, host[batch.stream.offsets[k]:batch.stream.offsets[k] + batch.stream.lengths[k]])
+            for rid, text in zip(batch.ids, batch.full_texts):
+                by_id.setdefault(rid, text)
         seq_table = _table_for(seq_pm, "rna")
         for k, name in enumerate(names):
-            sym = by_id.get(name)
-            if sym is None or len(sym) != lengths[k]:
-                codes[offsets[k]:offsets[k] + lengths[k]] = device._lib.RS_RNA_OTHER   # no joint hit possible
-            else:
-                codes[offsets[k]:offsets[k] + lengths[k]] = sym
-    codes[offsets + lengths] = device._lib.RS_SEP
-    stream = device.SymbolStream(codes, offsets, lengths)
-    profile = device.ProfileStream(device.pack_profiles(profiles, dtype=np.float64))
-    pos, _, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
-    rec, start0 = stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
-    n = len(pos)
+            seg = codes[offsets[k]:offsets[k] + lengths[k]]
+            seg[:] = device._lib.RS_RNA_OTHER
+            text = by_id.get(name)
+            if text is not None:
+                sym = device.pack_texts([text], "rna")[0][:-1]
+                m = min(len(sym), len(seg))
+                seg[:m] = sym[:m]
+    if len(profiles):
+        codes[offsets + lengths] = device._lib.RS_SEP
+    if len(codes):
+        stream = device.SymbolStream(codes, offsets, lengths)
+        profile = device.ProfileStream(device.pack_profiles(profiles, dtype=np.float64))
+        pos, _, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
+        rec, start0 = stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    else:
+        rec = start0 = np.zeros(0, np.int64)
+        scores = np.zeros(0, np.float64)
+    hit_names = [names[r] for r in rec.tolist()]
+    if size > 1:
+        gathered = shard.gather_objects((hit_names, start0, scores))
+        if gathered is None:
+            return pd.DataFrame(), n_files
+        hit_names = [x for g in gathered for x in g[0]]
+        start0 = np.concatenate([g[1] for g in gathered])
+        scores = np.concatenate([g[2] for g in gathered])
+    n = len(hit_names)
     frame = pd.DataFrame({
-        "Sequence_ID": np.array(names, dtype=object)[rec] if n else np.array([], dtype=object),
+        "Sequence_ID": np.array(hit_names, dtype=object),
         "Description": np.array([""] * n, dtype=object),
         "Motif_ID": np.array([motif_id] * n, dtype=object),
         "Start": (start0 + 1).astype(object), "End": (start0 + width).astype(object),
         "Sequence": np.array(["."] * n, dtype=object),
         "LogOdds": np.asarray(scores, dtype=np.float64).astype(object),
     })
-    return frame, len(files)
+    return frame, n_files
 
 
 def scan_main(fasta_file, pssm, alphabet, bg, args):
@@ -557,8 +668,8 @@ def compute_background(fastas, alphabet, verbose=True):
     counts = np.zeros(8, dtype=np.int64)
     n_records = 0
     for batch in _cached_batches(fastas, alphabet):
-        counts += device.histogram(batch.stream).cpu().numpy()
-        n_records += len(batch)
+        counts += device.histogram(batch.stream).cpu().numpy() - batch.overlap_counts()
+        n_records += len(batch.ids)
     counts = _allreduce_counts(counts)
     content = defaultdict(int)
     total = len(alphabet.letters)
@@ -637,15 +748,22 @@ def _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, ar
     parts, n_records = [], 0
     for sb, qb in zip(seq_batches, struct_batches):
         pos, _, scores = device.scan_pair_onehot(sb.stream, qb.stream, ts, tq, args.minscore)
-        rec, start0 = qb.stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
-        parts.append((rec + n_records, start0, scores, _fragments(qb.raw(), pos, width)))
-        n_records += len(qb)
+        keep, rec, start0 = qb.locate(pos)
+        pos = pos[keep]
+        parts.append((rec[keep] + n_records, start0[keep], scores[keep], _fragments(qb.raw(), pos, width),
+                      qb.ids, qb.descriptions))
+        n_records += len(qb.ids)
     eprint("Processed %d sequences" % n_records)
+    if _world_size() > 1:
+        parts = _gather_parts(parts, n_records, parts[0][4] if parts else [], parts[0][5] if parts else [])
+        if parts is None:
+            return pd.DataFrame()
+        parts = [parts[0]] + [(p[0], p[1], p[2], p[3], [], []) for p in parts[1:]]
     if n_records == 0:
         return pd.DataFrame()
     rec = np.concatenate([p[0] for p in parts])
-    ids = [i for b in struct_batches for i in b.ids]
-    descs = [d for b in struct_batches for d in b.descriptions]
+    ids = [i for p in parts for i in p[4]]
+    descs = [d for p in parts for d in p[5]]
     frame = _assemble_fasta_frame(n_records, rec, ids, descs, motif_id,
                                   np.concatenate([p[1] for p in parts]), width,
                                   [f for p in parts for f in p[3]],
@@ -655,6 +773,8 @@ def _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, ar
 
 def main(argv=None):
     tic = time.time()
+    from . import shard
+    rank, _ = shard.init()                # joins the torchrun rendezvous if there is one
     args = getoptions(argv)
     seq_type = _guess_seq_type(args)
     bg = None
@@ -672,7 +792,8 @@ def main(argv=None):
             seq_file = args.fastafiles[0]
             bg = load_background(args.bg_seq, args.uniform_background, seq_file, rna, not args.bgonly)
         if args.bgonly:
-            print(dict(bg))
+            if rank == 0:
+                print(dict(bg))
             sys.exit()
         seq_pssm = load_motif(args.pfm_seq, args.pseudocount, rna, bg)
         seq_results = scan_main(seq_file, seq_pssm, rna, bg, args)
@@ -689,7 +810,8 @@ def main(argv=None):
             bg = load_background(args.bg_struct, args.uniform_background, struct_file, structure,
                                  not args.bgonly)
         if args.bgonly:
-            print(dict(bg))
+            if rank == 0:
+                print(dict(bg))
             sys.exit()
         struct_pssm = load_motif(args.pfm_struct, args.pseudocount, structure, bg)
         struct_results = None
@@ -698,14 +820,17 @@ def main(argv=None):
         if struct_results is None:
             struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
 
-    if seq_type == "RNASS":
+    if rank != 0:
+        final = None
+    elif seq_type == "RNASS":
         final = combine(seq_results, struct_results)
     elif seq_type == "RNA":
         final = seq_results
     else:
         final = struct_results
-    _add_match_id(final)
-    final.to_csv(sys.stdout, sep="\t", index=False)
+    if rank == 0:
+        _add_match_id(final)
+        final.to_csv(sys.stdout, sep="\t", index=False)
 
     runtime = float(time.time() - tic)
     if runtime > 60:

@@ -33,3 +33,70 @@ def test_api_host_logic_against_golden(fn, in_repo, golden_api, capsys, monkeypa
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         _call(fn, in_repo=in_repo, golden_api=golden_api, capsys=capsys)
+
+
+# ----------------------------------------------------------------------------- two ranks (gloo)
+_RANK_WORKER = r"""
+import contextlib, io, json, os, sys, warnings
+sys.path.insert(0, %(repo)r)
+sys.path.insert(0, os.path.join(%(repo)r, "tests"))
+os.chdir(%(repo)r)
+import oracle_backend
+from rnascan_b200 import rnascan as ms, shard
+
+
+class Patch(object):
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+oracle_backend.install(Patch())
+rank, size = shard.init("gloo")
+cases = json.load(open("tests/golden/cli/cases.json"))
+bad = []
+for name in %(names)r:
+    ms._BATCH_CACHE.clear()
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            ms.main(list(cases[name]["argv"]))
+        except SystemExit:
+            pass
+    if rank == 0:
+        want = open("tests/golden/cli/%%s.stdout" %% name).read()
+        lines = [l for l in err.getvalue().splitlines() if "seconds" not in l and "minutes" not in l]
+        if out.getvalue() != want or lines != cases[name]["stderr_lines"]:
+            bad.append(name)
+    elif out.getvalue() or err.getvalue():
+        bad.append(name + ":rank%%d-wrote-output" %% rank)
+import torch.distributed as dist
+allbad = [None] * size
+dist.all_gather_object(allbad, bad)
+if rank == 0:
+    print(json.dumps({"bad": [b for part in allbad for b in part], "size": size}))
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_cli_sharded_over_ranks_matches_golden(tmp_path, nproc):
+    """torchrun with 2 and 3 ranks (gloo): records are split over ranks (rec6 of mixed.fa is cut
+    with an overlap), counts are all-reduced, rank 0 prints -- output identical to one process."""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ["rna_mixed_all", "rna_mixed_pc", "rna_bgonly", "rna_test_default", "ss_mixed_all", "ss_mixed_thr",
+             "ss_bgonly", "rnass_fasta_all", "rnass_fasta_thr", "rna_empty_fasta", "rna_nohits",
+             "rna_example_bg_all"]
+    script = tmp_path / "rank_worker.py"
+    script.write_text(_RANK_WORKER % {"repo": repo, "names": names})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1", "--master-port",
+                          str(29540 + nproc), str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res == {"bad": [], "size": nproc}
