@@ -261,6 +261,9 @@ def run_b200(args):
         c5_motif = torch.empty(hb.capacity, dtype=torch.int32, device=device)
         c5_counters = torch.zeros(2 * N_MOTIFS_C5, dtype=torch.int64, device=device)
         c5_bases = torch.zeros(N_MOTIFS_C5 + 1, dtype=torch.int64, device=device)
+        hb.work_bytes = int(lib.rs_scan_batched_workspace_bytes(n, N_MOTIFS_C5, int(c5_widths.max()), hb.capacity))
+        hb.work = torch.empty(hb.work_bytes, dtype=torch.uint8, device=device)
+        check(lib.rs_set_batched_path({"auto": 0, "cuda": 1, "tensor": 2}[args.c5_path]))
     launches = [0]
 
     def all_reduce(t):
@@ -312,7 +315,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches[0] = 0
-    per_step = N_MOTIFS_C5 if wl == "c5" else 1
+    per_step = N_MOTIFS_C5 if wl == "c5" else 1      # upper bound on profiled launches per step
     check(lib.rs_prof_begin(max(args.steps, 1) * per_step))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -378,8 +381,7 @@ def run_b200(args):
         "data": "synthetic (SURVEY.md 8d shapes; generated on device, seed 4000+rank)",
         "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile, fused AND scan",
                                 "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, dense f64 output",
-                                "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure, CUDA-core path "
-                                      "(one fused scan per motif)" % N_MOTIFS_C5}[wl],
+                                "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure" % N_MOTIFS_C5}[wl],
                    "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
                    "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
                    "background": "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step",
@@ -399,9 +401,26 @@ def run_b200(args):
         out["hits_rank0"] = hits
     if wl == "c5":
         out["motif_positions_per_s"] = out["value"] * N_MOTIFS_C5
-        out["roofline"]["note"] = ("CUDA-core path re-reads the streams once per motif: physical traffic is %d x the "
-                                   "algorithmic 29 B/position; the tensor-core (windows x motifs GEMM) path is the "
-                                   "replacement" % N_MOTIFS_C5)
+        took = int(lib.rs_last_batched_path())
+        out["config"]["c5_path"] = {1: "cuda-core loop (one fused scan per motif)", 2: "tcgen05 GEMM filter + exact re-score"}[took]
+        if took == 2:
+            # 2 * 96 (K, padded window x 8 channels) * 256 motifs flop per position on the tensor cores
+            flops = 2.0 * 96 * 256 * positions
+            tf = flops / (kernel_ms * 1e-3) / 1e12
+            try:
+                with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+                    tpeak = float(json.load(fh)["bf16_tflops_sustained"])
+                src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+            except Exception:
+                tpeak, src = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+            out["roofline"] = {"bound": "tensor", "kernel": "batched_tc_kernel", "achieved": tf, "peak": tpeak,
+                               "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": src,
+                               "flop_per_position": 2.0 * 96 * 256, "kernel_ms": kernel_ms,
+                               "kernel_share_of_step": kernel_ms / ms_step, "traffic": None,
+                               "hbm_GBps_algorithmic": 29.0 * positions / (kernel_ms * 1e-3) / 1e9}
+        else:
+            out["roofline"]["note"] = ("CUDA-core path re-reads the streams once per motif: physical traffic is %d x "
+                                       "the algorithmic 29 B/position" % N_MOTIFS_C5)
     if e2e:
         out["e2e"] = {"value": all_positions / (ms_e2e * 1e-3) / 1e9, "unit": "Gpos/s",
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -526,6 +545,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--n-per-gpu", type=int, default=125_000_000, dest="n_per_gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5-path", default="auto", choices=["auto", "cuda", "tensor"], dest="c5_path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -153,6 +153,13 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
  * hit_capacity the excess was dropped: re-run with a larger buffer); d_motif_counters2[2m]
  * = hits of motif m, [2m+1] = windows re-scored exactly for motif m.
  * Semantics per motif are exactly rs_scan_fused's.                                        */
+int64_t rs_scan_batched_workspace_bytes(int64_t n, int n_motifs, int table_stride_rows,
+                                        int64_t hit_capacity);
+/* 0 = choose (tensor cores from 32 motifs on, fp32 profiles, W <= 12), 1 = per-motif CUDA-core
+ * loop, 2 = tensor cores or RS_ERR_INVALID.  Both paths return identical results.  The tensor-core
+ * path synchronises the stream (candidate counts decide the size of the exact pass).          */
+int rs_set_batched_path(int path);
+int rs_last_batched_path(void);          /* 1 or 2: the path the last rs_scan_batched call took */
 int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
                     int n_motifs, const int *widths, const double *seq_tables,
                     const double *struct_tables, int table_stride_rows, double threshold,

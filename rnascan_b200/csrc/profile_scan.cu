@@ -581,6 +581,23 @@ extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int 
 // ------------------------------------------------------------------------------------------------
 // Batched many-PFM scan, CUDA-core path: one fused scan per motif over the same resident
 // streams; every motif's ordered hits are appended behind the previous motif's.
+static int g_batched_path = 0;       // 0 auto, 1 CUDA-core loop, 2 tensor cores (error if not applicable)
+static int g_batched_last = 0;       // path the last rs_scan_batched call actually took (1 or 2)
+extern "C" int rs_last_batched_path(void) { return g_batched_last; }
+extern "C" int rs_set_batched_path(int path)
+{
+    if (path < 0 || path > 2) { rs_set_error("rs_set_batched_path: 0, 1 or 2"); return RS_ERR_INVALID; }
+    g_batched_path = path;
+    return RS_OK;
+}
+extern "C" int64_t rs_scan_batched_workspace_bytes(int64_t n, int n_motifs, int table_stride_rows,
+                                                   int64_t hit_capacity)
+{
+    const int64_t a = rs_work_layout(n, hit_capacity).total;
+    const int64_t b = rs_batched_tc_work_bytes(n, n_motifs, table_stride_rows, hit_capacity);
+    return a > b ? a : b;
+}
+
 __global__ void batched_base_kernel(unsigned long long *bases, const unsigned long long *counters2, int m)
 {
     bases[m + 1] = bases[m] + counters2[2 * m];
@@ -603,6 +620,20 @@ extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, in
     if (hit_capacity > 0 && !d_hit_motif) { rs_set_error("null d_hit_motif"); return RS_ERR_INVALID; }
     for (int m = 0; m < n_motifs; m++)
         if (widths[m] < 1 || widths[m] > table_stride_rows) { rs_set_error("motif %d: width outside [1, stride]", m); return RS_ERR_INVALID; }
+    // Tensor-core path (batched_tc.cu): worth it from a few dozen motifs on; needs fp32 profiles
+    // and W <= 12.  It answers -1 when it does not apply, then the per-motif loop below runs.
+    if (g_batched_path != 1 && profile_dtype == RS_F32 && (n_motifs >= 32 || g_batched_path == 2) && n >= 1) {
+        if (!d_codes || !d_profile || ((uintptr_t)d_codes & 15) || ((uintptr_t)d_profile & 15)) {
+            rs_set_error("codes/profile pointer null or not 16-byte aligned"); return RS_ERR_INVALID;
+        }
+        int rc = rs_scan_batched_tc(d_codes, d_profile, n, n_motifs, widths, seq_tables, struct_tables,
+                                    table_stride_rows, threshold, profile_absrow_max, mode, hit_capacity,
+                                    d_hit_motif, d_hit_pos, d_hit_seq, d_hit_struct, d_motif_counters2, d_bases,
+                                    d_work, work_bytes, st);
+        if (rc >= 0) { g_batched_last = 2; return rc; }
+        if (g_batched_path == 2) return RS_ERR_INVALID;      // rs_last_error() says why it does not apply
+    }
+    g_batched_last = 1;
     RS_CUDA(cudaMemsetAsync(d_bases, 0, sizeof(uint64_t) * (size_t)(n_motifs + 1), st));
     RS_CUDA(cudaMemsetAsync(d_motif_counters2, 0, sizeof(uint64_t) * 2 * (size_t)n_motifs, st));
     for (int m = 0; m < n_motifs; m++) {

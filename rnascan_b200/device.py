@@ -329,7 +329,7 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     return (pos, sq, st, resc) if return_stats else (pos, sq, st)
 
 
-def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity=None):
+def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity=None, path=0):
     """Many motif pairs over the same resident streams (BASELINE config 5).
 
     seq_tables: list of (W_m, 4) arrays or None (structure-only); struct_tables: list of
@@ -365,8 +365,11 @@ def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity
     cap = int(capacity) if capacity else max(1 << 16, stream.n // 64)
     counters = torch.zeros(2 * M, dtype=torch.int64, device=dev)
     bases = torch.zeros(M + 1, dtype=torch.int64, device=dev)
+    check(lib.rs_set_batched_path(int(path)))
     while True:
         hb = HitBuffers(stream.n, cap, dev)
+        hb.work_bytes = int(lib.rs_scan_batched_workspace_bytes(stream.n, M, stride, cap))
+        hb.work = torch.empty(hb.work_bytes, dtype=torch.uint8, device=dev)
         motif = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
         check(lib.rs_scan_batched(_ptr(stream.codes), _ptr(profile.rows), profile.dtype, stream.n, M,
                                   widths.ctypes.data, 0 if ss is None else ss.ctypes.data, qs.ctypes.data,
@@ -376,6 +379,7 @@ def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity
         b = bases.cpu().numpy()
         total = int(b[-1])
         if total <= cap:
+            lib.rs_set_batched_path(0)
             return (motif[:total].cpu().numpy(), hb.pos[:total].cpu().numpy(),
                     hb.seq[:total].cpu().numpy() if ss is not None else None,
                     hb.struct[:total].cpu().numpy(), b)

@@ -263,22 +263,37 @@ def test_bad_arguments(dev):
 
 
 # ----------------------------------------------------------------------------- batched many-PFM scan
+@pytest.mark.parametrize("path,M,zero", [(1, 9, False), (2, 9, False), (2, 40, True), (2, 300, False)],
+                         ids=["cuda-core", "tensor-core", "tensor-core-inf-tables", "tensor-core-two-groups"])
 @pytest.mark.parametrize("with_seq", [True, False])
-def test_scan_batched_matches_per_motif_oracle(dev, oracle, with_seq):
+def test_scan_batched_matches_per_motif_oracle(dev, oracle, with_seq, path, M, zero):
+    """rs_scan_batched, CUDA-core loop (path 1) and tcgen05 GEMM filter + exact re-score (path 2):
+    both must reproduce, per motif, exactly what the oracle gives for that motif alone."""
     from rnascan_b200 import synth
-    rng = np.random.default_rng(555)
-    lengths = synth.record_lengths(400_000, 100, rng)
+    rng = np.random.default_rng(555 + M)
+    lengths = synth.record_lengths(100_000 if zero else (400_000 if M < 100 else 150_000), 100, rng)
     codes, off = synth.rna_codes(lengths, rng, n_frac=0.005)
     rows = synth.profile_rows(len(codes), rng, lengths=lengths)
+    if zero:
+        rows = rows.astype(np.float64)
+        rows[rows < 0.08] = 0.0
+        rows = (rows / np.maximum(rows.sum(axis=1, keepdims=True), 1e-300)).astype(np.float32)
     st, pf = dev.SymbolStream(codes, off, lengths), dev.ProfileStream(rows)
     bg = [synth.SS_P[c] for c in "BEHLMRT"]
-    M = 9
     widths = rng.integers(7, 13, size=M)
-    tq = [synth.pssm_table(synth.pfm_rows(int(w), 7, rng), background=bg) for w in widths]
+    widths[0], widths[-1] = 12, 1 if not zero else 7
+    tq = []
+    for w in widths:
+        pfm = synth.pfm_rows(int(w), 7, rng)
+        if zero:
+            pfm[pfm < 0.05] = 0.0
+        tq.append(synth.pssm_table(pfm, background=bg, pseudocount=0.0 if zero else 0.01))
     ts = [synth.pssm_table(synth.pfm_rows(int(w), 4, rng)) for w in widths]
     text = synth.to_text(codes, "rna")
-    thr = 0.5 if with_seq else 3.0
-    motif, pos, sq, sc, bases = dev.scan_batched(st, pf, ts if with_seq else None, tq, thr, capacity=128)
+    thr = -3.0 if zero else (0.5 if with_seq else 3.0)
+    # -inf table rows only give a loose upper bound to the tensor-core filter: allow many candidates
+    motif, pos, sq, sc, bases = dev.scan_batched(st, pf, ts if with_seq else None, tq, thr,
+                                                 capacity=(1 << 20) if (zero or M > 256) else 128, path=path)
     assert bases[0] == 0 and bases[-1] == len(pos) and np.all(np.diff(bases) >= 0)
     total = 0
     for m in range(M):
@@ -300,6 +315,7 @@ def test_scan_batched_matches_per_motif_oracle(dev, oracle, with_seq):
             assert_same_float(sq[lo:hi], a[want])
         total += len(want)
     assert total == len(pos) and total > 0
+    assert dev.lib.rs_last_batched_path() == path
 
 
 # ----------------------------------------------------------------------------- k-mer decision-table scan (W <= 8)
