@@ -80,6 +80,10 @@ int rs_prof_end(float *ms_out, int capacity, int *n_records);
 int rs_host_encode_rna(const uint8_t *text, int64_t n, uint8_t *codes);
 int rs_host_encode_struct(const uint8_t *text, int64_t n, uint8_t *codes);
 
+/* log2(p / b) tables in the arithmetic of Python's math.log(p / b, 2) as Biopython's log_odds
+ * uses it (called at rnascan.py:248): prob, out [W][A] row-major, bg [A] normalised.        */
+int rs_host_log_odds(const double *prob, const double *bg, int W, int A, double *out);
+
 /* ---- background counts (replaces the Seq.count loop of rnascan.py:450-453) ---------
  * d_counts8[k] += number of symbols with index k and bit 3 clear (k = 0..7); exact
  * integers.  The caller zeroes d_counts8 first (so shards can accumulate).            */

@@ -41,6 +41,7 @@ _SIGS = {
     "rs_prof_end": ([_vp, _int, _vp], _int),
     "rs_host_encode_rna": ([_vp, _i64, _vp], _int),
     "rs_host_encode_struct": ([_vp, _i64, _vp], _int),
+    "rs_host_log_odds": ([_vp, _vp, _int, _int, _vp], _int),
     "rs_hist": ([_vp, _i64, _vp, _vp], _int),
     "rs_scores_dense_seq": ([_vp, _i64, _vp, _int, _vp, _vp], _int),
     "rs_scores_dense_struct": ([_vp, _i64, _vp, _int, _vp, _vp], _int),

@@ -321,20 +321,22 @@ __device__ __forceinline__ bool tc_exact(const RescoreParams &prm, int m, int64_
 {
     const int W = prm.widths[m];
     if (pos + W > prm.n) return false;
-    const double s = rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS,
-                                                    prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS, W);
-    str_out = s;
-    if (!(s > prm.threshold)) return false;
+    seq_out = 0.f;
     if (prm.mode == RS_MODE_AND) {
+        // the sequence condition first: W byte gathers, and it rejects ~99.7 % of the structure candidates
         double qd;
         if (!rs_exact_onehot_window<4, 4>(prm.codes + pos, prm.seq_tables + (size_t)m * prm.stride_rows * 4, W, qd))
             return false;
-        const float qf = (float)qd;
+        const float qf = (float)qd;                                  // _pwm.c:65
         seq_out = qf;
-        return (double)qf > prm.threshold;
+        if (!((double)qf > prm.threshold)) return false;             // SURVEY.md note N1
+    } else if (!rs_no_separator(prm.codes + pos, W)) {
+        return false;
     }
-    seq_out = 0.f;
-    return rs_no_separator(prm.codes + pos, W);
+    const double s = rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS,
+                                                    prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS, W);
+    str_out = s;
+    return s > prm.threshold;
 }
 
 __global__ void batched_rescore_kernel(const RescoreParams prm)

@@ -6,6 +6,7 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 #include "../../include/rnascan_b200.h"
 
 namespace {
@@ -47,5 +48,24 @@ extern "C" int rs_host_encode_struct(const uint8_t *text, int64_t n, uint8_t *co
 {
     if (n < 0 || (n > 0 && (!text || !codes))) return RS_ERR_INVALID;
     run(text, n, codes, g_luts.ss);
+    return RS_OK;
+}
+
+// log2-odds of a normalised PFM against a background, in the arithmetic of CPython's
+// math.log(p / b, 2) = log(p / b) / log(2.0) (Biopython log_odds, called at rnascan.py:248):
+// p == 0 -> -inf; b == 0 -> +inf (p > 0) or NaN.  prob and out are [W][A] row-major, bg is [A]
+// (already normalised to sum 1 by the caller, as Biopython does).
+extern "C" int rs_host_log_odds(const double *prob, const double *bg, int W, int A, double *out)
+{
+    if (!prob || !bg || !out || W < 0 || A < 1) return RS_ERR_INVALID;
+    const double ln2 = std::log(2.0);
+    for (int i = 0; i < W; i++)
+        for (int a = 0; a < A; a++) {
+            const double p = prob[i * A + a], b = bg[a];
+            double v;
+            if (b > 0) v = p > 0 ? std::log(p / b) / ln2 : -INFINITY;
+            else       v = p > 0 ? INFINITY : NAN;
+            out[i * A + a] = v;
+        }
     return RS_OK;
 }

@@ -80,3 +80,18 @@ class Motif(object):
     def pssm(self, pseudocount=0, background=None):
         letters = self.alphabet.letters
         return log_odds(normalize_counts(self.counts, letters, pseudocount), letters, background)
+
+
+def log_odds_table(prob_rows, background_row):
+    """Array version of `log_odds` for many motifs per call (the batched scan): `prob_rows` is a
+    (W, A) array of probabilities, `background_row` an (A,) array already normalised to sum 1.
+    Computed by the library's host helper in the same arithmetic as math.log(p / b, 2), so the
+    result is bit-identical to `log_odds` (tests/test_host_cpu.py checks it)."""
+    import numpy as np
+    from . import _lib
+    prob = np.ascontiguousarray(prob_rows, dtype=np.float64)
+    bg = np.ascontiguousarray(background_row, dtype=np.float64)
+    out = np.empty_like(prob)
+    _lib.check(_lib.lib.rs_host_log_odds(prob.ctypes.data, bg.ctypes.data, prob.shape[0], prob.shape[1],
+                                         out.ctypes.data))
+    return out

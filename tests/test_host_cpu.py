@@ -301,3 +301,24 @@ def test_numpy_strided_dot_is_the_pinned_arithmetic(oracle):
     want = oracle.profile_scores_py(prof, tab)
     if not np.array_equal(got, want):
         pytest.skip("this machine's BLAS uses a different ddot kernel than the one the golden vectors pin")
+
+
+def test_c_log_odds_helper_is_bit_identical_to_the_python_path():
+    from rnascan_b200 import motifs
+    rng = np.random.default_rng(11)
+    letters = "GAUC"
+    for trial in range(50):
+        W = int(rng.integers(1, 13))
+        counts = {l: rng.dirichlet(0.3 * np.ones(4), size=W)[:, k].tolist() for k, l in enumerate(letters)}
+        if trial % 4 == 0:
+            counts["A"][0] = 0.0
+        pc = 0.0 if trial % 4 == 0 else 0.01
+        prob = motifs.normalize_counts(counts, letters, pc)
+        bgv = rng.dirichlet(np.ones(4))
+        bg = {l: float(bgv[k]) for k, l in enumerate(letters)}
+        want = motifs.log_odds(prob, letters, bg)
+        total = sum(bg.values())
+        bgn = np.array([bg[l] / total for l in letters])
+        got = motifs.log_odds_table(np.array([prob[l] for l in letters]).T, bgn)
+        for k, l in enumerate(letters):
+            assert same(got[:, k], want[l])
