@@ -58,43 +58,77 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled every ~10 ms through NVML while the benchmark runs
+    (in-process, so even millisecond-long timed regions get samples); falls back to an
+    `nvidia-smi -lms 200` child process when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.proc = index, None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop_flag = threading.Event()
 
-    def run(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        self.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                idx = int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        flags = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_flag.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(mx))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in flags.items():
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.01)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.proc = subprocess.Popen(
+            ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+             "--format=csv,noheader,nounits", "-lms", "200"],
+            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            try:
+                self._smi_loop()
+            except Exception:
+                pass
+
+    def stop(self):
+        self._stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ----------------------------------------------------------------------------- synthetic shard
