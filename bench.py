@@ -250,6 +250,12 @@ def make_tables_fn(workload, seed=102):
             tqs.append(np.array([sp[l] for l in "BEHLMRT"], np.float64).T.copy())
 
         prob_arrays = [np.array([prob[l] for l in "ACGU"], np.float64).T.copy() for prob in seq_probs]
+        stacked = np.concatenate(prob_arrays, axis=0)       # all motifs' rows: one helper call per step
+        stride = int(max(widths))
+        row_of = np.concatenate([m * stride + np.arange(w) for m, w in enumerate(widths)])
+        qs = np.zeros((N_MOTIFS_C5, stride, 7), np.float64)
+        for m, t in enumerate(tqs):
+            qs[m, :t.shape[0]] = t
 
         def batched(counts8):
             c = {"A": int(counts8[0]), "C": int(counts8[1]), "G": int(counts8[2]), "U": int(counts8[3])}
@@ -257,8 +263,11 @@ def make_tables_fn(workload, seed=102):
             bg = {l: (float(c[l]) + 1) / total for l in rna}
             norm = sum(bg.values())                         # Biopython re-normalises the background
             bgn = np.array([bg[l] / norm for l in "ACGU"])
-            tss = [motifs.log_odds_table(pa, bgn) for pa in prob_arrays]   # == motifs.log_odds, bit for bit
-            return tss, tqs
+            ss = np.zeros((N_MOTIFS_C5 * stride, 4), np.float64)
+            ss[row_of] = motifs.log_odds_table(stacked, bgn)   # == motifs.log_odds per motif, bit for bit
+            return ss.reshape(N_MOTIFS_C5, stride, 4), qs
+        batched.widths = np.asarray(widths, np.int32)
+        batched.lists = lambda counts8: ([t[:w] for t, w in zip(batched(counts8)[0], widths)], tqs)
         return batched
     if workload == "c2":
         return lambda counts8: (seq_table(counts8), None)
@@ -296,8 +305,7 @@ def run_b200(args):
     if wl in ("c4", "c5"):
         absmax = dev.ProfileStream.from_device(prof, n).absrow_max()
     if wl == "c5":
-        _, tq0 = tables(np.ones(8, np.int64))
-        c5_widths = np.array([t.shape[0] for t in tq0], np.int32)
+        c5_widths = tables.widths
         c5_motif = torch.empty(hb.capacity, dtype=torch.int32, device=device)
         c5_counters = torch.zeros(2 * N_MOTIFS_C5, dtype=torch.int64, device=device)
         c5_bases = torch.zeros(N_MOTIFS_C5 + 1, dtype=torch.int64, device=device)
@@ -312,7 +320,7 @@ def run_b200(args):
 
     def step():
         counts.zero_()
-        check(lib.rs_hist(_ptr(codes), n, _ptr(counts), sptr)); launches[0] += 1
+        check((lib.rs_hist if wl == "c3" else lib.rs_hist_rna)(_ptr(codes), n, _ptr(counts), sptr)); launches[0] += 1
         all_reduce(counts)                                  # the path's only collective
         counts_host.copy_(counts, non_blocking=True)
         stream.synchronize()
@@ -324,13 +332,9 @@ def run_b200(args):
                                     hb.work_bytes, sptr))
             launches[0] += 3
         elif wl == "c5":
-            M = len(tq)
-            stride = max(t.shape[0] for t in tq)
-            qs = np.zeros((M, stride, 7)); ss = np.zeros((M, stride, 4))
-            for m in range(M):
-                qs[m, :tq[m].shape[0]] = tq[m]; ss[m, :ts[m].shape[0]] = ts[m]
+            M, stride = tq.shape[0], tq.shape[1]            # ts, tq: (256, stride, 4|7) stacked tables
             check(lib.rs_scan_batched(_ptr(codes), _ptr(prof), _lib.RS_F32, n, M, c5_widths.ctypes.data,
-                                      ss.ctypes.data, qs.ctypes.data, stride, THRESHOLD, absmax, _lib.RS_MODE_AND,
+                                      ts.ctypes.data, tq.ctypes.data, stride, THRESHOLD, absmax, _lib.RS_MODE_AND,
                                       hb.capacity, _ptr(c5_motif), _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct),
                                       _ptr(c5_counters), _ptr(c5_bases), _ptr(hb.work), hb.work_bytes, sptr))
             launches[0] += 4 * M
@@ -514,7 +518,7 @@ def cpu_port_baseline(workload, n_symbols=None):
         cnt = np.zeros(4, np.int64)
         L.orc_count_letters(text, len(text), b"ACGU", 4, cnt.ctypes.data)
         counts[:4] = cnt
-        ts, tq = tables(counts)
+        ts, tq = tables.lists(counts) if workload == "c5" else tables(counts)
         if workload == "c5":
             nh = 0
             for ts_m, tq_m in zip(ts, tq):

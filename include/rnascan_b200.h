@@ -88,6 +88,9 @@ int rs_host_log_odds(const double *prob, const double *bg, int W, int A, double 
  * d_counts8[k] += number of symbols with index k and bit 3 clear (k = 0..7); exact
  * integers.  The caller zeroes d_counts8 first (so shards can accumulate).            */
 int rs_hist(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream);
+/* Same for NUCLEOTIDE streams only (codes 0-3, RS_RNA_OTHER, RS_SEP as rs_host_encode_rna
+ * writes them): two index bit-planes instead of three, half the arithmetic; bins 4..7 stay 0.  */
+int rs_hist_rna(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream);
 
 /* ---- dense scores: the calculate() semantics, every window, NaN in band ------------
  * seq    : _pwm.c:34-68   out[i] = (float)(sum_j table[j][code]) double accumulation

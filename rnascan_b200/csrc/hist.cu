@@ -18,13 +18,16 @@ __device__ __forceinline__ unsigned bytesum(unsigned x)       // sum of the four
     return __dp4a(x, 0x01010101u, 0u);
 }
 
+// PLANES = 3: any stream (letter index in bits 0-2).  PLANES = 2: nucleotide streams, whose
+// counted symbols are 0..3 (bit 2 never set with bit 3 clear): half the arithmetic.
+template <int PLANES>
 __global__ void __launch_bounds__(HI_THREADS) hist_kernel(const uint8_t *__restrict__ codes, int64_t n,
                                                           unsigned long long *__restrict__ counts)
 {
-    // subset sums: index bit s set <=> plane s is in the product; element 0 = valid count
-    unsigned long long tot[8];
+    constexpr int NS = 1 << PLANES;              // subset sums: index bit s set <=> plane s in the product
+    unsigned long long tot[NS];
 #pragma unroll
-    for (int k = 0; k < 8; k++) tot[k] = 0;
+    for (int k = 0; k < NS; k++) tot[k] = 0;
 
     const int64_t nvec = n / 16;
     const uint4 *v = reinterpret_cast<const uint4 *>(codes);
@@ -32,49 +35,66 @@ __global__ void __launch_bounds__(HI_THREADS) hist_kernel(const uint8_t *__restr
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 
     while (i < nvec) {
-        unsigned acc[8];
+        unsigned acc[NS];
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc[k] = 0;
-        // up to 15 vectors (60 words, each adds <= 1 per byte lane ... 4 words/vector => <= 60 < 256)
-        for (int rep = 0; rep < 15 && i < nvec; rep++, i += gstride) {
-            const uint4 q = __ldg(v + i);
-            const unsigned w4[4] = {q.x, q.y, q.z, q.w};
+        for (int k = 0; k < NS; k++) acc[k] = 0;
+        // 3 rounds of 4 independent 16-byte loads (12 vectors * 4 words: byte counters stay < 256)
+        for (int rep = 0; rep < 3 && i < nvec; rep++) {
+            uint4 q[4];
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const unsigned w = w4[t];
-                const unsigned nv = ~(w >> 3) & 0x01010101u;      // valid: bit 3 clear
-                const unsigned b0 = w & nv;
-                const unsigned b1 = (w >> 1) & nv;
-                const unsigned b2 = (w >> 2) & nv;
-                acc[0] += nv;
-                acc[1] += b0;
-                acc[2] += b1;
-                acc[4] += b2;
-                acc[3] += b0 & b1;
-                acc[5] += b0 & b2;
-                acc[6] += b1 & b2;
-                acc[7] += b0 & b1 & b2;
+            for (int u = 0; u < 4; u++) {
+                const int64_t j = i + u * gstride;
+                q[u] = j < nvec ? __ldg(v + j) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+            i += 4 * gstride;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const unsigned w = w4[t];
+                    const unsigned nv = ~(w >> 3) & 0x01010101u;      // counted: bit 3 clear
+                    const unsigned b0 = w & nv;
+                    const unsigned b1 = (w >> 1) & nv;
+                    acc[0] += nv;
+                    acc[1] += b0;
+                    acc[2] += b1;
+                    acc[3] += b0 & b1;
+                    if (PLANES == 3) {
+                        const unsigned b2 = (w >> 2) & nv;
+                        acc[4] += b2;
+                        acc[5] += b0 & b2;
+                        acc[6] += b1 & b2;
+                        acc[7] += b0 & b1 & b2;
+                    }
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) tot[k] += bytesum(acc[k]);
+        for (int k = 0; k < NS; k++) tot[k] += bytesum(acc[k]);
     }
     // tail symbols (n % 16) by the first threads of block 0
     if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
         const unsigned c = codes[nvec * 16 + threadIdx.x];
         if (!(c & 8)) {
-            const unsigned b0 = c & 1, b1 = (c >> 1) & 1, b2 = (c >> 2) & 1;
-            tot[0] += 1; tot[1] += b0; tot[2] += b1; tot[4] += b2;
-            tot[3] += b0 & b1; tot[5] += b0 & b2; tot[6] += b1 & b2; tot[7] += b0 & b1 & b2;
+            const unsigned b[3] = {c & 1, (c >> 1) & 1, (c >> 2) & 1};
+#pragma unroll
+            for (int T = 0; T < NS; T++) {
+                unsigned p = 1;
+#pragma unroll
+                for (int s = 0; s < PLANES; s++)
+                    if (T & (1 << s)) p &= b[s];
+                tot[T] += p;
+            }
         }
     }
     // inclusion-exclusion: count of index k = sum over supersets T of bits(k) of (-1)^{|T|-|k|} S[T]
-    long long cnt[8];
+    long long cnt[NS];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < NS; k++) {
         long long c = 0;
 #pragma unroll
-        for (int T = 0; T < 8; T++)
+        for (int T = 0; T < NS; T++)
             if ((T & k) == k) c += (__popc(T ^ k) & 1) ? -(long long)tot[T] : (long long)tot[T];
         cnt[k] = c;
     }
@@ -82,26 +102,37 @@ __global__ void __launch_bounds__(HI_THREADS) hist_kernel(const uint8_t *__restr
     if (threadIdx.x < 8) s_bins[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < NS; k++) {
         long long c = cnt[k];
         for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
         if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_bins[k], (unsigned long long)c);
     }
     __syncthreads();
-    if (threadIdx.x < 8 && s_bins[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_bins[threadIdx.x]);
+    if (threadIdx.x < NS && s_bins[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_bins[threadIdx.x]);
 }
 
-extern "C" int rs_hist(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream)
+template <int PLANES>
+static int hist_launch(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream)
 {
     if (!d_codes || !d_counts8 || n < 0) { rs_set_error("rs_hist: bad argument"); return RS_ERR_INVALID; }
     if ((uintptr_t)d_codes & 15) { rs_set_error("codes pointer must be 16-byte aligned"); return RS_ERR_INVALID; }
     if (n == 0) return RS_OK;
-    int64_t blocks = (n / 16 + HI_THREADS - 1) / HI_THREADS;
+    int64_t blocks = (n / 64 + HI_THREADS - 1) / HI_THREADS;
     int64_t cap = (int64_t)rs_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    hist_kernel<<<(unsigned)blocks, HI_THREADS, 0, (cudaStream_t)stream>>>(d_codes, n,
-                                                                         (unsigned long long *)d_counts8);
+    hist_kernel<PLANES><<<(unsigned)blocks, HI_THREADS, 0, (cudaStream_t)stream>>>(d_codes, n,
+                                                                                 (unsigned long long *)d_counts8);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
+}
+
+extern "C" int rs_hist_rna(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream)
+{
+    return hist_launch<2>(d_codes, n, d_counts8, stream);
+}
+
+extern "C" int rs_hist(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, void *stream)
+{
+    return hist_launch<3>(d_codes, n, d_counts8, stream);
 }

@@ -77,9 +77,10 @@ def pack_profiles(profiles, dtype=np.float64):
 class SymbolStream(object):
     """A symbol stream resident in HBM."""
 
-    def __init__(self, codes, offsets=None, lengths=None, device=None):
+    def __init__(self, codes, offsets=None, lengths=None, device=None, kind=None):
         require_cuda()
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.kind = kind                 # "rna" | "struct" | None (unknown: generic kernels)
         self.n = int(codes.shape[0])
         self.offsets = np.zeros(1, np.int64) if offsets is None else np.asarray(offsets, np.int64)
         self.lengths = np.array([self.n], np.int64) if lengths is None else np.asarray(lengths, np.int64)
@@ -94,7 +95,7 @@ class SymbolStream(object):
     @classmethod
     def from_texts(cls, texts, kind, device=None):
         codes, offsets, lengths = pack_texts(texts, kind)
-        return cls(codes, offsets, lengths, device)
+        return cls(codes, offsets, lengths, device, kind=kind)
 
     def host_codes(self):
         """The encoded symbols as a host uint8 array (the pinned upload buffer)."""
@@ -167,7 +168,8 @@ def _table(table, cols):
 def histogram(stream):
     """int64[8] exact counts of symbols 0..7 whose 'not counted' bit is clear."""
     counts = torch.zeros(8, dtype=torch.int64, device=stream.codes.device)
-    check(lib.rs_hist(_ptr(stream.codes), stream.n, _ptr(counts), _stream()))
+    fn = lib.rs_hist_rna if getattr(stream, "kind", None) == "rna" else lib.rs_hist
+    check(fn(_ptr(stream.codes), stream.n, _ptr(counts), _stream()))
     return counts
 
 
@@ -451,7 +453,7 @@ class HostFusedScanner(object):
         for k in range(min(2, len(order))):
             pending[k] = load(k)
         self.counts.zero_()
-        check(lib.rs_hist(_ptr(self.codes), n, _ptr(self.counts), comp.cuda_stream))
+        check(lib.rs_hist_rna(_ptr(self.codes), n, _ptr(self.counts), comp.cuda_stream))
         if all_reduce is not None:
             all_reduce(self.counts)
         self.counts_host.copy_(self.counts, non_blocking=True)

@@ -14,8 +14,9 @@ from rnascan_b200 import device, synth, _lib
 
 
 class FakeSymbolStream(object):
-    def __init__(self, codes, offsets=None, lengths=None, device=None):
+    def __init__(self, codes, offsets=None, lengths=None, device=None, kind=None):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.kind = kind
         self.n = int(codes.shape[0])
         self.offsets = np.zeros(1, np.int64) if offsets is None else np.asarray(offsets, np.int64)
         self.lengths = np.array([self.n], np.int64) if lengths is None else np.asarray(lengths, np.int64)
@@ -25,7 +26,7 @@ class FakeSymbolStream(object):
     @classmethod
     def from_texts(cls, texts, kind, device=None):
         codes, offsets, lengths = device_pack(texts, kind)
-        return cls(codes, offsets, lengths)
+        return cls(codes, offsets, lengths, kind=kind)
 
     def host_codes(self):
         return self._codes

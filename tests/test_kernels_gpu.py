@@ -78,6 +78,17 @@ def test_hist_exact(dev, n):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("n", [0, 5, 16, 63, 64, 65, 1000, 65537, 5_000_003])
+def test_hist_rna_exact(dev, n):
+    rng = np.random.default_rng(n + 7)
+    codes = rng.choice(np.array([0, 1, 2, 3, 0x0C, 0xFF], np.uint8), size=n, p=[.27, .22, .22, .27, .01, .01])
+    st = dev.SymbolStream(codes, kind="rna")
+    got = dev.histogram(st).cpu().numpy()
+    want = np.array([(codes == k).sum() for k in range(8)], np.int64)
+    assert np.array_equal(got, want)
+    assert np.array_equal(dev.histogram(dev.SymbolStream(codes)).cpu().numpy(), want)     # generic kernel agrees
+
+
 # ----------------------------------------------------------------------------- sequence
 @pytest.mark.parametrize("W", [1, 4, 7, 12, 18, 33, 64])
 def test_dense_seq_bit_exact(dev, oracle, W):

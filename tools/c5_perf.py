@@ -12,12 +12,9 @@ n, codes, prof = shard["n"], shard["codes"], shard["prof"]
 tables = bench.make_tables_fn("c5")
 counts = torch.zeros(8, dtype=torch.int64, device=device)
 check(lib.rs_hist(_ptr(codes), n, _ptr(counts), 0)); torch.cuda.synchronize()
-ts, tq = tables(counts.cpu().numpy())
-M = len(tq); stride = max(t.shape[0] for t in tq)
-qs = np.zeros((M, stride, 7)); ss = np.zeros((M, stride, 4))
-widths = np.array([t.shape[0] for t in tq], np.int32)
-for m in range(M):
-    qs[m, :tq[m].shape[0]] = tq[m]; ss[m, :ts[m].shape[0]] = ts[m]
+ss, qs = tables(counts.cpu().numpy())
+M, stride = qs.shape[0], qs.shape[1]
+widths = tables.widths
 cap = max(1 << 16, n // 64)
 hb = dev.HitBuffers(n, cap, device)
 wb = int(lib.rs_scan_batched_workspace_bytes(n, M, stride, cap)); work = torch.empty(wb, dtype=torch.uint8, device=device)

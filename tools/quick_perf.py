@@ -39,7 +39,8 @@ st = S(); st.codes = codes; st.n = n
 ss = S(); ss.codes = scodes; ss.n = n
 pf = device.ProfileStream.from_device(prof, n)
 counts = torch.zeros(8, dtype=torch.int64, device=dev)
-timeit("hist", lambda: check(lib.rs_hist(_ptr(codes), n, _ptr(counts), _stream())), 1)
+timeit("hist (3 planes)", lambda: check(lib.rs_hist(_ptr(codes), n, _ptr(counts), _stream())), 1)
+timeit("hist_rna (2 planes)", lambda: check(lib.rs_hist_rna(_ptr(codes), n, _ptr(counts), _stream())), 1)
 hb = device.HitBuffers(n, n // 64, dev)
 outf = torch.empty(n, dtype=torch.float32, device=dev)
 outd = torch.empty(n, dtype=torch.float64, device=dev)
