@@ -171,6 +171,117 @@ __global__ void __launch_bounds__(OH_THREADS) onehot_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dense scores for W <= 16 with the motif width known at compile time (the generic kernel above
+// spends ~20 instructions per symbol on loop control and 64-bit addressing).  Lanes take
+// consecutive windows (coalesced stores); a window's bytes are fetched as aligned words (four
+// lanes share a word: broadcast, no bank conflict) and aligned with funnel shifts; each symbol
+// costs shift + mask (giving the byte offset of its table entry directly), one LDS.64 and one
+// fp64 add -- still the reference's sequential j-order sum (_pwm.c:36-60, matrix.py:34-38).
+#define DW_THREADS 256
+#define DW_PER     16
+#define DW_TILE    (DW_THREADS * DW_PER)
+#define DW_STAGES  3
+#define DW_STAGE_BYTES (DW_TILE + 32)
+
+template <int A, int W>
+__global__ void __launch_bounds__(DW_THREADS) dense_w_kernel(const __grid_constant__ OneHotParams prm)
+{
+    constexpr int NW = (W + 3) / 4;                       // words holding one window's symbols
+    __shared__ __align__(128) uint8_t s_stage[DW_STAGES * DW_STAGE_BYTES];
+    __shared__ __align__(16) double s_ta[W * OH_TS];
+    __shared__ uint64_t bars[DW_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < W * OH_TS; k += DW_THREADS) s_ta[k] = prm.ta[k];
+    if (tid == 0) {
+        for (int s = 0; s < DW_STAGES; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int64_t stride = gridDim.x, first = blockIdx.x;
+    const int64_t my_tiles = first < prm.n_tiles ? (prm.n_tiles - first + stride - 1) / stride : 0;
+    auto issue = [&](int64_t it) {
+        const int s = (int)(it % DW_STAGES);
+        const int64_t t0 = (first + it * stride) * DW_TILE;
+        const uint32_t bytes = (uint32_t)min((int64_t)DW_STAGE_BYTES, prm.padded - t0);
+        mbar_expect_tx(&bars[s], bytes);
+        bulk_g2s(s_stage + (size_t)s * DW_STAGE_BYTES, prm.codes_a + t0, bytes, &bars[s]);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < DW_STAGES - 1 && it < my_tiles; it++) issue(it);
+    const uint32_t tab = smem_u32(s_ta);
+
+    for (int64_t it = 0; it < my_tiles; it++) {
+        const int s = (int)(it % DW_STAGES);
+        if (tid == 0 && it + DW_STAGES - 1 < my_tiles) issue(it + DW_STAGES - 1);
+        mbar_wait(&bars[s], (uint32_t)((it / DW_STAGES) & 1));
+        const int64_t t0 = (first + it * stride) * DW_TILE;
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(s_stage + (size_t)s * DW_STAGE_BYTES);
+#pragma unroll 4
+        for (int k = 0; k < DW_PER; k++) {
+            const int w = warp * (32 * DW_PER) + k * 32 + lane;
+            const uint32_t *q = words + (w >> 2);
+            const unsigned sh = (unsigned)(w & 3) * 8u;
+            uint32_t x[NW];
+            uint32_t prev = q[0];
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const uint32_t nxt = q[i + 1];
+                x[i] = __funnelshift_r(prev, nxt, sh);
+                prev = nxt;
+            }
+            // validity: A = 4 -> any of bits 2,3 set; A = 7 -> (code & 7) == 7
+            uint32_t bad = 0;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const uint32_t m = (i == NW - 1 && (W & 3)) ? (0xFFFFFFFFu >> (32 - 8 * (W & 3))) : 0xFFFFFFFFu;
+                if (A == 4) bad |= x[i] & (0x0C0C0C0Cu & m);
+                else        bad |= x[i] & (x[i] >> 1) & (x[i] >> 2) & (0x01010101u & m);
+            }
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                const int sb = 8 * (j & 3);
+                const uint32_t off = sb >= 3 ? ((x[j >> 2] >> (sb - 3)) & 0x38u) : ((x[j >> 2] << 3) & 0x38u);
+                double t;
+                asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tab + (uint32_t)(j * OH_TS * 8) + off));
+                sum = __dadd_rn(sum, t);
+            }
+            const int64_t gpos = t0 + w;
+            if (gpos + W <= prm.n) {
+                if (A == 4) reinterpret_cast<float *>(prm.dense_out)[gpos] = bad ? nanf("") : (float)sum;
+                else        reinterpret_cast<double *>(prm.dense_out)[gpos] = bad ? nan("") : sum;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int A, int W>
+static int launch_dense_w(OneHotParams &prm, cudaStream_t stream)
+{
+    prm.n_tiles = (prm.n + DW_TILE - 1) / DW_TILE;
+    int64_t grid = (int64_t)rs_sm_count() * 6;
+    if (grid > prm.n_tiles) grid = prm.n_tiles;
+    rs_prof_start(stream);
+    dense_w_kernel<A, W><<<(unsigned)grid, DW_THREADS, 0, stream>>>(prm);
+    rs_prof_stop(stream);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+template <int A>
+static int dispatch_dense_w(int W, OneHotParams &prm, cudaStream_t stream)
+{
+    switch (W) {
+#define DW_CASE(w) case w: return launch_dense_w<A, w>(prm, stream);
+        DW_CASE(1) DW_CASE(2) DW_CASE(3) DW_CASE(4) DW_CASE(5) DW_CASE(6) DW_CASE(7) DW_CASE(8)
+        DW_CASE(9) DW_CASE(10) DW_CASE(11) DW_CASE(12) DW_CASE(13) DW_CASE(14) DW_CASE(15) DW_CASE(16)
+#undef DW_CASE
+    default: return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 static void fill_table(double *dst, const double *src, int W, int A)
 {
     for (int j = 0; j < W; j++)
@@ -209,6 +320,7 @@ static int dense_impl(const uint8_t *d_codes, int64_t n, const double *table, in
     prm.codes_a = d_codes; prm.dense_out = d_out; prm.n = n; prm.padded = rs_padded_count(n);
     prm.n_tiles = (n + OH_TILE - 1) / OH_TILE; prm.W = W;
     fill_table(prm.ta, table, W, A);
+    if (W <= 16) return dispatch_dense_w<A>(W, prm, (cudaStream_t)stream);
     return launch<A, false, true>(prm, (cudaStream_t)stream);
 }
 

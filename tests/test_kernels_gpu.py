@@ -90,7 +90,7 @@ def test_hist_rna_exact(dev, n):
 
 
 # ----------------------------------------------------------------------------- sequence
-@pytest.mark.parametrize("W", [1, 4, 7, 12, 18, 33, 64])
+@pytest.mark.parametrize("W", [1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 18, 33, 64])
 def test_dense_seq_bit_exact(dev, oracle, W):
     from rnascan_b200 import synth
     st, codes, _ = make_stream(dev, 200_000, 40, seed=W)
@@ -143,7 +143,7 @@ def test_scan_seq_hits(dev, oracle, thr):
 
 
 # ----------------------------------------------------------------------------- structure one-hot
-@pytest.mark.parametrize("W", [1, 7, 18, 64])
+@pytest.mark.parametrize("W", [1, 2, 3, 4, 6, 7, 8, 11, 13, 16, 17, 18, 64])
 def test_dense_struct_bit_exact(dev, oracle, W):
     from rnascan_b200 import synth
     st, codes, _ = make_stream(dev, 150_000, 30, seed=W, kind="struct")
