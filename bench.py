@@ -278,8 +278,7 @@ def make_tables_fn(workload, seed=102):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from rnascan_b200 import device as dev, _lib
-    from rnascan_b200.device import lib, check, _ptr
+    from rnascan_b200 import device as dev
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus and world > 1:
@@ -289,7 +288,41 @@ def run_b200(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    wl = args.workload
+    out = measure(args, args.workload, args.steps, (rank, world, local, device), full=True)
+    if world == 1 and not args.no_others:
+        # the other BASELINE.json configurations, briefly, so that one bench line shows them all
+        others = {}
+        for wl in ("c2", "c3", "c5", "c4"):
+            if wl == args.workload:
+                continue
+            torch.cuda.empty_cache()
+            o = measure(args, wl, 3, (rank, world, local, device), full=False)
+            others[wl] = {"workload": o["config"]["workload"], "value": o["value"], "unit": o["unit"],
+                          "ms_per_step": o["ms_per_step"], "kernel": o["roofline"]["kernel"],
+                          "kernel_ms": o["roofline"]["kernel_ms"], "bound": o["roofline"]["bound"],
+                          "achieved": o["roofline"]["achieved"], "roofline_unit": o["roofline"]["unit"],
+                          "frac": o["roofline"]["frac"]}
+            if "e2e" in o:
+                others[wl]["e2e"] = o["e2e"]["value"]
+            if "motif_positions_per_s" in o:
+                others[wl]["motif_positions_per_s_G"] = o["motif_positions_per_s"]
+        out["other_workloads"] = others
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_port_baseline(args.workload)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(args, wl, steps, ctx, full=True):
+    """Time `steps` steps of workload `wl` on this rank's shard; returns the JSON object."""
+    import torch
+    import torch.distributed as dist
+    from rnascan_b200 import device as dev, _lib
+    from rnascan_b200.device import lib, check, _ptr
+
+    rank, world, local, device = ctx
     n_target = args.n_per_gpu
     shard = make_device_shard(n_target, 4000 + rank, wl, device)
     n, codes, prof = shard["n"], shard["codes"], shard["prof"]
@@ -353,35 +386,36 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and full:
         sampler.start()                  # covers warm-up + timed region + e2e (all under load)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches[0] = 0
     per_step = N_MOTIFS_C5 if wl == "c5" else 1      # upper bound on profiled launches per step
-    check(lib.rs_prof_begin(max(args.steps, 1) * per_step))
+    check(lib.rs_prof_begin(max(steps, 1) * per_step))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    kms = np.zeros(max(args.steps, 1) * per_step, np.float32)
+    kms = np.zeros(max(steps, 1) * per_step, np.float32)
     nrec = np.zeros(1, np.int32)
     check(lib.rs_prof_end(kms.ctypes.data, len(kms), nrec.ctypes.data))
-    kernel_ms = float(kms[:int(nrec[0])].sum()) / args.steps if nrec[0] else float("nan")
+    kernel_ms = float(kms[:int(nrec[0])].sum()) / steps if nrec[0] else float("nan")
     n_launch = launches[0]
     hits = int(hb.counters[0].item()) if wl in ("c4", "c2") else None
     if wl == "c5":
         hits = int(c5_bases[-1].item())
 
-    # ---- end to end: host buffers -> device -> hits back on the host, every step
+    # ---- end to end: host buffers -> device -> results back on the host, every step
     e2e = None
+    k2 = max(2, min(steps, 5))
+    h_codes = torch.empty(codes.shape, dtype=torch.uint8).pin_memory()
+    h_codes.copy_(codes)
     if wl == "c4":
-        h_codes = torch.empty(codes.shape, dtype=torch.uint8).pin_memory()
-        h_codes.copy_(codes)
         h_prof = torch.empty(prof.shape, dtype=torch.float32).pin_memory()
         h_prof.copy_(prof)
         torch.cuda.synchronize()
@@ -390,7 +424,6 @@ def run_b200(args):
         for _ in range(2):
             res = pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax, all_reduce=all_reduce)
         barrier()
-        k2 = max(2, min(args.steps, 5))
         t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(k2):
@@ -398,11 +431,53 @@ def run_b200(args):
         e1.record(stream)
         torch.cuda.synchronize()
         ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k2
-        e2e = {"ms": ms_e2e, "h2d": pipe.h2d_bytes, "d2h": pipe.d2h_bytes, "hits": int(len(res[0]))}
+        e2e = {"ms": ms_e2e, "h2d": pipe.h2d_bytes, "d2h": pipe.d2h_bytes, "hits": int(len(res[0])),
+               "api": "rnascan_b200.device.HostFusedScanner.run (pinned host streams in, host hit arrays out; "
+                      "profile chunks double-buffered against the scan)"}
         if hits is not None and e2e["hits"] != hits:
             raise SystemExit("e2e hit count %d != device-resident hit count %d" % (e2e["hits"], hits))
         del h_prof, pipe
-    clocks = sampler.stop() if rank == 0 else None
+    else:
+        # plain copy-in / step / copy-out through the same C-ABI calls
+        h_prof = None
+        if wl == "c5":
+            h_prof = torch.empty(prof.shape, dtype=torch.float32).pin_memory()
+            h_prof.copy_(prof)
+        h_out = torch.empty(dense_out.shape, dtype=dense_out.dtype).pin_memory() if wl == "c3" else None
+        h_pos = torch.empty(hb.capacity, dtype=torch.int64).pin_memory()
+        h_sc = torch.empty(hb.capacity, dtype=torch.float64).pin_memory()
+        io = [0, 0]
+
+        def e2e_step():
+            codes.copy_(h_codes, non_blocking=True); io[0] = codes.numel()
+            if h_prof is not None:
+                prof.copy_(h_prof, non_blocking=True); io[0] += prof.numel() * 4
+            step()
+            if wl == "c3":
+                h_out.copy_(dense_out, non_blocking=True); io[1] = dense_out.numel() * 8
+                stream.synchronize()
+            else:
+                stream.synchronize()
+                found = int(c5_bases[-1].item()) if wl == "c5" else int(hb.counters[0].item())
+                k = min(found, hb.capacity)
+                h_pos[:k].copy_(hb.pos[:k], non_blocking=True)
+                h_sc[:k].copy_((hb.struct if wl == "c5" else hb.seq)[:k], non_blocking=True)
+                stream.synchronize()
+                io[1] = 64 + 16 + k * (20 if wl == "c5" else 12)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(k2):
+            e2e_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k2
+        e2e = {"ms": ms_e2e, "h2d": io[0], "d2h": io[1],
+               "api": "pinned host streams -> device -> C-ABI step -> pinned host results"}
+        del h_prof, h_out
+    del h_codes
+    clocks = sampler.stop() if (rank == 0 and full) else None
 
     # ---- max over ranks, totals
     stats = torch.tensor([ms_total, kernel_ms, e2e["ms"] if e2e else 0.0], device=device, dtype=torch.float64)
@@ -412,12 +487,12 @@ def run_b200(args):
         dist.all_reduce(tot)
     ms_total, kernel_ms, ms_e2e = (float(v) for v in stats.cpu())
     all_positions, all_n = (int(v) for v in tot.cpu())
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     peak, peak_src = measured_peaks()
     achieved = ALGO_BYTES[wl] * positions / (kernel_ms * 1e-3) / 1e9
     out = {
         "metric": "scored positions/sec", "value": all_positions / (ms_step * 1e-3) / 1e9, "unit": "Gpos/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 filter + f64 exact re-score (sequence: f64 accumulate -> f32)" if wl == "c4" else
                  ("f64 accumulate -> f32" if wl == "c2" else ("f64" if wl == "c3" else
@@ -434,7 +509,7 @@ def run_b200(args):
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
         "gpu_launches": n_launch,
         "roofline": {"bound": "hbm", "kernel": {"c4": "fused_filter_kernel<7>", "c2": "kmer_scan_kernel<7>",
-                                               "c3": "onehot_kernel<7,dense>",
+                                               "c3": "dense_w_kernel<7,7>",
                                                "c5": "fused_filter_kernel<W> x %d motifs" % N_MOTIFS_C5}[wl],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],
@@ -469,13 +544,11 @@ def run_b200(args):
         out["e2e"] = {"value": all_positions / (ms_e2e * 1e-3) / 1e9, "unit": "Gpos/s",
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                       "ms_per_step": ms_e2e,
-                      "api": "rnascan_b200.device.HostFusedScanner.run (pinned host streams in, host hit arrays out)"}
-    if rank == 0:
-        if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_port_baseline(wl)
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+                      "link_GBps": (e2e["h2d"] + e2e["d2h"]) / (ms_e2e * 1e-3) / 1e9,
+                      "api": e2e["api"]}
+    if wl == "c5":
+        check(lib.rs_set_batched_path(0))
+    return out
 
 
 # ----------------------------------------------------------------------------- CPU legs
@@ -589,6 +662,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--n-per-gpu", type=int, default=125_000_000, dest="n_per_gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", dest="no_others",
+                    help="skip the brief runs of the other configurations (other_workloads)")
     ap.add_argument("--c5-path", default="auto", choices=["auto", "cuda", "tensor"], dest="c5_path")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -5,7 +5,7 @@ TAG=${1:-r1b}
 mkdir -p gpurun_out
 for WL in c4 c2 c5; do
   case $WL in c4) K=fused_filter;; c2) K=kmer_scan_kernel;; c5) K=batched_tc_kernel;; esac
-  CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline"
+  CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-others"
   $CMD > gpurun_out/${TAG}_${WL}_plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o gpurun_out/${TAG}_${WL} $CMD > gpurun_out/${TAG}_${WL}_ncu.log 2>&1
   tail -1 gpurun_out/${TAG}_${WL}_ncu.log
