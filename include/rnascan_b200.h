@@ -84,6 +84,15 @@ int rs_host_encode_struct(const uint8_t *text, int64_t n, uint8_t *codes);
  * uses it (called at rnascan.py:248): prob, out [W][A] row-major, bg [A] normalised.        */
 int rs_host_log_odds(const double *prob, const double *bg, int W, int A, double *out);
 
+/* ---- dot-bracket -> structural contexts (replaces scripts/parse_secondary_structure.cpp:65-221,
+ * the C++ tool run_folding pipes RNAfold centroids through; O(L) instead of O(L^2)) ------------
+ * Structure r is text[offsets[r] .. +lengths[r]) over the alphabet ( ) . ; its annotation over
+ * B,E,H,L,M,R,T is written to `out` at the same offsets.  status[r] (may be NULL) = RS_OK or
+ * RS_ERR_INVALID (unbalanced parentheses / foreign characters -- the reference has undefined
+ * behaviour there).  Host function, multi-threaded over structures.                          */
+int rs_host_annotate_structures(const char *text, const int64_t *offsets, const int64_t *lengths,
+                                int64_t n_structs, char *out, int *status);
+
 /* ---- background counts (replaces the Seq.count loop of rnascan.py:450-453) ---------
  * d_counts8[k] += number of symbols with index k and bit 3 clear (k = 0..7); exact
  * integers.  The caller zeroes d_counts8 first (so shards can accumulate).            */

@@ -326,6 +326,46 @@ def pfmutil_vectors():
     return V
 
 
+def dotbracket_vectors():
+    """Annotations by the reference's own C++ tool (oracle/_ref/parse_secondary_structure, built
+    from /root/reference/scripts/parse_secondary_structure.cpp) for seeded random balanced
+    structures and a few hand-written ones."""
+    import random
+    import subprocess
+    import tempfile
+    rnd = random.Random(20170106)
+
+    def rand_struct(n):
+        s, depth = [], 0
+        while len(s) < n:
+            r, rem = rnd.random(), n - len(s)
+            if depth >= rem:
+                s.append(")"); depth -= 1
+            elif r < 0.35:
+                s.append(".")
+            elif r < 0.70 and rem > depth + 1:
+                s.append("("); depth += 1
+            elif depth > 0:
+                s.append(")"); depth -= 1
+            else:
+                s.append(".")
+        return "".join(s)
+    structs = [rand_struct(rnd.randint(2, 160)) for _ in range(400)]
+    structs += ["..((...))..", "((..((...))..((...))..))", "(((...)))", "((.))..((.))", "(.)", "....",
+                "(((..)).(..))", "((((...)).((...)).))", ".((..)).", "(.(.(.).).)", "((.(...).(...).))..(..)",
+                "((((((..((((........)))).(((((.......))))).....(((((.......))))))))))).."]
+    structs = [s for s in structs if "." in s and s.count("(") == s.count(")")]
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, "in.txt"), os.path.join(d, "out.txt")
+        with open(fi, "w") as fh:
+            fh.write("\n".join(structs) + "\n")
+        subprocess.check_call([os.path.join(REPO, "oracle", "_ref", "parse_secondary_structure"), fi, fo])
+        with open(fo) as fh:
+            ann = fh.read().split("\n")[:-1]
+    assert len(ann) == len(structs)
+    return [[s, a] for s, a in zip(structs, ann)]
+
+
 def main():
     os.chdir(REPO)
     author_fixtures()
@@ -346,6 +386,8 @@ def main():
     A = api_vectors()
     with open(os.path.join(HERE, "api.json"), "w") as fh:
         json.dump(A, fh, indent=1, sort_keys=True)
+    with open(os.path.join(HERE, "dotbracket.json"), "w") as fh:
+        json.dump(dotbracket_vectors(), fh, indent=0)
     print("api.json written: %d pssm, %d calculate, %d averaged" %
           (len(A["pssm"]), len(A["calculate"]), len(A["averaged"])))
 

@@ -322,3 +322,67 @@ def test_c_log_odds_helper_is_bit_identical_to_the_python_path():
         got = motifs.log_odds_table(np.array([prob[l] for l in letters]).T, bgn)
         for k, l in enumerate(letters):
             assert same(got[:, k], want[l])
+
+
+# ----------------------------------------------------------------------------- dot-bracket annotation
+def test_structure_annotation_matches_the_reference_tool():
+    """tests/golden/dotbracket.json holds the output of the reference's own C++ program
+    (scripts/parse_secondary_structure.cpp) for 400+ structures."""
+    import json
+    from rnascan_b200 import structure
+    with open(os.path.join(REPO, "tests", "golden", "dotbracket.json")) as fh:
+        cases = json.load(fh)
+    got = structure.parse_many([c[0] for c in cases])
+    assert got == [c[1] for c in cases]
+    assert set("".join(got)) == set("BEHLMRT")
+    assert structure.parse("..((...))..") == "EELLHHHRREE"
+    for bad in ("((..)", "())(", "((.x.))"):
+        with pytest.raises(ValueError):
+            structure.parse(bad)
+    assert structure.parse_many([]) == []
+
+
+def test_structure_annotation_fuzz_against_the_reference_binary(tmp_path):
+    import random
+    from rnascan_b200 import structure
+    binary = os.path.join(REPO, "oracle", "_ref", "parse_secondary_structure")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/parse_secondary_structure not built")
+    rnd = random.Random(5)
+
+    def rand_struct(n):
+        s, depth = [], 0
+        while len(s) < n:
+            r, rem = rnd.random(), n - len(s)
+            if depth >= rem:
+                s.append(")"); depth -= 1
+            elif r < 0.3:
+                s.append(".")
+            elif r < 0.68 and rem > depth + 1:
+                s.append("("); depth += 1
+            elif depth > 0:
+                s.append(")"); depth -= 1
+            else:
+                s.append(".")
+        return "".join(s)
+    structs = [s for s in (rand_struct(rnd.randint(1, 300)) for _ in range(3000)) if "." in s]
+    fi, fo = tmp_path / "in.txt", tmp_path / "out.txt"
+    fi.write_text("\n".join(structs) + "\n")
+    subprocess.check_call([binary, str(fi), str(fo)])
+    assert fo.read_text().split("\n")[:-1] == structure.parse_many(structs)
+    # file interface of the tool
+    out2 = tmp_path / "out2.txt"
+    structure.parse_file(str(fi), str(out2))
+    assert out2.read_text() == fo.read_text()
+
+
+def test_structure_annotation_is_linear_time():
+    """The reference is O(L^2) (nested pair search, enclosing-pair scan); 2 M nested symbols here."""
+    import time
+    from rnascan_b200 import structure
+    n = 1_000_000
+    s = "(" * n + "...." + ")" * n
+    t0 = time.perf_counter()
+    a = structure.parse(s)
+    assert time.perf_counter() - t0 < 5.0
+    assert a == "L" * n + "HHHH" + "R" * n
