@@ -366,6 +366,26 @@ def dotbracket_vectors():
     return [[s, a] for s, a in zip(structs, ann)]
 
 
+def averaging_vectors():
+    """struct_pfm_from_aligned + norm_pfm of the reference (average_structure.py:28-42, pfmutil.py:136-151)
+    on seeded aligned annotation strings."""
+    import random
+    from rnascan import average_structure as av
+    from rnascan import pfmutil as pu
+    rnd = random.Random(7)
+    cases = []
+    for L, nfrag, flen in ((40, 9, 20), (120, 30, 50), (7, 3, 7)):
+        seqs = []
+        for k in range(nfrag):
+            start = (k * (L - flen)) // max(1, nfrag - 1)          # first at 0, last flush with the end
+            body = "".join(rnd.choice("BEHLMRT") for _ in range(min(flen, L - start)))
+            seqs.append("-" * start + body + "-" * (L - start - len(body)))
+        counts = av.struct_pfm_from_aligned(seqs)
+        cases.append({"sequences": seqs, "counts": counts, "profile": pu.norm_pfm(counts),
+                      "text": pu.format_pfm(pu.norm_pfm(counts))})
+    return cases
+
+
 def main():
     os.chdir(REPO)
     author_fixtures()
@@ -388,6 +408,8 @@ def main():
         json.dump(A, fh, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "dotbracket.json"), "w") as fh:
         json.dump(dotbracket_vectors(), fh, indent=0)
+    with open(os.path.join(HERE, "averaging.json"), "w") as fh:
+        json.dump(averaging_vectors(), fh, indent=0)
     print("api.json written: %d pssm, %d calculate, %d averaged" %
           (len(A["pssm"]), len(A["calculate"]), len(A["averaged"])))
 

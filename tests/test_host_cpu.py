@@ -386,3 +386,23 @@ def test_structure_annotation_is_linear_time():
     a = structure.parse(s)
     assert time.perf_counter() - t0 < 5.0
     assert a == "L" * n + "HHHH" + "R" * n
+
+
+def test_profile_averaging_matches_the_reference():
+    """struct_pfm_from_aligned + norm_pfm (the post-RNAfold half of run_folding) against outputs of the
+    reference's own functions, and the profile text format the scan reads back."""
+    import json
+    from rnascan_b200 import structure, pfmutil
+    with open(os.path.join(REPO, "tests", "golden", "averaging.json")) as fh:
+        cases = json.load(fh)
+    for c in cases:
+        assert structure.struct_pfm_from_aligned(c["sequences"]) == c["counts"]
+        prof = structure.profile_from_aligned(c["sequences"])
+        assert prof == c["profile"]
+        assert pfmutil.format_pfm(prof) == c["text"]
+    with pytest.raises(KeyError):
+        structure.struct_pfm_from_aligned(["EEX-", "EEH-"])
+    # fragments -> annotate -> align -> average
+    prof = structure.profile_from_fragments(11, [(-3, "((...))"), (2, "..((...))"), (4, "(....)")])
+    assert all(abs(sum(prof[l][i] for l in prof) - 1.0) < 1e-12 for i in range(11))
+    assert prof["L"][0] == 1.0 and prof["E"][2] == 0.5
