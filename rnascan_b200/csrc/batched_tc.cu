@@ -518,10 +518,11 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     const size_t smem = 160 * 1024;
     static_assert(TC_B_BYTES + TC_STAGES * (TC_A_BYTES + TC_RAW_BYTES) + 256 <= 96 * 1024, "smem layout");
     static_assert(96 * 1024 + 8 * TC_CBUF * 8 <= 160 * 1024, "smem layout");
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[RS_MAX_DEVICES] = {};          // the attribute is per device
+    const int dev = rs_current_device();
+    if (!configured[dev]) {
         RS_CUDA(cudaFuncSetAttribute(batched_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev] = true;
     }
     TcParams tp = {};
     tp.profile = (const float *)d_profile; tp.n = n; tp.padded = rs_padded_count(n);

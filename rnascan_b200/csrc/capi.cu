@@ -20,6 +20,13 @@ int rs_cuda_fail(cudaError_t e, const char *what)
     return RS_ERR_CUDA;
 }
 
+int rs_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < RS_MAX_DEVICES ? dev : RS_MAX_DEVICES - 1;
+}
+
 int rs_sm_count()
 {
     static int cached_dev = -1, cached = 0;

@@ -287,10 +287,11 @@ template <int W>
 static int launch_kmer(const KmerParams &prm, cudaStream_t stream)
 {
     const size_t smem = 128 + KM_LUT_BYTES + (size_t)KM_STAGES * KM_STAGE_BYTES;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[RS_MAX_DEVICES] = {};          // the attribute is per device
+    const int dev = rs_current_device();
+    if (!configured[dev]) {
         RS_CUDA(cudaFuncSetAttribute(kmer_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev] = true;
     }
     int64_t grid = (int64_t)rs_sm_count() * 2;
     if (grid > prm.n_tiles) grid = prm.n_tiles;

@@ -384,10 +384,11 @@ static int launch_filter(const ProfileParams &prm, cudaStream_t stream)
     constexpr int ROWS = FT_TILE + W - 1;
     constexpr uint32_t STAGE_BYTES = ru16(ROWS * RS_CHANNELS * 4) + ru16(ROWS);
     const size_t smem = 128 + (size_t)FT_STAGES * STAGE_BYTES;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[RS_MAX_DEVICES] = {};          // the attribute is per device
+    const int dev = rs_current_device();
+    if (!configured[dev]) {
         RS_CUDA(cudaFuncSetAttribute(fused_filter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev] = true;
     }
     int64_t grid = (int64_t)rs_sm_count() * 2;
     if (grid > prm.n_tiles) grid = prm.n_tiles;
@@ -421,10 +422,11 @@ static int launch_exact(const ProfileParams &prm, cudaStream_t stream)
     const int rows_max = EX_TILE + RS_MAX_W - 1;
     const size_t stage = ru16(rows_max * RS_CHANNELS * (uint32_t)sizeof(PT)) + ru16(rows_max);
     const size_t smem = 128 + (size_t)EX_STAGES * stage;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[RS_MAX_DEVICES] = {};          // the attribute is per device
+    const int dev = rs_current_device();
+    if (!configured[dev]) {
         RS_CUDA(cudaFuncSetAttribute(profile_exact_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev] = true;
     }
     int64_t grid = (int64_t)rs_sm_count() * (sizeof(PT) == 4 ? 3 : 1);
     if (grid > prm.n_tiles) grid = prm.n_tiles;

@@ -1,0 +1,162 @@
+"""Parity at BASELINE.json's full sizes (100-125 M symbols per GPU), where the CPU oracle is too slow
+to be the checker: size-independent properties of the path, each comparing two INDEPENDENT
+implementations of the same quantity or two decompositions of the same input.
+
+* sortedness / uniqueness of hit positions;
+* the k-mer decision-table scan == thresholding the dense scores of a different kernel;
+* the fused AND scan == intersection of the sequence scan and the structure-only scan;
+* shard invariance: scanning two overlapping halves and keeping owned starts == scanning the whole
+  (the multi-GPU decomposition, shard.plan_shards);
+* background counts: sum over shards == whole, and == a torch.bincount of the same bytes;
+* the tensor-core batched path == the per-motif CUDA-core loop;
+* idempotence: a second run returns bit-identical arrays;
+* a bounded random sample of positions is re-scored by the CPU oracle (bit-exact).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_FULL = 100_000_000          # BASELINE configs 2/3: 100 Mnt
+
+
+@pytest.fixture(scope="module")
+def env():
+    import bench
+    from rnascan_b200 import device as dev
+    dev.require_cuda()
+    device = torch.device("cuda", 0)
+    shard = bench.make_device_shard(N_FULL, 4242, "c4", device)
+    n = shard["n"]
+
+    class Stream(object):
+        pass
+    st = Stream()
+    st.codes, st.n, st.kind = shard["codes"], n, "rna"
+    st.offsets, st.lengths = shard["offsets"], shard["lengths"]
+    pf = dev.ProfileStream.from_device(shard["prof"], n)
+    counts = dev.histogram(st).cpu().numpy()
+    ts, tq = bench.make_tables_fn("c4")(counts)
+    return {"dev": dev, "st": st, "pf": pf, "ts": ts, "tq": tq, "counts": counts, "shard": shard, "bench": bench}
+
+
+def test_counts_full_size(env):
+    dev, st = env["dev"], env["st"]
+    want = torch.bincount(st.codes[:st.n].to(torch.int64), minlength=256)[:8].cpu().numpy()
+    assert np.array_equal(env["counts"], want)
+    # generic 3-plane kernel and the sum over two shards agree
+    st.kind = None
+    assert np.array_equal(dev.histogram(st).cpu().numpy(), want)
+    st.kind = "rna"
+    half = (st.n // 2) // 256 * 256
+
+    class Part(object):
+        pass
+    a, b = Part(), Part()
+    a.codes, a.n, a.kind = st.codes, half, "rna"
+    b.codes, b.n, b.kind = st.codes[half:], st.n - half, "rna"
+    assert np.array_equal(dev.histogram(a).cpu().numpy() + dev.histogram(b).cpu().numpy(), want)
+
+
+def test_sequence_scan_full_size(env):
+    dev, st, ts = env["dev"], env["st"], env["ts"]
+    pos, sc = dev.scan_seq(st, ts, 6.0)
+    assert len(pos) > 100_000 and np.all(np.diff(pos) > 0)
+    # an independent kernel: dense scores (dense_w_kernel) thresholded on the device
+    dense = dev.dense_seq(st, ts)
+    keep = torch.nonzero(dense.double() > 6.0).flatten()
+    assert np.array_equal(pos, keep.cpu().numpy())
+    assert np.array_equal(sc.view(np.uint32), dense[keep].cpu().numpy().view(np.uint32))
+    # idempotence
+    pos2, sc2 = dev.scan_seq(st, ts, 6.0)
+    assert np.array_equal(pos, pos2) and np.array_equal(sc.view(np.uint32), sc2.view(np.uint32))
+    env["seq_hits"] = (pos, sc)
+
+
+def test_shard_invariance_full_size(env):
+    """Two ranks' view of the same stream: pieces overlap by W-1 symbols, each keeps the starts it owns."""
+    dev, st, ts = env["dev"], env["st"], env["ts"]
+    W = ts.shape[0]
+    pos, sc = env.get("seq_hits") or dev.scan_seq(st, ts, 6.0)
+    cut = (st.n // 2) // 256 * 256 + 256          # 16-byte aligned piece start
+
+    class Part(object):
+        pass
+    a, b = Part(), Part()
+    a.codes, a.n = st.codes, cut + W - 1          # owns starts [0, cut)
+    b.codes, b.n = st.codes[cut:], st.n - cut     # owns starts [cut, n)
+    pa, sa = dev.scan_seq(a, ts, 6.0)
+    pb, sb = dev.scan_seq(b, ts, 6.0)
+    keep = pa < cut
+    got_pos = np.concatenate([pa[keep], pb + cut])
+    got_sc = np.concatenate([sa[keep], sb])
+    assert np.array_equal(got_pos, pos)
+    assert np.array_equal(got_sc.view(np.uint32), sc.view(np.uint32))
+
+
+def test_fused_scan_is_the_intersection_full_size(env):
+    dev, st, pf, ts, tq = env["dev"], env["st"], env["pf"], env["ts"], env["tq"]
+    thr = 2.0                                       # low enough for thousands of joint hits
+    pos, sq, sb = dev.scan_fused(st, pf, ts, tq, thr)
+    assert len(pos) > 1000 and np.all(np.diff(pos) > 0)
+    ps, ss = dev.scan_seq(st, ts, thr)
+    pq, _, sq_only = dev.scan_fused(st, pf, None, tq, thr)
+    both, ia, ib = np.intersect1d(ps, pq, assume_unique=True, return_indices=True)
+    assert np.array_equal(pos, both)
+    assert np.array_equal(sq.view(np.uint32), ss[ia].view(np.uint32))
+    assert np.array_equal(sb.view(np.uint64), sq_only[ib].view(np.uint64))
+    env["fused"] = (pos, sq, sb, thr)
+
+
+def test_sampled_positions_against_the_cpu_oracle(env, oracle):
+    """Bit-exact re-score of hits and of random windows by the oracle on the bytes/rows they cover."""
+    from rnascan_b200 import synth
+    dev, st, pf, ts, tq = env["dev"], env["st"], env["pf"], env["ts"], env["tq"]
+    pos, sq, sb, thr = env.get("fused") or (dev.scan_fused(st, pf, ts, tq, 2.0) + (2.0,))
+    W = ts.shape[0]
+    rng = np.random.default_rng(1)
+    pick = rng.choice(len(pos), size=min(300, len(pos)), replace=False)
+    for k in pick.tolist():
+        p = int(pos[k])
+        codes = st.codes[p:p + W].cpu().numpy()
+        rows = pf.rows[p:p + W].cpu().numpy()
+        a = oracle.seq_scores(synth.to_text(codes, "rna"), ts)
+        b = oracle.profile_scores(rows, tq)
+        assert a.view(np.uint32)[0] == sq[k:k + 1].view(np.uint32)[0]
+        assert b.view(np.uint64)[0] == sb[k:k + 1].view(np.uint64)[0]
+        assert float(a[0]) > thr and b[0] > thr
+    # random windows through the dense kernels
+    starts = rng.integers(0, st.n - 4096, size=40)
+    dense = dev.dense_seq(st, ts)
+    for s0 in starts.tolist():
+        codes = st.codes[s0:s0 + 2048 + W - 1].cpu().numpy()
+        want = oracle.seq_scores(synth.to_text(codes, "rna"), ts)
+        got = dense[s0:s0 + 2048].cpu().numpy()
+        nan = np.isnan(want)
+        assert np.array_equal(nan, np.isnan(got))
+        assert np.array_equal(want[~nan].view(np.uint32), got[~nan].view(np.uint32))
+
+
+def test_batched_paths_agree_full_size(env):
+    dev, st, pf, bench = env["dev"], env["st"], env["pf"], env["bench"]
+    tables = bench.make_tables_fn("c5")
+    ss, qs = tables(env["counts"])
+    M = 64                                          # a quarter of config 5's motifs keeps the CUDA-core loop short
+    tsl = [ss[m, :tables.widths[m]] for m in range(M)]
+    tql = [qs[m, :tables.widths[m]] for m in range(M)]
+    a = dev.scan_batched(st, pf, tsl, tql, 6.0, path=1)
+    b = dev.scan_batched(st, pf, tsl, tql, 6.0, path=2)
+    assert len(a[1]) > 100
+    for x, y in zip(a, b):
+        assert np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8))
+    motif, pos = a[0], a[1]
+    key = motif.astype(np.int64) * (1 << 40) + pos
+    assert np.all(np.diff(key) > 0)                 # grouped by motif, sorted by position
