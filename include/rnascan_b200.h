@@ -93,6 +93,28 @@ int rs_host_log_odds(const double *prob, const double *bg, int W, int A, double 
 int rs_host_annotate_structures(const char *text, const int64_t *offsets, const int64_t *lengths,
                                 int64_t n_structs, char *out, int *status);
 
+/* ---- hits.tab text from hit arrays (replaces the per-record DataFrames + pd.concat + pd.merge +
+ * DataFrame.to_csv of rnascan.py:284-286,401-413,416-434,555-567; same bytes) -------------------
+ * Strings come as (blob, offsets[n+1]) pairs indexed by rec[r]; Start = start0[r] + 1,
+ * End = start0[r] + width; fragments are text[text_pos[r] .. +width) (NULL prints ".").
+ * score kinds: 0 float32 (already rounded) as numpy float32 text; 1 the same widened to a Python
+ * float; 2 float64 with Python's round(x, 3) applied here; 3 float64 unrounded (averaged profiles).
+ * Returns RS_OK and *written; RS_ERR_WORKSPACE when `capacity` is too small (*written = need);
+ * RS_ERR_INVALID when a value is outside the covered text formats (caller falls back).        */
+int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const int64_t *rec, const char *id_blob,
+                        const int64_t *id_off, const char *desc_blob, const int64_t *desc_off,
+                        const char *motif_id, const int64_t *start0, int64_t width, const uint8_t *text,
+                        const int64_t *text_pos, int score_kind, const void *scores, char *out,
+                        int64_t capacity, int64_t *written);
+int rs_host_format_hits_combined(int64_t n_rows, int64_t match_id_first, const int64_t *rec,
+                                 const char *id_blob, const int64_t *id_off, const char *desc_blob,
+                                 const int64_t *desc_off, const char *sdesc_blob, const int64_t *sdesc_off,
+                                 const char *motif_seq, const char *motif_struct, const int64_t *start0,
+                                 int64_t width, const uint8_t *seq_text, const uint8_t *struct_text,
+                                 const int64_t *text_pos, int seq_kind, const float *seq_scores,
+                                 int struct_kind, const double *struct_scores, char *out, int64_t capacity,
+                                 int64_t *written);
+
 /* ---- background counts (replaces the Seq.count loop of rnascan.py:450-453) ---------
  * d_counts8[k] += number of symbols with index k and bit 3 clear (k = 0..7); exact
  * integers.  The caller zeroes d_counts8 first (so shards can accumulate).            */

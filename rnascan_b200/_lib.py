@@ -43,6 +43,11 @@ _SIGS = {
     "rs_host_encode_struct": ([_vp, _i64, _vp], _int),
     "rs_host_log_odds": ([_vp, _vp, _int, _int, _vp], _int),
     "rs_host_annotate_structures": ([_vp, _vp, _vp, _i64, _vp, _vp], _int),
+    "rs_host_format_hits": ([_i64, _i64, _vp, ctypes.c_char_p, _vp, ctypes.c_char_p, _vp, ctypes.c_char_p, _vp, _i64,
+                             _vp, _vp, _int, _vp, _vp, _i64, _vp], _int),
+    "rs_host_format_hits_combined": ([_i64, _i64, _vp, ctypes.c_char_p, _vp, ctypes.c_char_p, _vp, ctypes.c_char_p,
+                                      _vp, ctypes.c_char_p, ctypes.c_char_p, _vp, _i64, _vp, _vp, _vp, _int, _vp,
+                                      _int, _vp, _vp, _i64, _vp], _int),
     "rs_hist": ([_vp, _i64, _vp, _vp], _int),
     "rs_hist_rna": ([_vp, _i64, _vp, _vp], _int),
     "rs_scores_dense_seq": ([_vp, _i64, _vp, _int, _vp, _vp], _int),

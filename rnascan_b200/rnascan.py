@@ -478,6 +478,9 @@ def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
     if kind == "struct" and not pm._is_structure():
         raise NotImplementedError("GPU scoring supports the nucleotide and BEHLMRT structure alphabets")
     width = pm.length
+    if _world_size() == 1 and restrict is None:
+        hits = _scan_fasta_hits(fasta_file, pssm, alphabet, minscore)
+        return hits.frame(), hits.n_records
     parts, n_records = [], 0
     for b, batch in enumerate(_cached_batches(fasta_file, alphabet)):
         pos, rec, start0, scores = _scan_batch(batch, pm, kind, minscore)
@@ -505,6 +508,158 @@ def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
     logodds = _round3_f32(scores) if kind == "rna" else _round3_f64(scores)
     return _assemble_fasta_frame(n_records, rec, ids, descs, motif_id, start0, width, fragments,
                                  logodds), n_records
+
+
+NATIVE_WRITER_MIN_ROWS = 50000       # from this many rows on main() formats hits.tab natively (no DataFrame)
+
+
+class _Hits(object):
+    """Hits of one FASTA input as plain arrays, one part per device batch (single process).
+    `frame()` gives the DataFrame the reference builds; `write_native()` the same text without
+    creating a Python object per row (rs_host_format_hits)."""
+
+    def __init__(self, motif_id, width, kind):
+        self.motif_id, self.width, self.kind = motif_id, width, kind
+        self.ids, self.descs, self.parts = [], [], []        # parts: (batch, pos, rec_global, start0, scores)
+
+    def add(self, batch, pos, rec, start0, scores):
+        self.parts.append((batch, pos, rec + len(self.ids), start0, scores))
+        self.ids.extend(batch.ids)
+        self.descs.extend(batch.descriptions)
+
+    @property
+    def n_records(self):
+        return len(self.ids)
+
+    def total(self):
+        return int(sum(len(p[1]) for p in self.parts))
+
+    def per_record(self):
+        rec = np.concatenate([p[2] for p in self.parts]) if self.parts else np.zeros(0, np.int64)
+        return np.bincount(rec, minlength=self.n_records) if self.n_records else np.zeros(0, np.int64)
+
+    def any_record_without_hits(self):
+        return self.n_records > 1 and bool((self.per_record() == 0).any())
+
+    def frame(self):
+        if self.n_records == 0:
+            return pd.DataFrame()
+        rec = np.concatenate([p[2] for p in self.parts])
+        start0 = np.concatenate([p[3] for p in self.parts])
+        scores = np.concatenate([p[4] for p in self.parts])
+        fragments = [f for p in self.parts for f in _fragments(p[0].raw(), p[1], self.width)]
+        logodds = _round3_f32(scores) if self.kind == "rna" else _round3_f64(scores)
+        return _assemble_fasta_frame(self.n_records, rec, self.ids, self.descs, self.motif_id, start0,
+                                     self.width, fragments, logodds)
+
+    def write_native(self, out):
+        """hits.tab of modes RNA / SS.  Returns False (nothing written) when a value falls outside
+        the formats the native writer covers; the caller then uses frame().to_csv()."""
+        blobs = _StringBlobs(self.ids, self.descs)
+        if self.kind == "rna":                     # float32 text unless a record has no hit (H8, a17)
+            kind = 1 if self.any_record_without_hits() else 0
+        else:
+            kind = 2
+        header = "\t".join(["Sequence_ID", "Description", "Motif_ID", "Start", "End", "Sequence", "LogOdds",
+                            "Match_ID"]) + "\n"
+        first, started = 1, False
+        for batch, pos, rec, start0, scores in self.parts:
+            sc = _round3_f32(scores) if self.kind == "rna" else np.ascontiguousarray(scores, np.float64)
+            for a in range(0, len(pos), NATIVE_CHUNK_ROWS):
+                b = min(len(pos), a + NATIVE_CHUNK_ROWS)
+                text = _native_rows(b - a, first, rec[a:b], blobs, None, self.motif_id, None, start0[a:b],
+                                    self.width, batch.raw(), None, pos[a:b], kind, sc[a:b], None, None)
+                if text is None:
+                    if started:
+                        raise ValueError("hit score outside the text formats of the native hits.tab writer")
+                    return False
+                if not started:
+                    _emit(out, header)
+                    started = True
+                _emit(out, text)
+                first += b - a
+        if not started:
+            _emit(out, header)
+        return True
+
+
+class _StringBlobs(object):
+    """Per-record id and description strings as (utf-8 blob, offsets) pairs for the C writer."""
+
+    def __init__(self, ids, descs):
+        self.id_blob, self.id_off = self._pack(ids)
+        self.desc_blob, self.desc_off = self._pack(descs)
+
+    @staticmethod
+    def _pack(strings):
+        enc = [s.encode("utf-8") for s in strings]
+        off = np.zeros(len(enc) + 1, np.int64)
+        if enc:
+            np.cumsum([len(e) for e in enc], out=off[1:])
+        return b"".join(enc), off
+
+
+def _native_rows(n_rows, match_first, rec, blobs, sblobs, motif_a, motif_b, start0, width, text_a, text_b,
+                 text_pos, kind_a, scores_a, kind_b, scores_b):
+    """Text of n_rows hits.tab rows from arrays (single-modality when motif_b is None, combined
+    otherwise); None when the native formatter declines."""
+    from . import _lib
+    if n_rows == 0:
+        return ""
+    rec = np.ascontiguousarray(rec, np.int64)
+    start0 = np.ascontiguousarray(start0, np.int64)
+    text_pos = np.ascontiguousarray(text_pos, np.int64)
+    text_a = None if text_a is None else np.ascontiguousarray(text_a, np.uint8)
+    text_b = None if text_b is None else np.ascontiguousarray(text_b, np.uint8)
+    ptr = lambda a: 0 if a is None else a.ctypes.data
+    capacity = int(n_rows) * 160 + 4096
+    written = np.zeros(1, np.int64)
+    while True:
+        out = np.empty(capacity, np.uint8)
+        if motif_b is None:
+            rc = _lib.lib.rs_host_format_hits(
+                n_rows, match_first, rec.ctypes.data, blobs.id_blob, blobs.id_off.ctypes.data, blobs.desc_blob,
+                blobs.desc_off.ctypes.data, motif_a.encode("utf-8"), start0.ctypes.data, width, ptr(text_a),
+                text_pos.ctypes.data, kind_a, scores_a.ctypes.data, out.ctypes.data, capacity, written.ctypes.data)
+        else:
+            rc = _lib.lib.rs_host_format_hits_combined(
+                n_rows, match_first, rec.ctypes.data, blobs.id_blob, blobs.id_off.ctypes.data, blobs.desc_blob,
+                blobs.desc_off.ctypes.data, None if sblobs is None else sblobs.desc_blob,
+                0 if sblobs is None else sblobs.desc_off.ctypes.data, motif_a.encode("utf-8"),
+                motif_b.encode("utf-8"), start0.ctypes.data, width, ptr(text_a), ptr(text_b), text_pos.ctypes.data,
+                kind_a, scores_a.ctypes.data, kind_b, scores_b.ctypes.data, out.ctypes.data, capacity,
+                written.ctypes.data)
+        if rc == _lib.RS_ERR_WORKSPACE:
+            capacity = int(written[0]) + 64
+            continue
+        if rc != _lib.RS_OK:
+            return None
+        return out[:int(written[0])].tobytes().decode("utf-8", "replace")
+
+
+NATIVE_CHUNK_ROWS = 4_000_000        # rows formatted per call (bounds the text buffer to ~0.5 GB)
+
+
+def _emit(out, text):
+    """Write to a text stream, through its binary buffer when it has one (sys.stdout)."""
+    if hasattr(out, "buffer"):
+        out.flush()
+        out.buffer.write(text.encode("utf-8"))
+    else:
+        out.write(text)
+
+
+def _scan_fasta_hits(fasta_file, pssm, alphabet, minscore):
+    """Single-process scan of a FASTA input as a _Hits object."""
+    motif_id, pm = _first_motif(pssm)
+    kind = _kind_of(alphabet)
+    if kind == "struct" and not pm._is_structure():
+        raise NotImplementedError("GPU scoring supports the nucleotide and BEHLMRT structure alphabets")
+    hits = _Hits(motif_id, pm.length, kind)
+    for batch in _cached_batches(fasta_file, alphabet):
+        pos, rec, start0, scores = _scan_batch(batch, pm, kind, minscore)
+        hits.add(batch, pos, rec, start0, scores)
+    return hits
 
 
 # one parsed + uploaded input is reused by compute_background and the scan that follows it
@@ -540,7 +695,7 @@ def _profile_files(directory):
     return structures
 
 
-def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None):
+def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None, want_arrays=False):
     """All ``structure.<id>.txt`` profiles of a directory in one launch (rnascan.py:348-375).
     With `seq_batches`/`seq_pm` (combined mode) the sequence PSSM is evaluated in the same
     kernel and only windows passing BOTH thresholds come back.  Under torchrun every rank
@@ -588,16 +743,21 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     if len(codes):
         stream = device.SymbolStream(codes, offsets, lengths)
         profile = device.ProfileStream(device.pack_profiles(profiles, dtype=np.float64))
-        pos, _, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
+        pos, seq_scores, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
         rec, start0 = stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
     else:
         rec = start0 = np.zeros(0, np.int64)
         scores = np.zeros(0, np.float64)
+        seq_scores = None
     hit_names = [names[r] for r in rec.tolist()]
+    arrays = None
+    if want_arrays and size == 1 and seq_table is not None:
+        arrays = (list(hit_names), start0.copy(), np.zeros(0, np.float32) if seq_scores is None else seq_scores,
+                  np.asarray(scores, np.float64))
     if size > 1:
         gathered = shard.gather_objects((hit_names, start0, scores))
         if gathered is None:
-            return pd.DataFrame(), n_files
+            return (pd.DataFrame(), n_files, None) if want_arrays else (pd.DataFrame(), n_files)
         hit_names = [x for g in gathered for x in g[0]]
         start0 = np.concatenate([g[1] for g in gathered])
         scores = np.concatenate([g[2] for g in gathered])
@@ -610,7 +770,7 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         "Sequence": np.array(["."] * n, dtype=object),
         "LogOdds": np.asarray(scores, dtype=np.float64).astype(object),
     })
-    return frame, n_files
+    return (frame, n_files, arrays) if want_arrays else (frame, n_files)
 
 
 def scan_main(fasta_file, pssm, alphabet, bg, args):
@@ -715,11 +875,51 @@ def load_background(bg_file, uniform, *args):
 ###############################################################################
 # Main
 ###############################################################################
-def _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, args):
-    """Structure side of the combined mode, restricted on the device to windows whose
-    SEQUENCE score also passes (the inner join of rnascan.py:422 keeps nothing else).
-    Returns None when the restriction cannot be applied (then the caller scans the structure
-    input on its own)."""
+class _Joint(object):
+    """Windows where BOTH scores pass, as arrays in the order of the sequence input (= the order of
+    the reference's inner join, whose left side is the sequence frame)."""
+
+    def __init__(self):
+        self.rec = self.start0 = self.text_pos = np.zeros(0, np.int64)
+        self.seq_scores = np.zeros(0, np.float32)
+        self.struct_scores = np.zeros(0, np.float64)
+        self.struct_kind = 2               # 2 one-hot (rounded when printed), 3 averaged (unrounded)
+        self.seq_raw = self.struct_raw = None
+        self.struct_descs = None           # per seq record, or None: empty Description.Struct
+        self.struct_frame = None           # callable -> the restricted structure frame (DataFrame path)
+
+    def write_native(self, out, seq_hits, motif_struct, width):
+        blobs = _StringBlobs(seq_hits.ids, seq_hits.descs)
+        sblobs = None if self.struct_descs is None else _StringBlobs(seq_hits.ids, self.struct_descs)
+        seq_kind = 1 if seq_hits.any_record_without_hits() else 0
+        header = "\t".join(["Sequence_ID", "Description.Seq", "Motif_ID.Seq", "Start", "End", "Sequence.Seq",
+                            "LogOdds.Seq", "Description.Struct", "Motif_ID.Struct", "Sequence.Struct",
+                            "LogOdds.Struct", "LogOdds.SeqStruct", "Match_ID"]) + "\n"
+        seq_sc = _round3_f32(self.seq_scores)
+        str_sc = np.ascontiguousarray(self.struct_scores, np.float64)
+        started = False
+        for a in range(0, max(len(self.rec), 1), NATIVE_CHUNK_ROWS):
+            b = min(len(self.rec), a + NATIVE_CHUNK_ROWS)
+            text = _native_rows(b - a, 1 + a, self.rec[a:b], blobs, sblobs, seq_hits.motif_id, motif_struct,
+                                self.start0[a:b], width, self.seq_raw, self.struct_raw, self.text_pos[a:b],
+                                seq_kind, seq_sc[a:b], self.struct_kind, str_sc[a:b])
+            if text is None:
+                if started:
+                    raise ValueError("hit score outside the text formats of the native hits.tab writer")
+                return False
+            if not started:
+                _emit(out, header)
+                started = True
+            _emit(out, text)
+        return True
+
+
+def _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args):
+    """Structure side of the combined mode, restricted ON THE DEVICE to windows whose sequence
+    score also passes (the inner join of rnascan.py:422 keeps nothing else): one fused launch
+    instead of a second full scan + merge.  Returns a _Joint, or None when the restriction cannot
+    be applied (different motif widths, duplicate ids, inputs that do not line up) -- the caller
+    then scans the structure input on its own and merges as the reference does."""
     from . import device
     _, seq_pm = _first_motif(seq_pssm)
     motif_id, pm = _first_motif(struct_pssm)
@@ -730,12 +930,28 @@ def _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, ar
     ids = [i for b in seq_batches for i in b.ids]
     if len(set(ids)) != len(ids):
         return None                       # duplicate ids join across records: keep the plain path
+    width = pm.length
+    joint = _Joint()
     if os.path.isdir(struct_file):
         eprint("Scanning averaged secondary structures ")
-        frame, count = _scan_profile_dir(struct_file, struct_pssm, args.minscore, args.debug,
-                                         seq_batches=seq_batches, seq_pm=seq_pm)
+        frame, count, arrays = _scan_profile_dir(struct_file, struct_pssm, args.minscore, args.debug,
+                                                 seq_batches=seq_batches, seq_pm=seq_pm, want_arrays=True)
         eprint("Processed %d sequences" % count)
-        return frame
+        joint.struct_frame = lambda: frame
+        if arrays is None or len(seq_batches) != 1 or _world_size() > 1:
+            joint.rec = None              # frames only
+            return joint
+        names, start0, seq_sc, str_sc = arrays
+        index = {rid: k for k, rid in enumerate(seq_batches[0].ids)}
+        rec = np.array([index.get(nm, -1) for nm in names], dtype=np.int64)
+        keep = rec >= 0
+        order = np.lexsort((start0[keep], rec[keep]))            # sequence-record order, then Start
+        joint.rec, joint.start0 = rec[keep][order], start0[keep][order]
+        joint.seq_scores, joint.struct_scores = seq_sc[keep][order], str_sc[keep][order]
+        joint.struct_kind = 3
+        joint.seq_raw = seq_batches[0].raw()
+        joint.text_pos = seq_batches[0].stream.offsets[joint.rec] + joint.start0
+        return joint
     alphabet = ContextualSecondaryStructure()
     struct_batches = _cached_batches(struct_file, alphabet)
     if len(struct_batches) != len(seq_batches) or any(
@@ -744,31 +960,44 @@ def _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, ar
         return None
     eprint("Scanning sequences ")
     ts, tq = _table_for(seq_pm, "rna"), _table_for(pm, "struct")
-    width = pm.length
     parts, n_records = [], 0
     for sb, qb in zip(seq_batches, struct_batches):
-        pos, _, scores = device.scan_pair_onehot(sb.stream, qb.stream, ts, tq, args.minscore)
+        pos, seq_sc, scores = device.scan_pair_onehot(sb.stream, qb.stream, ts, tq, args.minscore)
         keep, rec, start0 = qb.locate(pos)
         pos = pos[keep]
-        parts.append((rec[keep] + n_records, start0[keep], scores[keep], _fragments(qb.raw(), pos, width),
-                      qb.ids, qb.descriptions))
+        parts.append((rec[keep] + n_records, start0[keep], scores[keep], _fragments(qb.raw(), pos, width)
+                      if (_world_size() > 1 or len(seq_batches) > 1) else None, qb.ids, qb.descriptions,
+                      pos, seq_sc[keep]))
         n_records += len(qb.ids)
     eprint("Processed %d sequences" % n_records)
-    if _world_size() > 1:
-        parts = _gather_parts(parts, n_records, parts[0][4] if parts else [], parts[0][5] if parts else [])
-        if parts is None:
+    single = _world_size() == 1 and len(seq_batches) == 1
+
+    def struct_frame():
+        ps = parts
+        if _world_size() > 1:
+            ps = _gather_parts([p[:6] for p in parts], n_records, parts[0][4] if parts else [],
+                               parts[0][5] if parts else [])
+            if ps is None:
+                return pd.DataFrame()
+            ps = [ps[0]] + [(p[0], p[1], p[2], p[3], [], []) for p in ps[1:]]
+        if n_records == 0:
             return pd.DataFrame()
-        parts = [parts[0]] + [(p[0], p[1], p[2], p[3], [], []) for p in parts[1:]]
-    if n_records == 0:
-        return pd.DataFrame()
-    rec = np.concatenate([p[0] for p in parts])
-    ids = [i for p in parts for i in p[4]]
-    descs = [d for p in parts for d in p[5]]
-    frame = _assemble_fasta_frame(n_records, rec, ids, descs, motif_id,
-                                  np.concatenate([p[1] for p in parts]), width,
-                                  [f for p in parts for f in p[3]],
-                                  _round3_f64(np.concatenate([p[2] for p in parts])))
-    return frame
+        frags = [f for k, p in enumerate(ps)
+                 for f in (p[3] if p[3] is not None else _fragments(struct_batches[k].raw(), parts[k][6], width))]
+        return _assemble_fasta_frame(n_records, np.concatenate([p[0] for p in ps]),
+                                     [i for p in ps for i in p[4]], [d for p in ps for d in p[5]], motif_id,
+                                     np.concatenate([p[1] for p in ps]), width, frags,
+                                     _round3_f64(np.concatenate([p[2] for p in ps])))
+    joint.struct_frame = struct_frame
+    if not single:
+        joint.rec = None
+        return joint
+    p = parts[0]
+    joint.rec, joint.start0, joint.struct_scores, joint.seq_scores = p[0], p[1], p[2], p[7]
+    joint.text_pos = p[6]
+    joint.seq_raw, joint.struct_raw = seq_batches[0].raw(), struct_batches[0].raw()
+    joint.struct_descs = struct_batches[0].descriptions
+    return joint
 
 
 def main(argv=None):
@@ -780,6 +1009,9 @@ def main(argv=None):
     bg = None
     seq_file = struct_file = None
     seq_pssm = None
+    seq_hits = struct_hits = joint = None          # array-level results (single process, FASTA inputs)
+    seq_results = struct_results = None
+    arrays_ok = _world_size() == 1 and not args.testseq
 
     if args.testseq:
         testseq_stack = args.testseq.split(",")[::-1]
@@ -796,7 +1028,12 @@ def main(argv=None):
                 print(dict(bg))
             sys.exit()
         seq_pssm = load_motif(args.pfm_seq, args.pseudocount, rna, bg)
-        seq_results = scan_main(seq_file, seq_pssm, rna, bg, args)
+        if arrays_ok and not os.path.isdir(seq_file):
+            eprint("Scanning sequences ")
+            seq_hits = _scan_fasta_hits(seq_file, seq_pssm, rna, args.minscore)
+            eprint("Processed %d sequences" % seq_hits.n_records)
+        else:
+            seq_results = scan_main(seq_file, seq_pssm, rna, bg, args)
 
     if seq_type in ["SS", "RNASS"]:
         structure = ContextualSecondaryStructure()
@@ -814,23 +1051,44 @@ def main(argv=None):
                 print(dict(bg))
             sys.exit()
         struct_pssm = load_motif(args.pfm_struct, args.pseudocount, structure, bg)
-        struct_results = None
         if seq_type == "RNASS" and not args.testseq:
-            struct_results = _combined_scan(seq_file, struct_file, seq_pssm, struct_pssm, seq_results, args)
-        if struct_results is None:
-            struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
+            joint = _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args)
+        if joint is None:
+            if seq_type == "SS" and arrays_ok and not os.path.isdir(struct_file):
+                eprint("Scanning sequences ")
+                struct_hits = _scan_fasta_hits(struct_file, struct_pssm, structure, args.minscore)
+                eprint("Processed %d sequences" % struct_hits.n_records)
+            else:
+                struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
 
-    if rank != 0:
-        final = None
-    elif seq_type == "RNASS":
-        final = combine(seq_results, struct_results)
-    elif seq_type == "RNA":
-        final = seq_results
-    else:
-        final = struct_results
     if rank == 0:
-        _add_match_id(final)
-        final.to_csv(sys.stdout, sep="\t", index=False)
+        written = False
+        if seq_type == "RNASS":
+            if (joint is not None and joint.rec is not None and seq_hits is not None
+                    and len(joint.rec) >= NATIVE_WRITER_MIN_ROWS):
+                written = joint.write_native(sys.stdout, seq_hits, _first_motif(struct_pssm)[0],
+                                             _first_motif(struct_pssm)[1].length)
+        else:
+            hits = seq_hits if seq_type == "RNA" else struct_hits
+            if hits is not None and hits.n_records > 0 and hits.total() >= NATIVE_WRITER_MIN_ROWS:
+                written = hits.write_native(sys.stdout)
+        if not written:
+            if seq_results is None and seq_hits is not None:
+                seq_results = seq_hits.frame()
+            if struct_results is None and struct_hits is not None:
+                struct_results = struct_hits.frame()
+            if struct_results is None and joint is not None:
+                struct_results = joint.struct_frame()
+            if seq_type == "RNASS":
+                final = combine(seq_results, struct_results)
+            elif seq_type == "RNA":
+                final = seq_results
+            else:
+                final = struct_results
+            _add_match_id(final)
+            final.to_csv(sys.stdout, sep="\t", index=False)
+    elif joint is not None and joint.struct_frame is not None:
+        joint.struct_frame()              # other ranks take part in the gather
 
     runtime = float(time.time() - tic)
     if runtime > 60:

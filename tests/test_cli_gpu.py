@@ -42,6 +42,15 @@ def same(a, b):
 
 
 @pytest.mark.parametrize("name", ALIGNED)
+def test_cli_output_is_byte_identical_native_writer(name, in_repo, monkeypatch):
+    """Same golden files through the C++ hits.tab formatter (rs_host_format_hits*), which main() uses
+    from NATIVE_WRITER_MIN_ROWS rows on instead of building DataFrames."""
+    from rnascan_b200 import rnascan as ms
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 0)
+    test_cli_output_is_byte_identical(name, in_repo)
+
+
+@pytest.mark.parametrize("name", ALIGNED)
 def test_cli_output_is_byte_identical(name, in_repo):
     case = CASES[name]
     with open(os.path.join(CLI, name + ".stdout")) as fh:
@@ -79,6 +88,20 @@ def test_averaged_cli_is_label_aligned_not_the_py3_misaligned_variant(in_repo):
     assert best[i_start] == "213" and float(best[i_str]) > 10.0              # the SLBP stem-loop
     # sequence column is unaffected by the alignment question
     assert [r.split("\t")[i_seq] for r in rows[1:]] == [r.split("\t")[i_seq] for r in mrows[1:]]
+
+
+def test_averaged_combined_native_writer_equals_dataframe_path(in_repo, monkeypatch):
+    """FASTA + profile directory (mode RNASS, averaged): the array/native-writer path and the
+    DataFrame + merge path print the same bytes, at -m -inf and at a threshold."""
+    from rnascan_b200 import rnascan as ms
+    base = CASES["rnass_avg_example_misaligned"]["argv"]
+    for extra in ([], ["-m", "-3"]):
+        argv = [a for a in base if a not in ("-m", " -inf")] + (extra or ["-m", " -inf"])
+        monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 10 ** 9)
+        frames = run_cli(argv)[0]
+        monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 0)
+        native = run_cli(argv)[0]
+        assert frames == native and frames.count("\n") > 5
 
 
 # ----------------------------------------------------------------------------- API level

@@ -406,3 +406,54 @@ def test_profile_averaging_matches_the_reference():
     prof = structure.profile_from_fragments(11, [(-3, "((...))"), (2, "..((...))"), (4, "(....)")])
     assert all(abs(sum(prof[l][i] for l in prof) - 1.0) < 1e-12 for i in range(11))
     assert prof["L"][0] == 1.0 and prof["E"][2] == 0.5
+
+
+# ----------------------------------------------------------------------------- native hits.tab writer
+def test_native_writer_text_equals_pandas_to_csv():
+    """rs_host_format_hits vs DataFrame.to_csv on random rows: float32 text, widened float32,
+    Python round(x, 3) of float64, unrounded float64 (incl. huge/small magnitudes), csv quoting."""
+    import io
+    import pandas as pd
+    from rnascan_b200 import rnascan as ms
+    rng = np.random.default_rng(0)
+    n, W = 5000, 5
+    ids = ["id%d" % k for k in range(7)] + ['we"ird', "tab\there"]
+    descs = ["desc %d" % k for k in range(7)] + ['has "quotes" inside', ""]
+    blobs = ms._StringBlobs(ids, descs)
+    rec = np.sort(rng.integers(0, len(ids), size=n))
+    start0 = rng.integers(0, 10_000_000, size=n)
+    raw = rng.choice(np.frombuffer(b"ACGUN", np.uint8), size=4096)
+    tpos = rng.integers(0, 4096 - W, size=n)
+    frags = [raw[p:p + W].tobytes().decode() for p in tpos]
+    f32 = np.round((rng.normal(size=n) * 30).astype(np.float32), 3)
+    f32[:5] = [0.0, -0.0, 0.001, 123456.7, -999.999]
+    f64 = rng.normal(size=n) * 30
+    f64[:8] = [0.0005, 2.0005, 1e-7, -1.7976931348623157e308, 1234567.891, 2.5, -0.00049, 1e15]
+
+    def frame(scores):
+        return pd.DataFrame({"Sequence_ID": np.array(ids, object)[rec], "Description": np.array(descs, object)[rec],
+                             "Motif_ID": "m", "Start": start0 + 1, "End": start0 + W, "Sequence": frags,
+                             "LogOdds": scores, "Match_ID": np.arange(1, n + 1)})
+
+    def csv(df):
+        b = io.StringIO()
+        df.to_csv(b, sep="\t", index=False, header=False)
+        return b.getvalue()
+    for kind, arr, col in ((0, f32, f32), (1, f32, f32.astype(object)),
+                           (2, f64, np.array([round(v, 3) for v in f64.tolist()], dtype=object))):
+        got = ms._native_rows(n, 1, rec, blobs, None, "m", None, start0, W, raw, None, tpos, kind,
+                              np.ascontiguousarray(arr), None, None)
+        assert got == csv(frame(col)), kind
+    # combined rows: float32 + unrounded float64 + their sum
+    got = ms._native_rows(n, 1, rec, blobs, None, "ms", "mq", start0, W, raw, None, tpos, 0, f32, 3, f64)
+    df = pd.DataFrame({"Sequence_ID": np.array(ids, object)[rec], "Description.Seq": np.array(descs, object)[rec],
+                       "Motif_ID.Seq": "ms", "Start": start0 + 1, "End": start0 + W, "Sequence.Seq": frags,
+                       "LogOdds.Seq": f32, "Description.Struct": "", "Motif_ID.Struct": "mq",
+                       "Sequence.Struct": ".", "LogOdds.Struct": f64})
+    df["LogOdds.SeqStruct"] = df["LogOdds.Seq"] + df["LogOdds.Struct"]
+    df["Match_ID"] = np.arange(1, n + 1)
+    assert got == csv(df)
+    # out-of-range float32 text is declined (the caller falls back to pandas)
+    bad = f32.copy()
+    bad[3] = 3e9
+    assert ms._native_rows(n, 1, rec, blobs, None, "m", None, start0, W, raw, None, tpos, 0, bad, None, None) is None

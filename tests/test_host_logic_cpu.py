@@ -10,7 +10,16 @@ import test_cli_gpu as gpu_cases
 from oracle_backend import install
 
 FUNCS = [getattr(gpu_cases, n) for n in dir(gpu_cases) if n.startswith("test_")
-         and n not in ("test_cli_output_is_byte_identical", "test_pwm_module_signature_and_errors")]
+         and n not in ("test_cli_output_is_byte_identical", "test_cli_output_is_byte_identical_native_writer",
+                       "test_pwm_module_signature_and_errors")]
+
+
+@pytest.mark.parametrize("name", gpu_cases.ALIGNED)
+def test_cli_native_writer_against_golden(name, in_repo, monkeypatch):
+    from rnascan_b200 import rnascan as ms
+    install(monkeypatch)
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 0)
+    _call(gpu_cases.test_cli_output_is_byte_identical, name=name, in_repo=in_repo)
 
 
 @pytest.mark.parametrize("name", gpu_cases.ALIGNED)
@@ -32,7 +41,7 @@ def test_api_host_logic_against_golden(fn, in_repo, golden_api, capsys, monkeypa
     install(monkeypatch)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        _call(fn, in_repo=in_repo, golden_api=golden_api, capsys=capsys)
+        _call(fn, in_repo=in_repo, golden_api=golden_api, capsys=capsys, monkeypatch=monkeypatch)
 
 
 # ----------------------------------------------------------------------------- two ranks (gloo)
