@@ -104,6 +104,42 @@ def test_averaged_combined_native_writer_equals_dataframe_path(in_repo, monkeypa
         assert frames == native and frames.count("\n") > 5
 
 
+def test_every_position_structure_scan_through_the_cli(tmp_path, in_repo, oracle):
+    """BASELINE config 3 in small: one-hot structure FASTA, -m -inf, every scorable window is a row of
+    hits.tab (native writer); rows are rebuilt here from the oracle's dense scores."""
+    from rnascan_b200 import synth
+    from rnascan_b200 import rnascan as ms
+    rng = np.random.default_rng(33)
+    lengths = synth.record_lengths(60_000, 40, rng)
+    codes, off = synth.struct_codes(lengths, rng)
+    text = synth.to_text(codes, "struct").decode()
+    recs = text.split("\n")[:-1]
+    fa = tmp_path / "contexts.fa"
+    with open(fa, "w") as fh:
+        for k, r in enumerate(recs):
+            fh.write(">s%d structure %d\n" % (k, k))
+            for a in range(0, len(r), 70):
+                fh.write(r[a:a + 70] + "\n")
+    pfm = os.path.join(INP, "test_struct_pfm.txt")
+    out, err, code = run_cli(["-q", pfm, "-u", "-C", "0.01", "-m", " -inf", str(fa)])
+    assert code == 0 and "Processed 40 sequences" in err
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    pm = ms.pfm2pssm(pfm, 0.01, ContextualSecondaryStructure(), None)
+    tab = np.array([pm[c] for c in "BEHLMRT"]).T.copy()
+    W = tab.shape[0]
+    want = ["Sequence_ID\tDescription\tMotif_ID\tStart\tEnd\tSequence\tLogOdds\tMatch_ID"]
+    k = 0
+    for r_i, r in enumerate(recs):
+        sc = oracle.alpha_scores(r, tab, "BEHLMRT")
+        for i, v in enumerate(sc.tolist()):
+            if v > float("-inf"):
+                k += 1
+                want.append("s%d\ts%d structure %d\ttest_struct_pfm\t%d\t%d\t%s\t%r\t%d"
+                            % (r_i, r_i, r_i, i + 1, i + W, r[i:i + W], round(v, 3), k))
+    assert k > 50_000
+    assert out.splitlines() == want
+
+
 # ----------------------------------------------------------------------------- API level
 def _pssm(golden_api, name):
     from rnascan_b200 import rnascan as ms

@@ -37,11 +37,12 @@ def _call(fn, **available):
 
 
 @pytest.mark.parametrize("fn", FUNCS, ids=[f.__name__ for f in FUNCS])
-def test_api_host_logic_against_golden(fn, in_repo, golden_api, capsys, monkeypatch):
+def test_api_host_logic_against_golden(fn, in_repo, golden_api, capsys, monkeypatch, tmp_path, oracle):
     install(monkeypatch)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        _call(fn, in_repo=in_repo, golden_api=golden_api, capsys=capsys, monkeypatch=monkeypatch)
+        _call(fn, in_repo=in_repo, golden_api=golden_api, capsys=capsys, monkeypatch=monkeypatch,
+              tmp_path=tmp_path, oracle=oracle)
 
 
 # ----------------------------------------------------------------------------- two ranks (gloo)
