@@ -577,7 +577,7 @@ def host_sample(n_symbols, workload, seed=4999, min_records=1):
         codes, offsets = synth.struct_codes(lengths, rng)
         return lengths, offsets, codes, None
     codes, offsets = synth.rna_codes(lengths, rng)
-    rows = synth.profile_rows(len(codes), rng, lengths=lengths) if workload == "c4" else None
+    rows = synth.profile_rows(len(codes), rng, lengths=lengths) if workload in ("c4", "c5") else None
     return lengths, offsets, codes, rows
 
 
@@ -637,11 +637,18 @@ def run_reference(args):
     wl = args.workload
     cores = os.cpu_count() or 1
     tables = make_tables_fn(wl)
-    rate = ref_driver.calibrate(wl, tables, W_MOTIF, THRESHOLD)          # windows/s on one core
-    target_s = float(os.environ.get("RNASCAN_REF_STEP_SECONDS", "8"))
-    n_symbols = int(max(2000, min(50_000_000, rate * cores * target_s)))
-    # the reference parallelises over records only: keep >= 2 records per core in the sample
-    lengths, offsets, codes, rows = host_sample(n_symbols, wl, seed=5999, min_records=2 * cores)
+    target_s = float(os.environ.get("RNASCAN_REF_STEP_SECONDS", "5"))
+    # size the per-step sample from a calibration pass through the SAME Pool fan-out (load imbalance
+    # between records included), so that one step takes about target_s seconds on this box
+    rate1 = ref_driver.calibrate(wl, tables, W_MOTIF, THRESHOLD)          # windows/s on one core
+    n_cal = int(max(300 if wl == "c5" else 2000, min(5_000_000, rate1 * cores * 1.0)))
+    lengths, offsets, codes, rows = host_sample(n_cal, wl, seed=5998, min_records=8 * cores)
+    t0 = time.perf_counter()
+    ref_driver.run_step(wl, lengths, offsets, codes, rows, tables, W_MOTIF, THRESHOLD, cores)
+    rate = scored_positions(lengths, W_MOTIF) / max(time.perf_counter() - t0, 1e-6)      # windows/s, all cores
+    n_symbols = int(max(300 if wl == "c5" else 2000, min(50_000_000, rate * target_s)))
+    # the reference parallelises over records only: keep >= 8 records per core in the sample
+    lengths, offsets, codes, rows = host_sample(n_symbols, wl, seed=5999, min_records=8 * cores)
     positions = scored_positions(lengths, W_MOTIF)
     times = []
     for it in range(args.warmup + args.steps):
@@ -659,7 +666,8 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64 accumulate -> f32 (sequence), f64 (structure)", "data": "synthetic (bounded sample)",
            "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile",
-                                   "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan"}[wl],
+                                   "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan",
+                                   "c5": "C5 batched 256 motif pairs, one reference run per pair"}[wl],
                       "W": W_MOTIF, "minscore": THRESHOLD, "sample_symbols": len(codes)},
            "gpu_launches": 0,
            "cpu_baseline": {"value": value, "unit": "Gpos/s", "cores": cores,

@@ -64,7 +64,8 @@ def describe(workload):
            % ("reference-compiled" if k == "reference" else "C-port"))
     avg = "pandas .iloc + np.dot + nan_to_num per (window, row) as rnascan.py:302-307"
     one = "pure-Python dict lookups per (window, row) as matrix.py:25-43"
-    return {"c2": seq, "c3": one, "c4": seq + " AND " + avg}[workload]
+    return {"c2": seq, "c3": one, "c4": seq + " AND " + avg,
+            "c5": "for each of the 256 motif pairs: " + seq + " AND " + avg}[workload]
 
 
 # ----------------------------------------------------------------------------- per-record work
@@ -120,6 +121,13 @@ def _scan_averaged(rows, pssm_frame, threshold):
 def _record_task(task):
     workload, text, rows, seq_pssm, str_pssm, m, threshold = task
     hits = 0
+    if workload == "c5":                         # one rnascan run per motif pair
+        import pandas as pd
+        for sp, qp in zip(seq_pssm, str_pssm):
+            w = len(sp["A"])
+            hits += _search_seq(text, sp, w, threshold)
+            hits += _scan_averaged(rows, pd.DataFrame({c: qp[c] for c in "BEHLMRT"}), threshold)
+        return hits
     if workload in ("c2", "c4"):
         hits += _search_seq(text, seq_pssm, m, threshold)
     if workload == "c3":
@@ -133,6 +141,10 @@ def _record_task(task):
 # ----------------------------------------------------------------------------- steps
 def _pssm_dicts(workload, tables, codes):
     counts = np.array([(codes == k).sum() for k in range(8)], np.int64)
+    if workload == "c5":
+        tsl, tql = tables.lists(counts)
+        return ([{l: t[:, k].tolist() for k, l in enumerate("ACGU")} for t in tsl],
+                [{l: t[:, k].tolist() for k, l in enumerate("BEHLMRT")} for t in tql])
     ts, tq = tables(counts)
     seq_pssm = None if ts is None else {l: ts[:, k].tolist() for k, l in enumerate("ACGU")}
     str_pssm = None if tq is None else {l: tq[:, k].tolist() for k, l in enumerate("BEHLMRT")}
@@ -153,6 +165,8 @@ def _tasks(workload, lengths, offsets, codes, rows, tables, m, threshold):
 def calibrate(workload, tables, m, threshold, windows=300):
     """scored positions per second of ONE core on a small record."""
     from rnascan_b200 import synth
+    if workload == "c5":
+        windows = 12
     rng = np.random.default_rng(1)
     lengths = np.array([windows + m - 1], np.int64)
     if workload == "c3":
@@ -160,7 +174,7 @@ def calibrate(workload, tables, m, threshold, windows=300):
         rows = None
     else:
         codes, offsets = synth.rna_codes(lengths, rng, n_frac=0.0)
-        rows = synth.profile_rows(len(codes), rng, lengths=lengths) if workload == "c4" else None
+        rows = synth.profile_rows(len(codes), rng, lengths=lengths) if workload in ("c4", "c5") else None
     tasks = _tasks(workload, lengths, offsets, codes, rows, tables, m, threshold)
     _record_task(tasks[0])                       # imports, first-call costs
     t0 = time.perf_counter()
