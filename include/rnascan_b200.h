@@ -75,6 +75,16 @@ int64_t     rs_scan_workspace_bytes(int64_t n, int64_t hit_capacity);
 int rs_prof_begin(int max_records);
 int rs_prof_end(float *ms_out, int capacity, int *n_records);
 
+/* ---- FASTA text -> symbol stream (replaces fileinput + Bio.SeqIO.parse, rnascan.py:170-174, and
+ * Seq.transcribe()/upper(), rnascan.py:186-193, for file inputs) -------------------------------
+ * Two passes over an ASCII buffer: rs_host_fasta_index sizes the outputs, rs_host_fasta_fill writes
+ * the pre-processed letters (text), their codes, per-record offsets/lengths and the header lines.
+ * kind 0 = RNA target alphabet (T->U, upper-cased), 1 = structure contexts (unchanged).      */
+int rs_host_fasta_index(const uint8_t *buf, int64_t n, int64_t *n_records, int64_t *n_symbols,
+                        int64_t *title_bytes);
+int rs_host_fasta_fill(const uint8_t *buf, int64_t n, int kind, uint8_t *text, uint8_t *codes,
+                       int64_t *rec_off, int64_t *rec_len, char *titles, int64_t *title_off);
+
 /* ---- host-side encoding (CPU threads; replaces str.upper()/transcribe() + the char
  *      switch of _pwm.c:41-63 and the dict lookup of matrix.py:36-41) ---------------- */
 int rs_host_encode_rna(const uint8_t *text, int64_t n, uint8_t *codes);

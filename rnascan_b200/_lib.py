@@ -39,6 +39,8 @@ _SIGS = {
     "rs_scan_workspace_bytes": ([_i64, _i64], _i64),
     "rs_prof_begin": ([_int], _int),
     "rs_prof_end": ([_vp, _int, _vp], _int),
+    "rs_host_fasta_index": ([_vp, _i64, _vp, _vp, _vp], _int),
+    "rs_host_fasta_fill": ([_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp], _int),
     "rs_host_encode_rna": ([_vp, _i64, _vp], _int),
     "rs_host_encode_struct": ([_vp, _i64, _vp], _int),
     "rs_host_log_odds": ([_vp, _vp, _int, _int, _vp], _int),

@@ -254,6 +254,89 @@ class _Batch(object):
         return self._raw
 
 
+class _LazyTexts(object):
+    """List-like view of the records of a packed text buffer; strings are made on demand."""
+
+    def __init__(self, raw, offsets, lengths):
+        self.raw, self.offsets, self.lengths = raw, offsets, lengths
+
+    def __len__(self):
+        return len(self.offsets)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        o, n = int(self.offsets[k]), int(self.lengths[k])
+        return self.raw[o:o + n].tobytes().decode("ascii")
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+def _read_fasta_bytes(fasta_file):
+    """The bytes fileinput would feed the parser (rnascan.py:173: .gz/.bz2 transparently, several
+    files chained)."""
+    import bz2
+    import gzip
+    paths = [fasta_file] if isinstance(fasta_file, str) else list(fasta_file)
+    chunks = []
+    for path in paths:
+        ext = os.path.splitext(path)[1]
+        opener = gzip.open if ext == ".gz" else (bz2.open if ext == ".bz2" else open)
+        with opener(path, "rb") as fh:
+            chunks.append(fh.read())
+    return b"\n".join(chunks)
+
+
+def _native_batch(fasta_file, alphabet):
+    """Parse + pre-process + encode a FASTA input in one native pass (rs_host_fasta_*); None when
+    the input is not plain ASCII or too large for one batch (the Python parser handles those)."""
+    from . import device, _lib
+    rna_target = _seq.is_ambiguous_rna_alphabet(alphabet)
+    kind = _kind_of(alphabet)
+    if kind == "rna" and not rna_target:
+        return None                                   # DNA target alphabets: no transcription (not a CLI path)
+    try:
+        data = _read_fasta_bytes(fasta_file)
+    except (OSError, EOFError):
+        return None
+    if not data.isascii():
+        return None
+    buf = np.frombuffer(data, dtype=np.uint8)
+    sizes = np.zeros(3, np.int64)
+    _lib.check(_lib.lib.rs_host_fasta_index(buf.ctypes.data if len(buf) else 0, len(buf), sizes[0:].ctypes.data,
+                                            sizes[1:].ctypes.data, sizes[2:].ctypes.data))
+    n_rec, n_sym, n_title = (int(v) for v in sizes)
+    if n_sym + n_rec > MAX_BATCH_SYMBOLS:
+        return None
+    text = np.empty(max(n_sym + n_rec, 1), np.uint8)
+    codes = np.empty(max(n_sym + n_rec, 1), np.uint8)
+    off = np.zeros(max(n_rec, 1), np.int64)
+    ln = np.zeros(max(n_rec, 1), np.int64)
+    titles = np.empty(max(n_title, 1), np.uint8)
+    toff = np.zeros(n_rec + 1, np.int64)
+    _lib.check(_lib.lib.rs_host_fasta_fill(buf.ctypes.data if len(buf) else 0, len(buf), 0 if kind == "rna" else 1,
+                                           text.ctypes.data, codes.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                           titles.ctypes.data, toff.ctypes.data))
+    text, codes, off, ln = text[:n_sym + n_rec], codes[:n_sym + n_rec], off[:n_rec], ln[:n_rec]
+    blob = titles[:n_title].tobytes().decode("ascii")
+    descs = [blob[a:b] for a, b in zip(toff[:-1].tolist(), toff[1:].tolist())]
+    ids = [(d.split(None, 1) or [""])[0] for d in descs]
+    batch = _Batch.__new__(_Batch)
+    batch.ids, batch.descriptions, batch.kind = ids, descs, kind
+    batch.texts = batch.full_texts = _LazyTexts(text, off, ln)
+    batch.record = np.arange(n_rec, dtype=np.int64)
+    batch.piece_start = np.zeros(n_rec, np.int64)
+    batch.own = None
+    batch.stream = device.SymbolStream(codes, off if n_rec else None, ln if n_rec else None, kind=kind) \
+        if n_rec else device.SymbolStream(np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int64), kind=kind)
+    batch._raw = text
+    return batch
+
+
+NATIVE_INGEST = True                 # tests switch it off to exercise the Python parser
+
+
 def _kind_of(alphabet):
     return "rna" if _seq.is_nucleotide_alphabet(alphabet) else "struct"
 
@@ -281,6 +364,12 @@ def _record_batches(fasta_file, alphabet, max_symbols=None):
     if size > 1:
         yield _sharded_batch(fasta_file, alphabet, _rank(), size)
         return
+    if NATIVE_INGEST and max_symbols is None:
+        batch = _native_batch(fasta_file, alphabet)
+        if batch is not None:
+            if len(batch.ids):
+                yield batch
+            return
     max_symbols = max_symbols or MAX_BATCH_SYMBOLS
     ids, descs, texts, size = [], [], [], 0
     for rec in parse_sequences(fasta_file):

@@ -457,3 +457,67 @@ def test_native_writer_text_equals_pandas_to_csv():
     bad = f32.copy()
     bad[3] = 3e9
     assert ms._native_rows(n, 1, rec, blobs, None, "m", None, start0, W, raw, None, tpos, 0, bad, None, None) is None
+
+
+# ----------------------------------------------------------------------------- native FASTA ingest
+def test_native_fasta_ingest_equals_the_python_parser(tmp_path):
+    """rs_host_fasta_index/_fill vs the Biopython-semantics Python parser (seq.iter_fasta + preprocess_seq +
+    pack_texts) on hostile FASTA text: CRLF / lone CR, blank lines, leading junk, blanks inside lines,
+    lower case, T/U, ambiguity codes, empty records, empty titles, no trailing newline, gzip."""
+    import gzip
+    import random
+    from rnascan_b200 import rnascan as ms, device
+    from rnascan_b200.seq import IUPAC
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    rnd = random.Random(3)
+
+    def fake(k):
+        out = ["junk before the first record\n", "more junk\n"] if k % 3 == 0 else []
+        for r in range(rnd.randint(0, 12)):
+            title = rnd.choice(["", "id%d" % r, "id%d some words\t tabbed " % r, "  leading blank %d" % r,
+                                "id%d\x1c odd" % r])
+            out.append(">" + title + rnd.choice(["\n", "\r\n", "\r", " \n", "\t\n"]))
+            for _ in range(rnd.randint(0, 6)):
+                line = "".join(rnd.choice("ACGTUacgtunNRY-BEHLMRTbehlmrt. ") for _ in range(rnd.randint(0, 70)))
+                out.append(line + rnd.choice(["\n", "\r\n", "\r", "  \n", "\n\n"]))
+        text = "".join(out)
+        return text[:-1] if (k % 4 == 0 and text.endswith("\n")) else text
+
+    def python_path(path, alphabet, kind):
+        recs = list(ms.parse_sequences(path))
+        texts = [str(ms.preprocess_seq(r, alphabet)) for r in recs]
+        codes, off, ln = device.pack_texts(texts, kind)
+        return [r.id for r in recs], [r.description for r in recs], texts, codes, off, ln
+
+    for k in range(40):
+        path = str(tmp_path / ("f%d.fa%s" % (k, ".gz" if k % 5 == 0 else "")))
+        data = fake(k).encode("ascii")
+        if path.endswith(".gz"):
+            with gzip.open(path, "wb") as fh:
+                fh.write(data)
+        else:
+            with open(path, "wb") as fh:
+                fh.write(data)
+        for alphabet, kind in ((IUPAC.IUPACUnambiguousRNA(), "rna"), (ContextualSecondaryStructure(), "struct")):
+            ids, descs, texts, codes, off, ln = python_path(path, alphabet, kind)
+            data_b = ms._read_fasta_bytes(path)
+            buf = np.frombuffer(data_b, np.uint8)
+            sizes = np.zeros(3, np.int64)
+            from rnascan_b200 import _lib
+            _lib.check(_lib.lib.rs_host_fasta_index(buf.ctypes.data if len(buf) else 0, len(buf), sizes[0:].ctypes.data,
+                                                    sizes[1:].ctypes.data, sizes[2:].ctypes.data))
+            n_rec, n_sym, n_title = (int(v) for v in sizes)
+            assert n_rec == len(ids) and n_sym == int(ln.sum())
+            text = np.empty(max(n_sym + n_rec, 1), np.uint8); cds = np.empty(max(n_sym + n_rec, 1), np.uint8)
+            o = np.zeros(max(n_rec, 1), np.int64); l = np.zeros(max(n_rec, 1), np.int64)
+            titles = np.empty(max(n_title, 1), np.uint8); toff = np.zeros(n_rec + 1, np.int64)
+            _lib.check(_lib.lib.rs_host_fasta_fill(buf.ctypes.data if len(buf) else 0, len(buf), 0 if kind == "rna" else 1,
+                                                   text.ctypes.data, cds.ctypes.data, o.ctypes.data, l.ctypes.data,
+                                                   titles.ctypes.data, toff.ctypes.data))
+            assert np.array_equal(cds[:n_sym + n_rec], codes), (k, kind)
+            assert np.array_equal(o[:n_rec], off) and np.array_equal(l[:n_rec], ln)
+            assert text[:n_sym + n_rec].tobytes().decode() == "".join(t + "\n" for t in texts)
+            blob = titles[:n_title].tobytes().decode()
+            got_desc = [blob[a:b] for a, b in zip(toff[:-1].tolist(), toff[1:].tolist())]
+            assert got_desc == descs
+            assert [(d.split(None, 1) or [""])[0] for d in got_desc] == ids
