@@ -251,11 +251,15 @@ struct ExpandParams {
     int64_t n_segs, capacity;
     OrderDest od;
     int W;
-    double ta[8 * 4];
+    int ppm;                  // positions per mask word: 28 (k-mer scan) or 32 (ballot masks)
+    double ta[16 * 8];        // exact table, row stride A_STRIDE
 };
 
+// A = 4: float32 sequence scores (row stride 4); A = 7: float64 structure scores (row stride 8)
+template <int A>
 __global__ void __launch_bounds__(256) kmer_expand_kernel(const __grid_constant__ ExpandParams prm)
 {
+    constexpr int TS = A == 4 ? 4 : 8;
     const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (seg >= prm.n_segs) return;
@@ -274,17 +278,206 @@ __global__ void __launch_bounds__(256) kmer_expand_kernel(const __grid_constant_
         if (lane >= d) incl += v;
     }
     unsigned long long k = bbase + slocal + (incl - cnt) + obase;
-    const int64_t g0 = seg * KM_SEG + (int64_t)lane * KM_P;       // segments tile the stream contiguously
+    const int64_t g0 = (seg * 32 + lane) * (int64_t)prm.ppm;      // segments tile the stream contiguously
     for (uint32_t h = hit; h; h &= h - 1, k++) {
         if ((int64_t)k >= prm.capacity) break;
         const int p = __ffs(h) - 1;
         const uint8_t *c = prm.codes + g0 + p;
         double s = 0.0;
-        for (int j = 0; j < prm.W; j++) s = __dadd_rn(s, prm.ta[j * 4 + (c[j] & 3)]);
+        for (int j = 0; j < prm.W; j++) s = __dadd_rn(s, prm.ta[j * TS + (c[j] & (A == 4 ? 3 : 7))]);
         prm.od.pos[k] = g0 + p;
-        prm.od.seq[k] = (float)s;                                  // _pwm.c:65
+        if (A == 4) prm.od.seq[k] = (float)s;                      // _pwm.c:65
+        else        prm.od.str[k] = s;                             // matrix.py:34-42
         if (prm.od.out_motif) prm.od.out_motif[k] = prm.od.motif_id;
     }
+}
+
+// ---- one-hot threshold scan, W <= 16, any alphabet: exact scores, hit bits by warp ballot ----------
+// Structure contexts (A = 7) and sequence motifs wider than the k-mer table (A = 4, 8 < W <= 16).
+// Same scoring loop as dense_w_kernel (onehot_scan.cu): lanes take consecutive windows, symbols are
+// fetched as aligned words + funnel shifts, one LDS.64 + one fp64 add per symbol in j order -- the
+// reference's arithmetic, so the ballot bit IS the decision (score > m, strict).  Instead of a dense
+// 4-8 B/position output each warp keeps 32 ballot words (1024 positions = one segment) and stores them
+// with one coalesced 128-byte write; ordering and exact output scores are the segment scan + expansion
+// shared with the k-mer scan.
+#define MS_THREADS 256
+#define MS_PER     32
+#define MS_TILE    (MS_THREADS * MS_PER)           // 8192 positions; 1024 per warp
+#define MS_STAGES  3
+#define MS_STAGE_BYTES (MS_TILE + 32)
+
+struct MaskScanParams {
+    const uint8_t *codes;
+    int64_t n, padded, n_tiles;
+    double threshold;
+    KmerWork wk;
+    double ta[16 * 8];
+};
+
+template <int A, int W>
+__global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_constant__ MaskScanParams prm)
+{
+    constexpr int NW = (W + 3) / 4;
+    constexpr int TS = 8;
+    __shared__ __align__(128) uint8_t s_stage[MS_STAGES * MS_STAGE_BYTES];
+    __shared__ __align__(16) double s_ta[W * TS];
+    __shared__ uint64_t bars[MS_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < W * TS; k += MS_THREADS) s_ta[k] = prm.ta[k];
+    if (tid == 0) {
+        for (int s = 0; s < MS_STAGES; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int64_t stride = gridDim.x, first = blockIdx.x;
+    const int64_t my_tiles = first < prm.n_tiles ? (prm.n_tiles - first + stride - 1) / stride : 0;
+    auto issue = [&](int64_t it) {
+        const int s = (int)(it % MS_STAGES);
+        const int64_t t0 = (first + it * stride) * MS_TILE;
+        const uint32_t bytes = (uint32_t)min((int64_t)MS_STAGE_BYTES, prm.padded - t0);
+        mbar_expect_tx(&bars[s], bytes);
+        bulk_g2s(s_stage + (size_t)s * MS_STAGE_BYTES, prm.codes + t0, bytes, &bars[s]);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < MS_STAGES - 1 && it < my_tiles; it++) issue(it);
+    const uint32_t tab = smem_u32(s_ta);
+
+    for (int64_t it = 0; it < my_tiles; it++) {
+        const int s = (int)(it % MS_STAGES);
+        if (tid == 0 && it + MS_STAGES - 1 < my_tiles) issue(it + MS_STAGES - 1);
+        mbar_wait(&bars[s], (uint32_t)((it / MS_STAGES) & 1));
+        const int64_t tile = first + it * stride;
+        const int64_t t0 = tile * MS_TILE;
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(s_stage + (size_t)s * MS_STAGE_BYTES);
+        uint32_t mine = 0, total = 0;
+#pragma unroll 4
+        for (int k = 0; k < MS_PER; k++) {
+            const int w = warp * (32 * MS_PER) + k * 32 + lane;
+            const uint32_t *q = words + (w >> 2);
+            const unsigned sh = (unsigned)(w & 3) * 8u;
+            uint32_t x[NW];
+            uint32_t prev = q[0];
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const uint32_t nxt = q[i + 1];
+                x[i] = __funnelshift_r(prev, nxt, sh);
+                prev = nxt;
+            }
+            uint32_t bad = 0;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const uint32_t m = (i == NW - 1 && (W & 3)) ? (0xFFFFFFFFu >> (32 - 8 * (W & 3))) : 0xFFFFFFFFu;
+                if (A == 4) bad |= x[i] & (0x0C0C0C0Cu & m);
+                else        bad |= x[i] & (x[i] >> 1) & (x[i] >> 2) & (0x01010101u & m);
+            }
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                const int sb = 8 * (j & 3);
+                const uint32_t off = sb >= 3 ? ((x[j >> 2] >> (sb - 3)) & 0x38u) : ((x[j >> 2] << 3) & 0x38u);
+                double t;
+                asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tab + (uint32_t)(j * TS * 8) + off));
+                sum = __dadd_rn(sum, t);
+            }
+            const double cmp = A == 4 ? (double)(float)sum : sum;          // _pwm.c:65 / note N1
+            const bool hit = !bad && cmp > prm.threshold && t0 + w + W <= prm.n;
+            const uint32_t b = __ballot_sync(0xffffffffu, hit);
+            if (lane == k) mine = b;
+            total += __popc(b);
+        }
+        const int64_t seg = tile * (MS_THREADS / 32) + warp;
+        prm.wk.mask[seg * 32 + lane] = mine;                               // one coalesced 128-byte store
+        if (lane == 0) prm.wk.segcnt[seg] = total;
+        __syncthreads();
+    }
+}
+
+template <int A, int W>
+static int launch_mask_scan(const MaskScanParams &prm, cudaStream_t stream)
+{
+    int64_t grid = (int64_t)rs_sm_count() * 6;
+    if (grid > prm.n_tiles) grid = prm.n_tiles;
+    rs_prof_start(stream);
+    mask_scan_kernel<A, W><<<(unsigned)grid, MS_THREADS, 0, stream>>>(prm);
+    rs_prof_stop(stream);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+template <int A>
+static int dispatch_mask_scan(int W, const MaskScanParams &prm, cudaStream_t stream)
+{
+    switch (W) {
+#define MS_CASE(w) case w: return launch_mask_scan<A, w>(prm, stream);
+        MS_CASE(1) MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6) MS_CASE(7) MS_CASE(8)
+        MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12) MS_CASE(13) MS_CASE(14) MS_CASE(15) MS_CASE(16)
+#undef MS_CASE
+    default: rs_set_error("internal: mask scan needs W <= 16"); return RS_ERR_INVALID;
+    }
+}
+
+static void carve_work(uint8_t *wk, int64_t n_masks, int64_t n_segs, int n_blocks, KmerWork &out)
+{
+    int64_t off = 0;
+    out.lut = wk + off;                               off += KM_LUT_BYTES;
+    out.mask = (uint32_t *)(wk + off);                off += rs_roundup(n_masks * 4, 256);
+    out.segcnt = (uint32_t *)(wk + off);              off += rs_roundup(n_segs * 4, 256);
+    out.seglocal = (uint32_t *)(wk + off);            off += rs_roundup(n_segs * 4, 256);
+    out.blockbase = (unsigned long long *)(wk + off); off += rs_roundup((int64_t)n_blocks * 8, 256);
+    out.ticket = (unsigned long long *)(wk + off);
+}
+
+template <int A>
+static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t n_segs, int n_blocks, int ppm,
+                            const double *table, int W, int64_t cap, int64_t *d_hit_pos, float *d_hit_seq,
+                            double *d_hit_str, uint64_t *d_counters2, cudaStream_t st)
+{
+    kmer_segscan_kernel<<<n_blocks, SS_THREADS, 0, st>>>(wk, n_segs, n_blocks, (unsigned long long *)d_counters2);
+    RS_CUDA(cudaGetLastError());
+    if (cap > 0) {
+        ExpandParams ep = {};
+        ep.codes = d_codes; ep.wk = wk; ep.n_segs = n_segs; ep.capacity = cap; ep.W = W; ep.ppm = ppm;
+        ep.od = OrderDest{d_hit_pos, d_hit_seq, d_hit_str, nullptr, nullptr, 0};
+        constexpr int TS = A == 4 ? 4 : 8;
+        for (int j = 0; j < W; j++)
+            for (int c = 0; c < A; c++) ep.ta[j * TS + c] = table[j * A + c];
+        const int64_t blocks = (n_segs * 32 + 255) / 256;
+        kmer_expand_kernel<A><<<(unsigned)blocks, 256, 0, st>>>(ep);
+        RS_CUDA(cudaGetLastError());
+    }
+    return RS_OK;
+}
+
+// One-hot threshold scan for W <= 16 (A = 7, or A = 4 beyond the k-mer table); called from onehot_scan.cu.
+template <int A>
+static int mask_scan_impl(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
+                          int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
+                          uint64_t *d_counters2, void *d_work, cudaStream_t st)
+{
+    WorkLayout wl = rs_work_layout(n, cap);
+    MaskScanParams prm = {};
+    prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.threshold = threshold;
+    prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
+    const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
+    const int n_blocks = (int)((n_segs + SS_CHUNK - 1) / SS_CHUNK);
+    carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
+    RS_CUDA(cudaMemsetAsync(prm.wk.ticket, 0, 8, st));
+    for (int j = 0; j < W; j++)
+        for (int c = 0; c < 8; c++) prm.ta[j * 8 + c] = c < A ? table[j * A + c] : 0.0;
+    int rc = dispatch_mask_scan<A>(W, prm, st);
+    if (rc) return rc;
+    return finish_mask_scan<A>(d_codes, prm.wk, n_segs, n_blocks, 32, table, W, cap, d_hit_pos, d_hit_seq, d_hit_str,
+                               d_counters2, st);
+}
+
+int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
+                         int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
+                         uint64_t *d_counters2, void *d_work, cudaStream_t st)
+{
+    if (A == 4) return mask_scan_impl<4>(d_codes, n, table, W, threshold, cap, d_hit_pos, d_hit_seq, nullptr,
+                                         d_counters2, d_work, st);
+    return mask_scan_impl<7>(d_codes, n, table, W, threshold, cap, d_hit_pos, nullptr, d_hit_str, d_counters2,
+                             d_work, st);
 }
 
 template <int W>
@@ -326,13 +519,7 @@ int rs_scan_seq_kmer(const uint8_t *d_codes, int64_t n, const double *table, int
     prm.n_tiles = (n + KM_TILE - 1) / KM_TILE;
     const int64_t n_segs = prm.n_tiles * KM_WARPS;
     const int n_blocks = (int)((n_segs + SS_CHUNK - 1) / SS_CHUNK);
-    int64_t off = 0;
-    prm.wk.lut = wk + off;                          off += KM_LUT_BYTES;
-    prm.wk.mask = (uint32_t *)(wk + off);           off += rs_roundup(prm.n_tiles * KM_CONSUMERS * 4, 256);
-    prm.wk.segcnt = (uint32_t *)(wk + off);         off += rs_roundup(n_segs * 4, 256);
-    prm.wk.seglocal = (uint32_t *)(wk + off);       off += rs_roundup(n_segs * 4, 256);
-    prm.wk.blockbase = (unsigned long long *)(wk + off); off += rs_roundup((int64_t)n_blocks * 8, 256);
-    prm.wk.ticket = (unsigned long long *)(wk + off);
+    carve_work(wk, prm.n_tiles * KM_CONSUMERS, n_segs, n_blocks, prm.wk);
     RS_CUDA(cudaMemsetAsync(prm.wk.ticket, 0, 8, st));
 
     KmerTable kt = {};
@@ -352,16 +539,6 @@ int rs_scan_seq_kmer(const uint8_t *d_codes, int64_t n, const double *table, int
     default: rs_set_error("internal: k-mer scan needs W <= 8"); return RS_ERR_INVALID;
     }
     if (rc) return rc;
-    kmer_segscan_kernel<<<n_blocks, SS_THREADS, 0, st>>>(prm.wk, n_segs, n_blocks, (unsigned long long *)d_counters2);
-    RS_CUDA(cudaGetLastError());
-    if (cap > 0) {
-        ExpandParams ep = {};
-        ep.codes = d_codes; ep.wk = prm.wk; ep.n_segs = n_segs; ep.capacity = cap; ep.W = W;
-        ep.od = OrderDest{d_hit_pos, d_hit_score, nullptr, nullptr, nullptr, 0};
-        for (int k = 0; k < W * 4; k++) ep.ta[k] = table[k];
-        const int64_t blocks = (n_segs * 32 + 255) / 256;
-        kmer_expand_kernel<<<(unsigned)blocks, 256, 0, st>>>(ep);
-        RS_CUDA(cudaGetLastError());
-    }
-    return RS_OK;
+    return finish_mask_scan<4>(d_codes, prm.wk, n_segs, n_blocks, KM_P, table, W, cap, d_hit_pos, d_hit_score, nullptr,
+                               d_counters2, st);
 }

@@ -379,3 +379,43 @@ def test_scan_seq_threshold_equal_to_a_score(dev, oracle):
     pos, sc = dev.scan_seq(st, tab, thr)
     wpos = oracle.search_hits(want, thr)
     assert np.array_equal(pos, wpos) and not np.any(sc.astype(np.float64) == thr)
+
+
+@pytest.mark.parametrize("W", [1, 3, 4, 7, 8, 11, 16, 17, 30])
+@pytest.mark.parametrize("q", ["q0.5", "q0.999"])
+def test_scan_struct_all_widths(dev, oracle, W, q):
+    """Structure threshold scan: ballot-mask kernel for W <= 16, generic kernel beyond."""
+    from rnascan_b200 import synth
+    st, codes, _ = make_stream(dev, 900_000, 250, seed=60 + W, kind="struct")
+    rng = np.random.default_rng(160 + W)
+    pfm = synth.pfm_rows(W, 7, rng)
+    if W % 4 == 0:
+        pfm[pfm < (0.02 if W <= 4 else 0.0005)] = 0.0          # some -inf log-odds, most windows still finite
+    tab = synth.pssm_table(pfm, background=[synth.SS_P[c] for c in "BEHLMRT"], pseudocount=0.0 if W % 4 == 0 else 0.01)
+    want = oracle.alpha_scores(synth.to_text(codes, "struct"), tab, "BEHLMRT")
+    thr = pick_threshold(want, q)
+    pos, sc = dev.scan_struct_onehot(st, tab, thr, capacity=1000)
+    wpos = oracle.search_hits(want, thr)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1023, 1024, 1025, 8191, 8192, 8193, 8192 + 1030, 3 * 8192])
+def test_scan_struct_tile_edges(dev, oracle, n):
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(n)
+    codes = rng.integers(0, 7, size=n).astype(np.uint8)
+    if n > 40:
+        codes[rng.integers(0, n, size=3)] = 0x0F
+        codes[n // 2] = 0xFF
+        codes[rng.integers(0, n, size=5)] |= 8
+        codes[n // 2] = 0xFF
+    st = dev.SymbolStream(codes)
+    for W in (5, 7, 16):
+        tab = synth.pssm_table(synth.pfm_rows(W, 7, rng))
+        want = oracle.alpha_scores(synth.to_text(codes, "struct"), tab, "BEHLMRT")
+        for thr in (-80.0, 0.0):
+            pos, sc = dev.scan_struct_onehot(st, tab, thr)
+            wpos = oracle.search_hits(want, thr)
+            assert np.array_equal(pos, wpos), (W, thr)
+            assert_same_float(sc, want[wpos])

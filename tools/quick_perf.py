@@ -50,6 +50,12 @@ for thr in (6.0, 2.0):
                               _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, _stream()))
     timeit("scan_seq thr=%g" % thr, f, 1)
     print("   hits", hb.counters.cpu().tolist())
+ss_hb = device.HitBuffers(n, n // 16, dev, want_seq=False)
+for thr in (3.0, 0.0):
+    def g():
+        check(lib.rs_scan_struct_onehot(_ptr(scodes), n, tq.ctypes.data, W, thr, ss_hb.capacity, _ptr(ss_hb.pos), _ptr(ss_hb.struct), _ptr(ss_hb.counters), _ptr(ss_hb.work), ss_hb.work_bytes, _stream()))
+    timeit("scan_struct thr=%g" % thr, g, 1)
+    print("   hits", ss_hb.counters.cpu().tolist())
 timeit("dense_seq", lambda: check(lib.rs_scores_dense_seq(_ptr(codes), n, ts.ctypes.data, W, _ptr(outf), _stream())), 5)
 timeit("dense_struct(f64 out)", lambda: check(lib.rs_scores_dense_struct(_ptr(scodes), n, tq.ctypes.data, W, _ptr(outd), _stream())), 9)
 absmax = pf.absrow_max()
