@@ -178,6 +178,9 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
 int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
                          int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
                          uint64_t *d_counters2, void *d_work, cudaStream_t st);
+int rs_scan_pair_masks(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes, int64_t n, const double *seq_table,
+                       const double *struct_table, int W, double threshold, int64_t cap, int64_t *d_hit_pos,
+                       float *d_hit_seq, double *d_hit_str, uint64_t *d_counters2, void *d_work, cudaStream_t st);
 int64_t rs_kmer_work_bytes(int64_t n);   // workspace of the W <= 8 sequence scan (kmer_scan.cu)
 
 int rs_scan_seq_kmer(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold, int64_t cap,

@@ -253,6 +253,8 @@ struct ExpandParams {
     int W;
     int ppm;                  // positions per mask word: 28 (k-mer scan) or 32 (ballot masks)
     double ta[16 * 8];        // exact table, row stride A_STRIDE
+    const uint8_t *codes_b;   // pair mode: structure stream scored with tb (row stride 8) into od.str
+    double tb[16 * 8];
 };
 
 // A = 4: float32 sequence scores (row stride 4); A = 7: float64 structure scores (row stride 8)
@@ -288,6 +290,12 @@ __global__ void __launch_bounds__(256) kmer_expand_kernel(const __grid_constant_
         prm.od.pos[k] = g0 + p;
         if (A == 4) prm.od.seq[k] = (float)s;                      // _pwm.c:65
         else        prm.od.str[k] = s;                             // matrix.py:34-42
+        if (A == 4 && prm.codes_b) {                               // pair mode: structure score of the same window
+            const uint8_t *cb = prm.codes_b + g0 + p;
+            double sb = 0.0;
+            for (int j = 0; j < prm.W; j++) sb = __dadd_rn(sb, prm.tb[j * 8 + (cb[j] & 7)]);
+            prm.od.str[k] = sb;
+        }
         if (prm.od.out_motif) prm.od.out_motif[k] = prm.od.motif_id;
     }
 }
@@ -308,79 +316,104 @@ __global__ void __launch_bounds__(256) kmer_expand_kernel(const __grid_constant_
 
 struct MaskScanParams {
     const uint8_t *codes;
+    const uint8_t *codes_b;   // PAIR: structure stream
     int64_t n, padded, n_tiles;
     double threshold;
     KmerWork wk;
     double ta[16 * 8];
+    double tb[16 * 8];        // PAIR: structure table
 };
 
+// exact one-hot score of the window starting at byte w of a staged tile; `bad` != 0 <=> invalid symbol
 template <int A, int W>
-__global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_constant__ MaskScanParams prm)
+__device__ __forceinline__ double ms_score(const uint32_t *words, int w, uint32_t tab, uint32_t &bad)
 {
     constexpr int NW = (W + 3) / 4;
+    const uint32_t *q = words + (w >> 2);
+    const unsigned sh = (unsigned)(w & 3) * 8u;
+    uint32_t x[NW];
+    uint32_t prev = q[0];
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const uint32_t nxt = q[i + 1];
+        x[i] = __funnelshift_r(prev, nxt, sh);
+        prev = nxt;
+    }
+    bad = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const uint32_t m = (i == NW - 1 && (W & 3)) ? (0xFFFFFFFFu >> (32 - 8 * (W & 3))) : 0xFFFFFFFFu;
+        if (A == 4) bad |= x[i] & (0x0C0C0C0Cu & m);
+        else        bad |= x[i] & (x[i] >> 1) & (x[i] >> 2) & (0x01010101u & m);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        const int sb = 8 * (j & 3);
+        const uint32_t off = sb >= 3 ? ((x[j >> 2] >> (sb - 3)) & 0x38u) : ((x[j >> 2] << 3) & 0x38u);
+        double t;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tab + (uint32_t)(j * 64) + off));
+        sum = __dadd_rn(sum, t);
+    }
+    return sum;
+}
+
+template <int A, int W, bool PAIR>
+__global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_constant__ MaskScanParams prm)
+{
     constexpr int TS = 8;
-    __shared__ __align__(128) uint8_t s_stage[MS_STAGES * MS_STAGE_BYTES];
+    constexpr int NSTREAM = PAIR ? 2 : 1;
+    constexpr int STAGES = PAIR ? 2 : MS_STAGES;          // static shared memory stays under 48 KB
+    __shared__ __align__(128) uint8_t s_stage[STAGES * NSTREAM * MS_STAGE_BYTES];
     __shared__ __align__(16) double s_ta[W * TS];
-    __shared__ uint64_t bars[MS_STAGES];
+    __shared__ __align__(16) double s_tb[PAIR ? W * TS : 1];
+    __shared__ uint64_t bars[STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < W * TS; k += MS_THREADS) s_ta[k] = prm.ta[k];
+    for (int k = tid; k < W * TS; k += MS_THREADS) {
+        s_ta[k] = prm.ta[k];
+        if (PAIR) s_tb[k] = prm.tb[k];
+    }
     if (tid == 0) {
-        for (int s = 0; s < MS_STAGES; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
     const int64_t stride = gridDim.x, first = blockIdx.x;
     const int64_t my_tiles = first < prm.n_tiles ? (prm.n_tiles - first + stride - 1) / stride : 0;
     auto issue = [&](int64_t it) {
-        const int s = (int)(it % MS_STAGES);
+        const int s = (int)(it % STAGES);
         const int64_t t0 = (first + it * stride) * MS_TILE;
         const uint32_t bytes = (uint32_t)min((int64_t)MS_STAGE_BYTES, prm.padded - t0);
-        mbar_expect_tx(&bars[s], bytes);
-        bulk_g2s(s_stage + (size_t)s * MS_STAGE_BYTES, prm.codes + t0, bytes, &bars[s]);
+        uint8_t *dst = s_stage + (size_t)s * NSTREAM * MS_STAGE_BYTES;
+        mbar_expect_tx(&bars[s], bytes * NSTREAM);
+        bulk_g2s(dst, prm.codes + t0, bytes, &bars[s]);
+        if (PAIR) bulk_g2s(dst + MS_STAGE_BYTES, prm.codes_b + t0, bytes, &bars[s]);
     };
     if (tid == 0)
-        for (int64_t it = 0; it < MS_STAGES - 1 && it < my_tiles; it++) issue(it);
-    const uint32_t tab = smem_u32(s_ta);
+        for (int64_t it = 0; it < STAGES - 1 && it < my_tiles; it++) issue(it);
+    const uint32_t tab = smem_u32(s_ta), tab_b = smem_u32(s_tb);
 
     for (int64_t it = 0; it < my_tiles; it++) {
-        const int s = (int)(it % MS_STAGES);
-        if (tid == 0 && it + MS_STAGES - 1 < my_tiles) issue(it + MS_STAGES - 1);
-        mbar_wait(&bars[s], (uint32_t)((it / MS_STAGES) & 1));
+        const int s = (int)(it % STAGES);
+        if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
+        mbar_wait(&bars[s], (uint32_t)((it / STAGES) & 1));
         const int64_t tile = first + it * stride;
         const int64_t t0 = tile * MS_TILE;
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(s_stage + (size_t)s * MS_STAGE_BYTES);
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(s_stage + (size_t)s * NSTREAM * MS_STAGE_BYTES);
+        const uint32_t *words_b = words + MS_STAGE_BYTES / 4;
         uint32_t mine = 0, total = 0;
 #pragma unroll 4
         for (int k = 0; k < MS_PER; k++) {
             const int w = warp * (32 * MS_PER) + k * 32 + lane;
-            const uint32_t *q = words + (w >> 2);
-            const unsigned sh = (unsigned)(w & 3) * 8u;
-            uint32_t x[NW];
-            uint32_t prev = q[0];
-#pragma unroll
-            for (int i = 0; i < NW; i++) {
-                const uint32_t nxt = q[i + 1];
-                x[i] = __funnelshift_r(prev, nxt, sh);
-                prev = nxt;
-            }
-            uint32_t bad = 0;
-#pragma unroll
-            for (int i = 0; i < NW; i++) {
-                const uint32_t m = (i == NW - 1 && (W & 3)) ? (0xFFFFFFFFu >> (32 - 8 * (W & 3))) : 0xFFFFFFFFu;
-                if (A == 4) bad |= x[i] & (0x0C0C0C0Cu & m);
-                else        bad |= x[i] & (x[i] >> 1) & (x[i] >> 2) & (0x01010101u & m);
-            }
-            double sum = 0.0;
-#pragma unroll
-            for (int j = 0; j < W; j++) {
-                const int sb = 8 * (j & 3);
-                const uint32_t off = sb >= 3 ? ((x[j >> 2] >> (sb - 3)) & 0x38u) : ((x[j >> 2] << 3) & 0x38u);
-                double t;
-                asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tab + (uint32_t)(j * TS * 8) + off));
-                sum = __dadd_rn(sum, t);
-            }
+            uint32_t bad;
+            const double sum = ms_score<A, W>(words, w, tab, bad);
             const double cmp = A == 4 ? (double)(float)sum : sum;          // _pwm.c:65 / note N1
-            const bool hit = !bad && cmp > prm.threshold && t0 + w + W <= prm.n;
+            bool hit = !bad && cmp > prm.threshold && t0 + w + W <= prm.n;
+            if (PAIR && hit) {                                             // both scores must pass (rnascan.py:416-434)
+                uint32_t bad_b;
+                const double sb = ms_score<7, W>(words_b, w, tab_b, bad_b);
+                hit = !bad_b && sb > prm.threshold;
+            }
             const uint32_t b = __ballot_sync(0xffffffffu, hit);
             if (lane == k) mine = b;
             total += __popc(b);
@@ -395,10 +428,11 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
 template <int A, int W>
 static int launch_mask_scan(const MaskScanParams &prm, cudaStream_t stream)
 {
-    int64_t grid = (int64_t)rs_sm_count() * 6;
+    int64_t grid = (int64_t)rs_sm_count() * (prm.codes_b ? 4 : 6);
     if (grid > prm.n_tiles) grid = prm.n_tiles;
     rs_prof_start(stream);
-    mask_scan_kernel<A, W><<<(unsigned)grid, MS_THREADS, 0, stream>>>(prm);
+    if (A == 4 && prm.codes_b) mask_scan_kernel<4, W, true><<<(unsigned)grid, MS_THREADS, 0, stream>>>(prm);
+    else mask_scan_kernel<A, W, false><<<(unsigned)grid, MS_THREADS, 0, stream>>>(prm);
     rs_prof_stop(stream);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
@@ -430,7 +464,8 @@ static void carve_work(uint8_t *wk, int64_t n_masks, int64_t n_segs, int n_block
 template <int A>
 static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t n_segs, int n_blocks, int ppm,
                             const double *table, int W, int64_t cap, int64_t *d_hit_pos, float *d_hit_seq,
-                            double *d_hit_str, uint64_t *d_counters2, cudaStream_t st)
+                            double *d_hit_str, uint64_t *d_counters2, cudaStream_t st,
+                            const uint8_t *d_codes_b = nullptr, const double *table_b = nullptr)
 {
     kmer_segscan_kernel<<<n_blocks, SS_THREADS, 0, st>>>(wk, n_segs, n_blocks, (unsigned long long *)d_counters2);
     RS_CUDA(cudaGetLastError());
@@ -441,6 +476,10 @@ static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t 
         constexpr int TS = A == 4 ? 4 : 8;
         for (int j = 0; j < W; j++)
             for (int c = 0; c < A; c++) ep.ta[j * TS + c] = table[j * A + c];
+        ep.codes_b = d_codes_b;
+        if (table_b)
+            for (int j = 0; j < W; j++)
+                for (int c = 0; c < 7; c++) ep.tb[j * 8 + c] = table_b[j * 7 + c];
         const int64_t blocks = (n_segs * 32 + 255) / 256;
         kmer_expand_kernel<A><<<(unsigned)blocks, 256, 0, st>>>(ep);
         RS_CUDA(cudaGetLastError());
@@ -468,6 +507,31 @@ static int mask_scan_impl(const uint8_t *d_codes, int64_t n, const double *table
     if (rc) return rc;
     return finish_mask_scan<A>(d_codes, prm.wk, n_segs, n_blocks, 32, table, W, cap, d_hit_pos, d_hit_seq, d_hit_str,
                                d_counters2, st);
+}
+
+// Two-stream AND scan (two-FASTA RNASS mode), W <= 16.
+int rs_scan_pair_masks(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes, int64_t n, const double *seq_table,
+                       const double *struct_table, int W, double threshold, int64_t cap, int64_t *d_hit_pos,
+                       float *d_hit_seq, double *d_hit_str, uint64_t *d_counters2, void *d_work, cudaStream_t st)
+{
+    WorkLayout wl = rs_work_layout(n, cap);
+    MaskScanParams prm = {};
+    prm.codes = d_seq_codes; prm.codes_b = d_struct_codes; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.threshold = threshold;
+    prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
+    const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
+    const int n_blocks = (int)((n_segs + SS_CHUNK - 1) / SS_CHUNK);
+    carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
+    RS_CUDA(cudaMemsetAsync(prm.wk.ticket, 0, 8, st));
+    for (int j = 0; j < W; j++)
+        for (int c = 0; c < 8; c++) {
+            prm.ta[j * 8 + c] = c < 4 ? seq_table[j * 4 + c] : 0.0;
+            prm.tb[j * 8 + c] = c < 7 ? struct_table[j * 7 + c] : 0.0;
+        }
+    int rc = dispatch_mask_scan<4>(W, prm, st);
+    if (rc) return rc;
+    return finish_mask_scan<4>(d_seq_codes, prm.wk, n_segs, n_blocks, 32, seq_table, W, cap, d_hit_pos, d_hit_seq,
+                               d_hit_str, d_counters2, st, d_struct_codes, struct_table);
 }
 
 int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,

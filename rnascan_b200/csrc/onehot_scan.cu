@@ -355,6 +355,9 @@ static int scan_impl(const uint8_t *ca, const uint8_t *cb, int64_t n, const doub
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
     if (A == 4 && !PAIR && W <= 8)       // exact k-mer decision table: one lookup decides 9-W positions
         return rs_scan_seq_kmer(ca, n, ta, W, threshold, cap, d_hit_pos, d_hit_seq, d_counters2, d_work, st);
+    if (PAIR && W <= 16)
+        return rs_scan_pair_masks(ca, cb, n, ta, tb, W, threshold, cap, d_hit_pos, d_hit_seq, d_hit_str, d_counters2,
+                                  d_work, st);
     if (!PAIR && W <= 16)                // compile-time width, ballot hit masks, segment scan + expansion
         return rs_scan_onehot_masks(A, ca, n, ta, W, threshold, cap, d_hit_pos, d_hit_seq, d_hit_str, d_counters2,
                                     d_work, st);
