@@ -430,7 +430,9 @@ def measure(args, wl, steps, ctx, full=True):
     k2 = max(2, min(steps, 5))
     h_codes = torch.empty(codes.shape, dtype=torch.uint8).pin_memory()
     h_codes.copy_(codes)
-    if wl == "c4":
+    if args.no_e2e:
+        pass
+    elif wl == "c4":
         h_prof = torch.empty(prof.shape, dtype=torch.float32).pin_memory()
         h_prof.copy_(prof)
         torch.cuda.synchronize()
@@ -685,6 +687,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--n-per-gpu", type=int, default=125_000_000, dest="n_per_gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e",
+                    help="skip the host-buffer end-to-end leg (e.g. for shards too large to pin on the host)")
     ap.add_argument("--no-others", action="store_true", dest="no_others",
                     help="skip the brief runs of the other configurations (other_workloads)")
     ap.add_argument("--c5-path", default="auto", choices=["auto", "cuda", "tensor"], dest="c5_path")
