@@ -346,12 +346,24 @@ def measure(args, wl, steps, ctx, full=True):
         hb.work = torch.empty(hb.work_bytes, dtype=torch.uint8, device=device)
         check(lib.rs_set_batched_path({"auto": 0, "cuda": 1, "tensor": 2}[args.c5_path]))
     launches = [0]
+    bgscan = None
+    if wl == "c4" and not args.serial_bg:
+        # the structure-only candidate scan overlaps histogram -> all-reduce -> host log-odds (side stream);
+        # rs_refine_hits_seq applies the sequence PSSM to the candidates (device.BackgroundFusedScan)
+        bgscan = dev.BackgroundFusedScan(n, device, capacity=hb.capacity)
+        hb = bgscan.hb
+        tq_fixed = tables(np.zeros(8, np.int64))[1]
 
     def all_reduce(t):
         if world > 1:
             dist.all_reduce(t)
 
     def step():
+        if bgscan is not None:
+            bgscan.launch(codes, prof, _lib.RS_F32, W_MOTIF, tq_fixed, lambda c: tables(c)[0], THRESHOLD, absmax,
+                          all_reduce if world > 1 else None)
+            launches[0] += bgscan.launches
+            return
         counts.zero_()
         check((lib.rs_hist if wl == "c3" else lib.rs_hist_rna)(_ptr(codes), n, _ptr(counts), sptr)); launches[0] += 1
         all_reduce(counts)                                  # the path's only collective
@@ -422,6 +434,8 @@ def measure(args, wl, steps, ctx, full=True):
     kernel_ms = float(kms[:int(nrec[0])].sum()) / steps if nrec[0] else float("nan")
     n_launch = launches[0]
     hits = int(hb.counters[0].item()) if wl in ("c4", "c2") else None
+    if bgscan is not None and int(hb.cand_counters[0].item()) > hb.capacity:
+        raise SystemExit("candidate buffer overflowed: %d > %d" % (int(hb.cand_counters[0].item()), hb.capacity))
     if wl == "c5":
         hits = int(c5_bases[-1].item())
 
@@ -520,7 +534,10 @@ def measure(args, wl, steps, ctx, full=True):
                                 "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure" % N_MOTIFS_C5}[wl],
                    "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
                    "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
-                   "background": "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step",
+                   "background": ("computed every step: histogram -> all-reduce(int64[8]) -> host log-odds on a side "
+                                  "stream, overlapped with the structure-only candidate scan; the sequence PSSM is "
+                                  "applied to the candidates afterwards (rs_refine_hits_seq)") if bgscan is not None else
+                                 "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step",
                    "l2_policy": ("L2 flushed between timed steps (512 MB overwrite, untimed); inputs %.2f GB per GPU"
                                  if flush_l2 else "inputs (%.2f GB per GPU) exceed the 126 MB L2") % (input_bytes / 1e9),
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
@@ -689,6 +706,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e",
                     help="skip the host-buffer end-to-end leg (e.g. for shards too large to pin on the host)")
+    ap.add_argument("--serial-bg", action="store_true", dest="serial_bg",
+                    help="c4: histogram -> tables -> one-pass AND scan, strictly in sequence (no overlap)")
     ap.add_argument("--no-others", action="store_true", dest="no_others",
                     help="skip the brief runs of the other configurations (other_workloads)")
     ap.add_argument("--c5-path", default="auto", choices=["auto", "cuda", "tensor"], dest="c5_path")

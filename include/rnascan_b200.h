@@ -189,6 +189,23 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
                   int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
                   uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
 
+/* ---- sequence half of the combined decision, applied to an ordered candidate list -------
+ * combine() (rnascan.py:416-434) joins two result sets thresholded with the same -m, so a
+ * combined hit = structure score > m AND sequence score > m.  Only the sequence side depends
+ * on the data's background (rnascan.py:507-511; the averaged-profile mode cannot compute a
+ * structure background, rnascan.py:533-540).  A caller can therefore run the structure-only
+ * candidate scan (rs_scan_fused, RS_MODE_STRUCT) while rs_hist, the all-reduce of the counts
+ * and the host log-odds are still in flight on another stream, and then call this:
+ * the first min(*d_n_candidates, hit_capacity) entries of d_hit_pos (ascending) / d_hit_struct
+ * (may be NULL) are the candidates; windows whose sequence score (_pwm.c:34-68 arithmetic,
+ * float32) also exceeds `threshold` are kept IN PLACE, in order, with their scores in d_hit_seq;
+ * d_counters2[0] = survivors.  d_n_candidates (device) must not alias d_counters2.  Results are
+ * identical to rs_scan_fused in RS_MODE_AND with the same tables.                          */
+int rs_refine_hits_seq(const uint8_t *d_codes, int64_t n, const double *seq_table_Wx4, int W,
+                       double threshold, const uint64_t *d_n_candidates, int64_t hit_capacity,
+                       int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                       uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
+
 /* ---- batched many-PFM scan (BASELINE config 5: 256 RNAcompete-style motif pairs) -------
  * The reference scans one PFM (pair) per process run; a motif collection means running
  * rnascan.py:490-576 once per motif.  Here all motifs are scanned over the SAME resident

@@ -62,6 +62,7 @@ _SIGS = {
                              _vp], _int),
     "rs_scan_fused": ([_vp, _vp, _int, _i64, _vp, _vp, _int, _dbl, _dbl, _int, _i64, _vp, _vp, _vp, _vp,
                        _vp, _i64, _vp], _int),
+    "rs_refine_hits_seq": ([_vp, _i64, _vp, _int, _dbl, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_scan_batched_workspace_bytes": ([_i64, _int, _int, _i64], _i64),
     "rs_set_batched_path": ([_int], _int),
     "rs_last_batched_path": ([], _int),

@@ -168,6 +168,46 @@ struct OrderDest {
 int rs_order_hits(const HitStage &st, int64_t n_tiles, const OrderDest &dst, void *d_scan_tmp,
                   cudaStream_t stream);
 
+// Append this tile's hits (bit i of `mask` = window i of this thread, consecutive windows
+// per thread) to the staging area in position order.  All threads of the CTA call it.
+template <int THREADS, typename RECOMPUTE>
+__device__ __forceinline__ void emit_tile_hits(const HitStage &st, int64_t tile, unsigned mask, int nbits,
+                                               RECOMPUTE recompute)
+{
+    __shared__ unsigned s_warp[THREADS / 32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned cnt = __popc(mask);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        unsigned v = s_warp[w];
+        if (w < warp) before += v;
+        total += v;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long base = atomicAdd(st.counters, (unsigned long long)total);   // one atomic per tile
+        s_base = base;
+        st.tile_seg[tile] = make_ulonglong2(base, (unsigned long long)total);
+    }
+    __syncthreads();
+    unsigned long long k = s_base + before + (incl - cnt);
+    for (int i = 0; i < nbits; i++) {
+        if (mask & (1u << i)) {
+            if ((int64_t)k < st.capacity) recompute(i, (int64_t)k);
+            k++;
+        }
+    }
+}
+
 #define RS_MIN_TILE 512          // no scan kernel orders segments shorter than this (sizes the segment table)
 int64_t rs_batched_tc_work_bytes(int64_t n, int n_motifs, int stride_rows, int64_t hit_capacity);
 int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n, int n_motifs, const int *widths,

@@ -70,46 +70,6 @@ __device__ __forceinline__ bool exact_window(const ProfileParams &prm, const PT 
     return codes == nullptr || rs_no_separator(codes + i, W);
 }
 
-// Append this tile's hits (bit i of `mask` = window i of this thread, consecutive windows
-// per thread) to the staging area in position order.  All threads of the CTA call it.
-template <int THREADS, typename RECOMPUTE>
-__device__ __forceinline__ void emit_tile_hits(const HitStage &st, int64_t tile, unsigned mask, int nbits,
-                                               RECOMPUTE recompute)
-{
-    __shared__ unsigned s_warp[THREADS / 32];
-    __shared__ unsigned long long s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned cnt = __popc(mask);
-    unsigned incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; w++) {
-        unsigned v = s_warp[w];
-        if (w < warp) before += v;
-        total += v;
-    }
-    if (threadIdx.x == 0) {
-        unsigned long long base = atomicAdd(st.counters, (unsigned long long)total);   // one atomic per tile
-        s_base = base;
-        st.tile_seg[tile] = make_ulonglong2(base, (unsigned long long)total);
-    }
-    __syncthreads();
-    unsigned long long k = s_base + before + (incl - cnt);
-    for (int i = 0; i < nbits; i++) {
-        if (mask & (1u << i)) {
-            if ((int64_t)k < st.capacity) recompute(i, (int64_t)k);
-            k++;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __grid_constant__ ProfileParams prm)

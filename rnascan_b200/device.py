@@ -212,6 +212,7 @@ class HitBuffers(object):
         self.seq = torch.empty(cap, dtype=torch.float32, device=device) if want_seq else None
         self.struct = torch.empty(cap, dtype=torch.float64, device=device) if want_struct else None
         self.counters = torch.zeros(2, dtype=torch.int64, device=device)
+        self.cand_counters = torch.zeros(2, dtype=torch.int64, device=device)   # first pass of two-pass scans
         self.work_bytes = int(lib.rs_scan_workspace_bytes(int(n), self.capacity))
         self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
 
@@ -329,6 +330,97 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     pos, sq, st, resc = _run_thresholded(stream.n, stream.codes.device, launch, ts is not None, True,
                                          capacity)
     return (pos, sq, st, resc) if return_stats else (pos, sq, st)
+
+
+class BackgroundFusedScan(object):
+    """Combined scan of device-resident streams whose sequence background is computed from the
+    same data (BASELINE config 4: "computed background").
+
+    The reference runs compute_background over the whole input, then builds the log-odds, then
+    scans (rnascan.py:507-521).  Only the SEQUENCE table depends on those counts (the averaged
+    profile mode cannot compute a structure background, rnascan.py:533-540), and combine() is an
+    AND of two separately thresholded result sets (rnascan.py:416-434).  So the structure-only
+    candidate scan starts at once on the caller's stream while histogram -> all-reduce -> counts
+    D2H run on a side stream and the host turns the counts into the sequence table;
+    rs_refine_hits_seq then keeps the candidates whose sequence score passes too.  Results are
+    identical to histogram -> tables -> rs_scan_fused(RS_MODE_AND).
+    """
+
+    def __init__(self, n, device=None, capacity=None):
+        require_cuda()
+        self.device = torch.device(device or "cuda")
+        self.n = int(n)
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.ready = torch.cuda.Event()
+        self.hb = HitBuffers(self.n, int(capacity) if capacity else max(1 << 16, self.n // 256), self.device)
+        self.launches = 0
+
+    def launch(self, codes, profile_rows, profile_dtype, W, struct_table, seq_table_fn, threshold,
+               absrow_max, all_reduce=None):
+        """Enqueue one whole pass.  codes / profile_rows: device tensors (padded); seq_table_fn(counts
+        int64[8]) -> (W, 4) table.  The host blocks only until the COUNTS are on the host (side
+        stream); the caller's stream keeps running.  Read the outcome with results()."""
+        n, hb = self.n, self.hb
+        tq = _table(struct_table, 7)
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.counts.zero_()
+            check(lib.rs_hist_rna(_ptr(codes), n, _ptr(self.counts), self.side.cuda_stream))
+            if all_reduce is not None:
+                all_reduce(self.counts)                     # the path's only collective
+            self.counts_host.copy_(self.counts, non_blocking=True)
+            self.ready.record(self.side)
+        check(lib.rs_scan_fused(_ptr(codes), _ptr(profile_rows), profile_dtype, n, 0, tq.ctypes.data, W,
+                                float(threshold), float(absrow_max), _lib.RS_MODE_STRUCT, hb.capacity,
+                                _ptr(hb.pos), 0, _ptr(hb.struct), _ptr(hb.cand_counters), _ptr(hb.work),
+                                hb.work_bytes, main.cuda_stream))
+        self.ready.synchronize()
+        ts = _table(seq_table_fn(self.counts_host.numpy()), 4)
+        if ts.shape[0] != W:
+            raise ValueError("sequence and structure motifs must have the same width")
+        check(lib.rs_refine_hits_seq(_ptr(codes), n, ts.ctypes.data, W, float(threshold),
+                                     _ptr(hb.cand_counters), hb.capacity, _ptr(hb.pos), _ptr(hb.seq),
+                                     _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes,
+                                     main.cuda_stream))
+        main.wait_stream(self.side)
+        self.launches = 7          # hist, filter, 2 x order, refine, 2 x order
+        return ts
+
+    def results(self):
+        """(pos, seq_scores, struct_scores) on the host, or None when the candidate buffer overflowed
+        (grow() and launch again)."""
+        hb = self.hb
+        cand = int(hb.cand_counters[0].item())
+        if cand > hb.capacity:
+            return None
+        found = int(hb.counters[0].item())
+        return (hb.pos[:found].cpu().numpy(), hb.seq[:found].cpu().numpy(), hb.struct[:found].cpu().numpy())
+
+    def grow(self):
+        cand = int(self.hb.cand_counters[0].item())
+        self.hb = HitBuffers(self.n, max(cand, 2 * self.hb.capacity), self.device)
+
+
+def scan_fused_bg(stream, profile, struct_table, seq_table_fn, threshold, all_reduce=None, capacity=None):
+    """histogram + combined scan in one overlapped pass (see BackgroundFusedScan).
+    Returns (pos, seq_scores, struct_scores, counts int64[8])."""
+    if stream.n != profile.n:
+        raise ValueError("symbol stream and profile stream differ in length")
+    if float(threshold) == float("-inf"):
+        raise ValueError("scan_fused_bg needs a finite threshold (use histogram() + scan_fused for -inf)")
+    W = _table(struct_table, 7).shape[0]
+    job = BackgroundFusedScan(stream.n, stream.codes.device, capacity)
+    absmax = profile.absrow_max()
+    while True:
+        job.launch(stream.codes, profile.rows, profile.dtype, W, struct_table, seq_table_fn, threshold,
+                   absmax, all_reduce)
+        res = job.results()
+        if res is not None:
+            return res + (job.counts_host.numpy().copy(),)
+        job.grow()
 
 
 def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity=None, path=0):

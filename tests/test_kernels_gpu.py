@@ -255,6 +255,50 @@ def test_scan_fused_and_mode(dev, oracle, dtype, W, thr):
     assert_same_float(sc, b[wpos])
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("W,thr,cap", [(7, 0.0, None), (7, 1.0, 64), (10, -2.0, None), (18, 0.5, 1000), (7, 6.0, None)])
+def test_scan_fused_bg_matches_oracle_and_one_pass(dev, oracle, dtype, W, thr, cap):
+    """histogram overlapped with the structure-only candidate scan + rs_refine_hits_seq ==
+    histogram -> tables -> one-pass RS_MODE_AND scan == oracle (computed background)."""
+    from rnascan_b200 import synth
+    st, pf, codes, rows, _, tq = _profile_case(dev, 800_000, 200, 131 + W, dtype, W)
+    prob = synth.pfm_rows(W, 4, np.random.default_rng(7 + W))
+    seen = []
+
+    def seq_table(counts8):
+        seen.append(np.array(counts8[:4], np.int64))
+        bg = (np.asarray(counts8[:4], np.float64) + 1) / (float(np.sum(counts8[:4])) + 4)
+        return synth.pssm_table(prob, background=list(bg / bg.sum()))
+
+    pos, sq, sc, counts = dev.scan_fused_bg(st, pf, tq, seq_table, thr, capacity=cap)
+    want_counts = np.array([(codes == k).sum() for k in range(4)], np.int64)
+    assert np.array_equal(counts[:4], want_counts) and np.array_equal(seen[-1], want_counts)
+    ts = seq_table(want_counts)
+    with np.errstate(all="ignore"):
+        b = oracle.profile_scores(rows, tq)
+    a = oracle.seq_scores(synth.to_text(codes, "rna"), ts)
+    with np.errstate(invalid="ignore"):
+        wpos = np.nonzero((a.astype(np.float64) > thr) & (b > thr))[0]
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sq, a[wpos])
+    assert_same_float(sc, b[wpos])
+    p1, q1, s1 = dev.scan_fused(st, pf, ts, tq, thr)
+    assert np.array_equal(pos, p1) and np.array_equal(_bits(sq), _bits(q1)) and np.array_equal(_bits(sc), _bits(s1))
+    if cap:
+        assert len(seen) > 2, "a tiny candidate buffer must have forced a regrow + second launch"
+
+
+def test_refine_hits_seq_rejects_aliased_counters(dev):
+    from rnascan_b200.device import lib, _ptr, HitBuffers
+    st = dev.SymbolStream(np.zeros(4096, np.uint8))
+    hb = HitBuffers(st.n, 128, st.codes.device)
+    t = np.zeros((7, 4))
+    rc = lib.rs_refine_hits_seq(_ptr(st.codes), st.n, t.ctypes.data, 7, 0.0, _ptr(hb.counters), hb.capacity,
+                                _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work),
+                                hb.work_bytes, 0)
+    assert rc == 1
+
+
 def test_fused_filter_is_used_and_rare(dev):
     """The fp32 filter must leave only a small fraction of windows for exact re-scoring."""
     st, pf, codes, rows, ts, tq = _profile_case(dev, 2_000_000, 500, 99, np.float32, 7)
