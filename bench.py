@@ -375,7 +375,7 @@ def measure(args, wl, steps, ctx, full=True):
                                     W_MOTIF, THRESHOLD, absmax, _lib.RS_MODE_AND, hb.capacity, _ptr(hb.pos),
                                     _ptr(hb.seq), _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work),
                                     hb.work_bytes, sptr))
-            launches[0] += 3
+            launches[0] += 2                                # scan, ordering
         elif wl == "c5":
             M, stride = tq.shape[0], tq.shape[1]            # ts, tq: (256, stride, 4|7) stacked tables
             check(lib.rs_scan_batched(_ptr(codes), _ptr(prof), _lib.RS_F32, n, M, c5_widths.ctypes.data,
@@ -386,7 +386,7 @@ def measure(args, wl, steps, ctx, full=True):
         elif wl == "c2":
             check(lib.rs_scan_seq(_ptr(codes), n, ts.ctypes.data, W_MOTIF, THRESHOLD, hb.capacity, _ptr(hb.pos),
                                   _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, sptr))
-            launches[0] += 3
+            launches[0] += 4                                # decision table, scan, segment scan, expansion
         else:
             check(lib.rs_scores_dense_struct(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
             launches[0] += 1

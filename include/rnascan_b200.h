@@ -206,6 +206,24 @@ int rs_refine_hits_seq(const uint8_t *d_codes, int64_t n, const double *seq_tabl
                        int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
                        uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
 
+/* The same decision split in two calls around the arrival of the background, cheaper than
+ * rs_scan_fused(RS_MODE_STRUCT) + rs_refine_hits_seq because the candidates are never ordered on
+ * their own: rs_scan_fused_candidates runs the structure-only scan and leaves its hits staged per
+ * tile inside d_work (d_cand_counters2[0] = candidates found; above hit_capacity => re-run larger;
+ * *staged_tiles, written on the host before returning, must be passed on);
+ * rs_scan_fused_resolve applies the sequence PSSM to the staged candidates while ordering them.
+ * Same d_work / hit_capacity / stream for both; d_counters2[0] = hits.  Results are identical to
+ * rs_scan_fused(RS_MODE_AND).                                                               */
+int rs_scan_fused_candidates(const uint8_t *d_codes, const void *d_profile, int profile_dtype,
+                             int64_t n, const double *struct_table_Wx7, int W, double threshold,
+                             double profile_absrow_max, int64_t hit_capacity,
+                             uint64_t *d_cand_counters2, void *d_work, int64_t work_bytes,
+                             int64_t *staged_tiles, void *stream);
+int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_table_Wx4, int W,
+                          double threshold, int64_t staged_tiles, int64_t hit_capacity,
+                          int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                          uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
+
 /* ---- batched many-PFM scan (BASELINE config 5: 256 RNAcompete-style motif pairs) -------
  * The reference scans one PFM (pair) per process run; a motif collection means running
  * rnascan.py:490-576 once per motif.  Here all motifs are scanned over the SAME resident

@@ -125,7 +125,7 @@ WorkLayout rs_work_layout(int64_t n, int64_t capacity)
     wl.off_str = off;  off += rs_roundup(cap * 8, 256);
     wl.off_seq = off;  off += rs_roundup(cap * 4, 256);
     wl.off_seg = off;  off += rs_roundup(tiles * 16, 256);
-    wl.off_scan = off; off += rs_roundup(16 + 8 * (tiles / 8192 + 2), 256);
+    wl.off_scan = off; off += rs_roundup(rs_order_tmp_bytes(tiles), 256);
     wl.off_lut = off;  off += rs_kmer_work_bytes(n);      // k-mer scan: table, hit masks, segment scan
     wl.total = off;
     return wl;

@@ -165,6 +165,7 @@ struct OrderDest {
     int32_t *out_motif;
     int32_t  motif_id;
 };
+int64_t rs_order_tmp_bytes(int64_t max_tiles);    // scratch rs_order_hits needs for up to max_tiles tiles
 int rs_order_hits(const HitStage &st, int64_t n_tiles, const OrderDest &dst, void *d_scan_tmp,
                   cudaStream_t stream);
 
@@ -207,6 +208,12 @@ __device__ __forceinline__ void emit_tile_hits(const HitStage &st, int64_t tile,
         }
     }
 }
+
+// Same, with the sequence half of the combined decision applied to the staged (structure-only)
+// candidates first; *d_total_out = survivors.
+int rs_order_hits_seq_refined(const HitStage &st, int64_t n_tiles, const OrderDest &dst, void *d_scan_tmp,
+                              cudaStream_t stream, const uint8_t *d_codes, int64_t n, const double *seq_table, int W,
+                              double threshold, unsigned long long *d_total_out);
 
 #define RS_MIN_TILE 512          // no scan kernel orders segments shorter than this (sizes the segment table)
 int64_t rs_batched_tc_work_bytes(int64_t n, int n_motifs, int stride_rows, int64_t hit_capacity);

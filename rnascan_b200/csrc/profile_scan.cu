@@ -451,7 +451,7 @@ static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int pr
                            double profile_absrow_max, int mode, int64_t hit_capacity, int64_t *d_hit_pos,
                            float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
                            int64_t work_bytes, void *stream, const unsigned long long *d_out_base,
-                           int32_t *d_hit_motif, int32_t motif_id)
+                           int32_t *d_hit_motif, int32_t motif_id, int64_t *staged_tiles_out = nullptr)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_common(d_profile, profile_dtype, n, struct_table, W);
@@ -459,11 +459,13 @@ static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int pr
     if (!d_codes || ((uintptr_t)d_codes & 15)) { rs_set_error("codes pointer null or not 16-byte aligned"); return RS_ERR_INVALID; }
     if (mode != RS_MODE_STRUCT && mode != RS_MODE_AND) { rs_set_error("bad mode"); return RS_ERR_INVALID; }
     if (mode == RS_MODE_AND && (!seq_table || !d_hit_seq)) { rs_set_error("RS_MODE_AND needs a sequence table and d_hit_seq"); return RS_ERR_INVALID; }
-    if (!d_counters2 || hit_capacity < 0 || (hit_capacity > 0 && (!d_hit_pos || !d_hit_struct))) {
+    if (!d_counters2 || hit_capacity < 0 ||
+        (hit_capacity > 0 && !staged_tiles_out && (!d_hit_pos || !d_hit_struct))) {
         rs_set_error("bad hit buffers"); return RS_ERR_INVALID;
     }
     if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
     RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    if (staged_tiles_out) *staged_tiles_out = 0;
     if (n < W) return RS_OK;
     WorkLayout wl = rs_work_layout(n, hit_capacity);
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
@@ -525,8 +527,55 @@ static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int pr
         rc = profile_dtype == RS_F32 ? launch_exact<float>(prm, st) : launch_exact<double>(prm, st);
     }
     if (rc) return rc;
+    if (staged_tiles_out) {            // rs_scan_fused_candidates: leave the hits staged per tile
+        *staged_tiles_out = n_tiles;
+        return RS_OK;
+    }
     OrderDest od = {d_hit_pos, d_hit_seq, d_hit_struct, d_out_base, d_hit_motif, motif_id};
     return rs_order_hits(prm.st, n_tiles, od, wk + wl.off_scan, st);
+}
+
+// ---- the combined scan in two halves, so that the half that needs the data's background can wait for it
+extern "C" int rs_scan_fused_candidates(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                                        const double *struct_table, int W, double threshold,
+                                        double profile_absrow_max, int64_t hit_capacity, uint64_t *d_cand_counters2,
+                                        void *d_work, int64_t work_bytes, int64_t *staged_tiles, void *stream)
+{
+    if (!staged_tiles) { rs_set_error("rs_scan_fused_candidates: null staged_tiles"); return RS_ERR_INVALID; }
+    return scan_fused_impl(d_codes, d_profile, profile_dtype, n, nullptr, struct_table, W, threshold,
+                           profile_absrow_max, RS_MODE_STRUCT, hit_capacity, nullptr, nullptr, nullptr,
+                           d_cand_counters2, d_work, work_bytes, stream, nullptr, nullptr, 0, staged_tiles);
+}
+
+extern "C" int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_table, int W,
+                                     double threshold, int64_t staged_tiles, int64_t hit_capacity,
+                                     int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                                     uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_codes || !seq_table || !d_counters2 || n < 0 || staged_tiles < 0) {
+        rs_set_error("rs_scan_fused_resolve: bad argument"); return RS_ERR_INVALID;
+    }
+    if (W < 1 || W > RS_MAX_W) { rs_set_error("motif width %d outside [1, %d]", W, RS_MAX_W); return RS_ERR_INVALID; }
+    if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
+    if (hit_capacity < 0 || (hit_capacity > 0 && (!d_hit_pos || !d_hit_seq || !d_hit_struct))) {
+        rs_set_error("bad hit buffers"); return RS_ERR_INVALID;
+    }
+    WorkLayout wl = rs_work_layout(n, hit_capacity);
+    if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+    if (staged_tiles > n / RS_MIN_TILE + 16) { rs_set_error("staged_tiles does not belong to this stream length"); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    uint8_t *wk = (uint8_t *)d_work;
+    HitStage hs = {};
+    hs.pos = (int64_t *)(wk + wl.off_pos);
+    hs.seq = (float *)(wk + wl.off_seq);
+    hs.str = (double *)(wk + wl.off_str);
+    hs.tile_seg = (ulonglong2 *)(wk + wl.off_seg);
+    hs.counters = (unsigned long long *)d_counters2;
+    hs.capacity = hit_capacity;
+    OrderDest od = {d_hit_pos, d_hit_seq, d_hit_struct, nullptr, nullptr, 0};
+    return rs_order_hits_seq_refined(hs, staged_tiles, od, wk + wl.off_scan, st, d_codes, n, seq_table, W, threshold,
+                                     (unsigned long long *)d_counters2);
 }
 
 extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,

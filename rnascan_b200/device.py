@@ -11,6 +11,8 @@ Layout in HBM:
                                                   B,E,H,L,M,R,T
   hits            int64 pos[], float32 seq[], float64 struct[]   (structure of arrays)
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -332,6 +334,28 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     return (pos, sq, st, resc) if return_stats else (pos, sq, st)
 
 
+def refine_hits_seq(stream, pos, struct_scores, seq_table, threshold):
+    """Keep, in order, the candidate windows `pos` (ascending stream positions, e.g. the hits of a
+    structure-only scan) whose sequence score also exceeds `threshold` (rs_refine_hits_seq).
+    Returns (pos, seq_scores float32, struct_scores | None)."""
+    ts = _table(seq_table, 4)
+    dev = stream.codes.device
+    pos = np.ascontiguousarray(pos, np.int64)
+    k = len(pos)
+    hb = HitBuffers(stream.n, k, dev, True, struct_scores is not None)
+    if k:
+        hb.pos[:k].copy_(torch.from_numpy(pos))
+        if struct_scores is not None:
+            hb.struct[:k].copy_(torch.from_numpy(np.ascontiguousarray(struct_scores, np.float64)))
+    hb.cand_counters[0] = k
+    check(lib.rs_refine_hits_seq(_ptr(stream.codes), stream.n, ts.ctypes.data, ts.shape[0], float(threshold),
+                                 _ptr(hb.cand_counters), hb.capacity, _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct),
+                                 _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, _stream()))
+    found = int(hb.counters[0].item())
+    return (hb.pos[:found].cpu().numpy(), hb.seq[:found].cpu().numpy(),
+            hb.struct[:found].cpu().numpy() if struct_scores is not None else None)
+
+
 class BackgroundFusedScan(object):
     """Combined scan of device-resident streams whose sequence background is computed from the
     same data (BASELINE config 4: "computed background").
@@ -373,20 +397,20 @@ class BackgroundFusedScan(object):
                 all_reduce(self.counts)                     # the path's only collective
             self.counts_host.copy_(self.counts, non_blocking=True)
             self.ready.record(self.side)
-        check(lib.rs_scan_fused(_ptr(codes), _ptr(profile_rows), profile_dtype, n, 0, tq.ctypes.data, W,
-                                float(threshold), float(absrow_max), _lib.RS_MODE_STRUCT, hb.capacity,
-                                _ptr(hb.pos), 0, _ptr(hb.struct), _ptr(hb.cand_counters), _ptr(hb.work),
-                                hb.work_bytes, main.cuda_stream))
+        tiles = ctypes.c_int64(0)
+        check(lib.rs_scan_fused_candidates(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,
+                                           float(threshold), float(absrow_max), hb.capacity,
+                                           _ptr(hb.cand_counters), _ptr(hb.work), hb.work_bytes,
+                                           ctypes.addressof(tiles), main.cuda_stream))
         self.ready.synchronize()
         ts = _table(seq_table_fn(self.counts_host.numpy()), 4)
         if ts.shape[0] != W:
             raise ValueError("sequence and structure motifs must have the same width")
-        check(lib.rs_refine_hits_seq(_ptr(codes), n, ts.ctypes.data, W, float(threshold),
-                                     _ptr(hb.cand_counters), hb.capacity, _ptr(hb.pos), _ptr(hb.seq),
-                                     _ptr(hb.struct), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes,
-                                     main.cuda_stream))
+        check(lib.rs_scan_fused_resolve(_ptr(codes), n, ts.ctypes.data, W, float(threshold), tiles.value,
+                                        hb.capacity, _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct),
+                                        _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, main.cuda_stream))
         main.wait_stream(self.side)
-        self.launches = 7          # hist, filter, 2 x order, refine, 2 x order
+        self.launches = 3          # hist, candidate scan, sequence check + ordering
         return ts
 
     def results(self):

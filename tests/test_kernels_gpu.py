@@ -288,6 +288,22 @@ def test_scan_fused_bg_matches_oracle_and_one_pass(dev, oracle, dtype, W, thr, c
         assert len(seen) > 2, "a tiny candidate buffer must have forced a regrow + second launch"
 
 
+@pytest.mark.parametrize("W,thr", [(7, 0.0), (12, -1.0), (30, -5.0)])
+def test_refine_hits_seq_equals_and_scan(dev, oracle, W, thr):
+    """structure-only scan, then rs_refine_hits_seq on its ordered hits == the one-pass AND scan."""
+    st, pf, codes, rows, ts, tq = _profile_case(dev, 500_000, 120, 171 + W, np.float32, W)
+    p0, _, s0 = dev.scan_fused(st, pf, None, tq, thr)
+    pos, sq, sc = dev.refine_hits_seq(st, p0, s0, ts, thr)
+    p1, q1, s1 = dev.scan_fused(st, pf, ts, tq, thr)
+    assert len(p1) > 0 and len(p0) > len(p1)
+    assert np.array_equal(pos, p1) and np.array_equal(_bits(sq), _bits(q1)) and np.array_equal(_bits(sc), _bits(s1))
+    # no candidates at all / candidates without structure scores
+    e = dev.refine_hits_seq(st, np.zeros(0, np.int64), None, ts, thr)
+    assert len(e[0]) == 0 and e[2] is None
+    pos2, sq2, none = dev.refine_hits_seq(st, p0, None, ts, thr)
+    assert none is None and np.array_equal(pos2, p1) and np.array_equal(_bits(sq2), _bits(q1))
+
+
 def test_refine_hits_seq_rejects_aliased_counters(dev):
     from rnascan_b200.device import lib, _ptr, HitBuffers
     st = dev.SymbolStream(np.zeros(4096, np.uint8))
