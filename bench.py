@@ -386,7 +386,7 @@ def measure(args, wl, steps, ctx, full=True):
         elif wl == "c2":
             check(lib.rs_scan_seq(_ptr(codes), n, ts.ctypes.data, W_MOTIF, THRESHOLD, hb.capacity, _ptr(hb.pos),
                                   _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, sptr))
-            launches[0] += 4                                # decision table, scan, segment scan, expansion
+            launches[0] += 3                                # decision table, scan, finish (segment scan + expansion)
         else:
             check(lib.rs_scores_dense_struct(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
             launches[0] += 1

@@ -22,10 +22,10 @@
 // The hot kernel is a pure stream: a producer warp feeds a 3-stage shared-memory ring with
 // bulk async copies (full/empty mbarriers, no CTA-wide barrier), 8 consumer warps turn
 // symbols into one 28-bit hit mask per thread (one coalesced 4-byte store) plus one count
-// per warp segment (896 positions).  No atomics, no divergent emission.  Ordering is then a
-// prefix sum over the segment counts (kmer_segscan_kernel) and an expansion pass
-// (kmer_expand_kernel, one warp per segment: ballot/popc prefix inside the segment) that
-// writes positions and exact scores straight to their final, position-sorted place.
+// per warp segment (896 positions; mask words of segments without a hit are not even written).  No
+// atomics, no divergent emission.  Ordering is ONE more launch (kmer_finish_kernel): a prefix sum over
+// the segment counts, then the non-empty segments are expanded (popc/shuffle prefix inside the
+// segment) with positions and exact scores written straight to their final, position-sorted place.
 #include "common.cuh"
 
 #define KM_CONSUMERS   256                         // consumer threads (8 warps)
@@ -37,17 +37,14 @@
 #define KM_LUT_BYTES   65536
 #define KM_WARPS       (KM_CONSUMERS / 32)
 #define KM_SEG         (32 * KM_P)                 // 896 positions per warp segment
-#define SS_THREADS     1024
-#define SS_PER         8
-#define SS_CHUNK       (SS_THREADS * SS_PER)       // segments per scan block
+#define FIN_THREADS    1024                        // segments per CTA of the finish kernel (one per thread)
 
 struct KmerWork {                 // carved out of the caller's workspace
     uint8_t  *lut;                // [65536]
     uint32_t *mask;               // [n_tiles * 256] hit mask per consumer thread
     uint32_t *segcnt;             // [n_segs] hits per warp segment
-    uint32_t *seglocal;           // [n_segs] exclusive offset inside its scan block
-    unsigned long long *blockbase;// [n_scan_blocks] exclusive offsets of scan blocks
-    unsigned long long *ticket;   // [1]
+    unsigned long long *ticket;   // [2]  ticket, pad -- zeroed together with agg before every scan
+    unsigned long long *agg;      // [n_ctas] finish kernel: 0 = not ready, else CTA aggregate + 1
 };
 
 struct KmerParams {
@@ -168,16 +165,34 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kmer_scan_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);                     // this warp is done with the stage
 
-        prm.wk.mask[tile * KM_CONSUMERS + tid] = hit;
         const unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(hit));
+        if (total) prm.wk.mask[tile * KM_CONSUMERS + tid] = hit;       // only non-empty segments are expanded
         if (lane == 0) prm.wk.segcnt[tile * KM_WARPS + warp] = total;
     }
 }
 
-// ---- exclusive prefix sum over the segment counts ------------------------------------------
-__device__ __forceinline__ unsigned long long ss_block_scan(unsigned long long v, unsigned long long &total)
+// ---- finish: prefix sum over the segment counts + expansion, ONE launch -----------------------
+// One thread per segment takes part in the exclusive prefix sum (CTAs chained by ticket + look-back over
+// the aggregates of the CTAs before them, as in order.cu); then the hits of the non-empty segments are
+// expanded (per-warp queue, see below) with positions and EXACT scores written straight to their
+// final, position-sorted place.
+struct ExpandParams {
+    const uint8_t *codes;
+    KmerWork wk;
+    int64_t n_segs, capacity;
+    int n_ctas;
+    unsigned long long *counters;
+    OrderDest od;
+    int W;
+    int ppm;                  // positions per mask word: 28 (k-mer scan) or 32 (ballot masks)
+    double ta[16 * 8];        // exact table, row stride A_STRIDE
+    const uint8_t *codes_b;   // pair mode: structure stream scored with tb (row stride 8) into od.str
+    double tb[16 * 8];
+};
+
+__device__ __forceinline__ unsigned long long fin_block_scan(unsigned long long v, unsigned long long &total)
 {
-    __shared__ unsigned long long s_w[SS_THREADS / 32];
+    __shared__ unsigned long long s_w[FIN_THREADS / 32];
     __shared__ unsigned long long s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long incl = v;
@@ -204,100 +219,118 @@ __device__ __forceinline__ unsigned long long ss_block_scan(unsigned long long v
     return s_w[warp] + incl - v;
 }
 
-__global__ void __launch_bounds__(SS_THREADS) kmer_segscan_kernel(KmerWork wk, int64_t n_segs, int n_blocks,
-                                                                  unsigned long long *counters)
+// exact score of the (W <= 16)-symbol window at stream position `pos`: its bytes come from five aligned
+// words fetched together (ONE memory round trip per hit instead of W dependent ones; the padding of the
+// stream covers the over-read), then sequential fp64 adds in j order.
+template <int A, int TS>
+__device__ __forceinline__ double fin_window_score(const uint8_t *codes, int64_t pos, int W, const double *tab)
 {
-    const int64_t base = (int64_t)blockIdx.x * SS_CHUNK + (int64_t)threadIdx.x * SS_PER;
-    unsigned c[SS_PER];
-    unsigned long long s = 0;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(codes + (pos & ~(int64_t)3));
+    const unsigned sh = (unsigned)(pos & 3) * 8u;
+    uint32_t w[5];
 #pragma unroll
-    for (int k = 0; k < SS_PER; k++) {
-        c[k] = base + k < n_segs ? wk.segcnt[base + k] : 0u;
-        s += c[k];
-    }
-    unsigned long long total;
-    unsigned long long ex = ss_block_scan(s, total);
+    for (int i = 0; i < 5; i++) w[i] = q[i];
+    double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < SS_PER; k++) {
-        if (base + k < n_segs) wk.seglocal[base + k] = (uint32_t)ex;
-        ex += c[k];
-    }
-    __shared__ bool s_last;
-    if (threadIdx.x == 0) {
-        wk.blockbase[blockIdx.x] = total;
-        __threadfence();
-        s_last = atomicAdd(wk.ticket, 1ull) == (unsigned long long)(n_blocks - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        unsigned long long carry = 0;
-        for (int b0 = 0; b0 < n_blocks; b0 += SS_THREADS) {
-            const int b = b0 + threadIdx.x;
-            unsigned long long v = b < n_blocks ? ((volatile unsigned long long *)wk.blockbase)[b] : 0ull;
-            unsigned long long tot;
-            unsigned long long e = ss_block_scan(v, tot);
-            if (b < n_blocks) wk.blockbase[b] = carry + e;
-            carry += tot;
+    for (int j = 0; j < 16; j++) {
+        if (j < W) {
+            const uint32_t x = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], sh);
+            s = __dadd_rn(s, tab[j * TS + ((x >> (8 * (j & 3))) & (A == 4 ? 3u : 7u))]);
         }
-        if (threadIdx.x == 0) { counters[0] = carry; *wk.ticket = 0ull; }
     }
+    return s;
 }
-
-// ---- expansion: one warp per segment writes its hits, in order, with exact scores ----------
-struct ExpandParams {
-    const uint8_t *codes;
-    KmerWork wk;
-    int64_t n_segs, capacity;
-    OrderDest od;
-    int W;
-    int ppm;                  // positions per mask word: 28 (k-mer scan) or 32 (ballot masks)
-    double ta[16 * 8];        // exact table, row stride A_STRIDE
-    const uint8_t *codes_b;   // pair mode: structure stream scored with tb (row stride 8) into od.str
-    double tb[16 * 8];
-};
 
 // A = 4: float32 sequence scores (row stride 4); A = 7: float64 structure scores (row stride 8)
 template <int A>
-__global__ void __launch_bounds__(256) kmer_expand_kernel(const __grid_constant__ ExpandParams prm)
+__global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_constant__ ExpandParams prm)
 {
     constexpr int TS = A == 4 ? 4 : 8;
-    const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (seg >= prm.n_segs) return;
-    // four independent loads issued together (one memory round trip instead of three)
-    const uint32_t segcnt = prm.wk.segcnt[seg];
-    const uint32_t hit = prm.wk.mask[seg * 32 + lane];
-    const unsigned long long bbase = prm.wk.blockbase[seg / SS_CHUNK];
-    const uint32_t slocal = prm.wk.seglocal[seg];
-    const unsigned long long obase = prm.od.out_base ? *prm.od.out_base : 0ull;
-    if (segcnt == 0) return;
-    const unsigned cnt = __popc(hit);
-    unsigned incl = cnt;
+    __shared__ unsigned s_vb;
+    if (threadIdx.x == 0) s_vb = (unsigned)atomicAdd(prm.wk.ticket, 1ull);
+    __syncthreads();
+    const unsigned vb = s_vb;
+    const int64_t seg = (int64_t)vb * FIN_THREADS + threadIdx.x;
+    const uint32_t segcnt = seg < prm.n_segs ? prm.wk.segcnt[seg] : 0u;
+    unsigned long long total;
+    const unsigned long long excl = fin_block_scan(segcnt, total);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ((volatile unsigned long long *)prm.wk.agg)[vb] = total + 1ull;
+    }
+    unsigned long long part = 0;
+    for (unsigned p = threadIdx.x; p < vb; p += FIN_THREADS) {
+        unsigned long long v;
+        while ((v = ((volatile unsigned long long *)prm.wk.agg)[p]) == 0ull) __nanosleep(20);
+        part += v - 1ull;
+    }
+    unsigned long long before;
+    fin_block_scan(part, before);
+    if (vb == (unsigned)(prm.n_ctas - 1) && threadIdx.x == 0) {
+        prm.counters[0] = before + total;
+        *prm.wk.ticket = 0ull;
+    }
+    if (prm.capacity <= 0) return;
+    // Expansion.  A lane owns one segment: its 32 mask words (128 contiguous bytes) are fetched with eight
+    // independent 16-byte loads.  Hits are sparse across (lane, word), so instead of scoring them where
+    // they are found (a few active lanes per pass) every lane pushes (output index, position) into a
+    // per-warp queue and the warp scores queue entries 32 at a time with all lanes busy.
+    __shared__ unsigned long long q_k[FIN_THREADS / 32][64];
+    __shared__ long long q_pos[FIN_THREADS / 32][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long k = before + excl + (prm.od.out_base ? *prm.od.out_base : 0ull);
+    uint4 m[8];
+    if (segcnt) {
+        const uint4 *mv = reinterpret_cast<const uint4 *>(prm.wk.mask + seg * 32);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+        for (int i = 0; i < 8; i++) m[i] = mv[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) m[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    unsigned long long k = bbase + slocal + (incl - cnt) + obase;
-    const int64_t g0 = (seg * 32 + lane) * (int64_t)prm.ppm;      // segments tile the stream contiguously
-    for (uint32_t h = hit; h; h &= h - 1, k++) {
-        if ((int64_t)k >= prm.capacity) break;
-        const int p = __ffs(h) - 1;
-        const uint8_t *c = prm.codes + g0 + p;
-        double s = 0.0;
-        for (int j = 0; j < prm.W; j++) s = __dadd_rn(s, prm.ta[j * TS + (c[j] & (A == 4 ? 3 : 7))]);
-        prm.od.pos[k] = g0 + p;
-        if (A == 4) prm.od.seq[k] = (float)s;                      // _pwm.c:65
-        else        prm.od.str[k] = s;                             // matrix.py:34-42
-        if (A == 4 && prm.codes_b) {                               // pair mode: structure score of the same window
-            const uint8_t *cb = prm.codes_b + g0 + p;
-            double sb = 0.0;
-            for (int j = 0; j < prm.W; j++) sb = __dadd_rn(sb, prm.tb[j * 8 + (cb[j] & 7)]);
-            prm.od.str[k] = sb;
+    unsigned head = 0, count = 0;                  // warp-uniform ring state
+    auto drain = [&](unsigned n_take) {
+        __syncwarp();
+        if ((unsigned)lane < n_take) {
+            const unsigned e = (head + lane) & 63u;
+            const unsigned long long kk = q_k[warp][e];
+            const int64_t pos = q_pos[warp][e];
+            if ((int64_t)kk < prm.capacity) {
+                const double sc = fin_window_score<A, TS>(prm.codes, pos, prm.W, prm.ta);
+                prm.od.pos[kk] = pos;
+                if (A == 4) prm.od.seq[kk] = (float)sc;                        // _pwm.c:65
+                else        prm.od.str[kk] = sc;                               // matrix.py:34-42
+                if (A == 4 && prm.codes_b)                                     // pair mode: structure score of the same window
+                    prm.od.str[kk] = fin_window_score<7, 8>(prm.codes_b, pos, prm.W, prm.tb);
+                if (prm.od.out_motif) prm.od.out_motif[kk] = prm.od.motif_id;
+            }
         }
-        if (prm.od.out_motif) prm.od.out_motif[k] = prm.od.motif_id;
+        __syncwarp();
+        head = (head + n_take) & 63u;
+        count -= n_take;
+    };
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t w4[4] = {m[i].x, m[i].y, m[i].z, m[i].w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            uint32_t h = w4[t];
+            const int64_t g0 = (seg * 32 + i * 4 + t) * (int64_t)prm.ppm;      // segments tile the stream contiguously
+            for (;;) {
+                const unsigned has = __ballot_sync(0xffffffffu, h != 0);
+                if (!has) break;
+                if (count > 32u) drain(32u);
+                if (h) {
+                    const unsigned e = (head + count + __popc(has & ((1u << lane) - 1u))) & 63u;
+                    q_k[warp][e] = k++;
+                    q_pos[warp][e] = g0 + (__ffs(h) - 1);
+                    h &= h - 1;
+                }
+                count += __popc(has);
+            }
+        }
     }
+    while (count) drain(count < 32u ? count : 32u);
 }
 
 // ---- one-hot threshold scan, W <= 16, any alphabet: exact scores, hit bits by warp ballot ----------
@@ -419,7 +452,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
             total += __popc(b);
         }
         const int64_t seg = tile * (MS_THREADS / 32) + warp;
-        prm.wk.mask[seg * 32 + lane] = mine;                               // one coalesced 128-byte store
+        if (total) prm.wk.mask[seg * 32 + lane] = mine;                    // one coalesced 128-byte store
         if (lane == 0) prm.wk.segcnt[seg] = total;
         __syncthreads();
     }
@@ -450,40 +483,41 @@ static int dispatch_mask_scan(int W, const MaskScanParams &prm, cudaStream_t str
     }
 }
 
-static void carve_work(uint8_t *wk, int64_t n_masks, int64_t n_segs, int n_blocks, KmerWork &out)
+static void carve_work(uint8_t *wk, int64_t n_masks, int64_t n_segs, int n_ctas, KmerWork &out)
 {
     int64_t off = 0;
     out.lut = wk + off;                               off += KM_LUT_BYTES;
     out.mask = (uint32_t *)(wk + off);                off += rs_roundup(n_masks * 4, 256);
     out.segcnt = (uint32_t *)(wk + off);              off += rs_roundup(n_segs * 4, 256);
-    out.seglocal = (uint32_t *)(wk + off);            off += rs_roundup(n_segs * 4, 256);
-    out.blockbase = (unsigned long long *)(wk + off); off += rs_roundup((int64_t)n_blocks * 8, 256);
-    out.ticket = (unsigned long long *)(wk + off);
+    out.ticket = (unsigned long long *)(wk + off);    off += 16;
+    out.agg = (unsigned long long *)(wk + off);
+    (void)n_ctas;
+}
+static int fin_ctas(int64_t n_segs) { return (int)((n_segs + FIN_THREADS - 1) / FIN_THREADS); }
+static cudaError_t fin_arm(const KmerWork &wk, int n_ctas, cudaStream_t st)
+{
+    return cudaMemsetAsync(wk.ticket, 0, 16 + (size_t)n_ctas * 8, st);
 }
 
 template <int A>
-static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t n_segs, int n_blocks, int ppm,
+static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t n_segs, int n_ctas, int ppm,
                             const double *table, int W, int64_t cap, int64_t *d_hit_pos, float *d_hit_seq,
                             double *d_hit_str, uint64_t *d_counters2, cudaStream_t st,
                             const uint8_t *d_codes_b = nullptr, const double *table_b = nullptr)
 {
-    kmer_segscan_kernel<<<n_blocks, SS_THREADS, 0, st>>>(wk, n_segs, n_blocks, (unsigned long long *)d_counters2);
-    RS_CUDA(cudaGetLastError());
-    if (cap > 0) {
-        ExpandParams ep = {};
-        ep.codes = d_codes; ep.wk = wk; ep.n_segs = n_segs; ep.capacity = cap; ep.W = W; ep.ppm = ppm;
-        ep.od = OrderDest{d_hit_pos, d_hit_seq, d_hit_str, nullptr, nullptr, 0};
-        constexpr int TS = A == 4 ? 4 : 8;
+    ExpandParams ep = {};
+    ep.codes = d_codes; ep.wk = wk; ep.n_segs = n_segs; ep.capacity = cap; ep.W = W; ep.ppm = ppm;
+    ep.n_ctas = n_ctas; ep.counters = (unsigned long long *)d_counters2;
+    ep.od = OrderDest{d_hit_pos, d_hit_seq, d_hit_str, nullptr, nullptr, 0};
+    constexpr int TS = A == 4 ? 4 : 8;
+    for (int j = 0; j < W; j++)
+        for (int c = 0; c < A; c++) ep.ta[j * TS + c] = table[j * A + c];
+    ep.codes_b = d_codes_b;
+    if (table_b)
         for (int j = 0; j < W; j++)
-            for (int c = 0; c < A; c++) ep.ta[j * TS + c] = table[j * A + c];
-        ep.codes_b = d_codes_b;
-        if (table_b)
-            for (int j = 0; j < W; j++)
-                for (int c = 0; c < 7; c++) ep.tb[j * 8 + c] = table_b[j * 7 + c];
-        const int64_t blocks = (n_segs * 32 + 255) / 256;
-        kmer_expand_kernel<A><<<(unsigned)blocks, 256, 0, st>>>(ep);
-        RS_CUDA(cudaGetLastError());
-    }
+            for (int c = 0; c < 7; c++) ep.tb[j * 8 + c] = table_b[j * 7 + c];
+    kmer_finish_kernel<A><<<(unsigned)n_ctas, FIN_THREADS, 0, st>>>(ep);
+    RS_CUDA(cudaGetLastError());
     return RS_OK;
 }
 
@@ -498,9 +532,9 @@ static int mask_scan_impl(const uint8_t *d_codes, int64_t n, const double *table
     prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.threshold = threshold;
     prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
     const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
-    const int n_blocks = (int)((n_segs + SS_CHUNK - 1) / SS_CHUNK);
+    const int n_blocks = fin_ctas(n_segs);
     carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
-    RS_CUDA(cudaMemsetAsync(prm.wk.ticket, 0, 8, st));
+    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
     for (int j = 0; j < W; j++)
         for (int c = 0; c < 8; c++) prm.ta[j * 8 + c] = c < A ? table[j * A + c] : 0.0;
     int rc = dispatch_mask_scan<A>(W, prm, st);
@@ -520,9 +554,9 @@ int rs_scan_pair_masks(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes
     prm.threshold = threshold;
     prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
     const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
-    const int n_blocks = (int)((n_segs + SS_CHUNK - 1) / SS_CHUNK);
+    const int n_blocks = fin_ctas(n_segs);
     carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
-    RS_CUDA(cudaMemsetAsync(prm.wk.ticket, 0, 8, st));
+    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
     for (int j = 0; j < W; j++)
         for (int c = 0; c < 8; c++) {
             prm.ta[j * 8 + c] = c < 4 ? seq_table[j * 4 + c] : 0.0;
@@ -567,9 +601,9 @@ int64_t rs_kmer_work_bytes(int64_t n)
 {
     const int64_t n_tiles = (n > 0 ? n : 0) / KM_TILE + 1;
     const int64_t n_segs = n_tiles * KM_WARPS;
-    const int64_t n_blocks = n_segs / SS_CHUNK + 1;
-    return KM_LUT_BYTES + rs_roundup(n_tiles * KM_CONSUMERS * 4, 256) + 2 * rs_roundup(n_segs * 4, 256) +
-           rs_roundup(n_blocks * 8, 256) + 256;
+    const int64_t n_ctas = n_segs / FIN_THREADS + 2;
+    return KM_LUT_BYTES + rs_roundup(n_tiles * KM_CONSUMERS * 4, 256) + rs_roundup(n_segs * 4, 256) +
+           rs_roundup(16 + n_ctas * 8, 256) + 256;
 }
 
 // Called by rs_scan_seq (onehot_scan.cu) when W <= 8.
@@ -582,9 +616,9 @@ int rs_scan_seq_kmer(const uint8_t *d_codes, int64_t n, const double *table, int
     prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n);
     prm.n_tiles = (n + KM_TILE - 1) / KM_TILE;
     const int64_t n_segs = prm.n_tiles * KM_WARPS;
-    const int n_blocks = (int)((n_segs + SS_CHUNK - 1) / SS_CHUNK);
+    const int n_blocks = fin_ctas(n_segs);
     carve_work(wk, prm.n_tiles * KM_CONSUMERS, n_segs, n_blocks, prm.wk);
-    RS_CUDA(cudaMemsetAsync(prm.wk.ticket, 0, 8, st));
+    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
 
     KmerTable kt = {};
     for (int k = 0; k < W * 4; k++) kt.t[k] = table[k];
