@@ -270,7 +270,9 @@ def make_tables_fn(workload, seed=102):
         batched.lists = lambda counts8: ([t[:w] for t, w in zip(batched(counts8)[0], widths)], tqs)
         return batched
     if workload == "c2":
-        return lambda counts8: (seq_table(counts8), None)
+        fn = lambda counts8: (seq_table(counts8), None)
+        fn.seq_prob = seq_prob_arr
+        return fn
     return lambda counts8: (None, struct_table_computed(counts8))
 
 
@@ -354,6 +356,12 @@ def measure(args, wl, steps, ctx, full=True):
         hb = bgscan.hb
         tq_fixed = tables(np.zeros(8, np.int64))[1]
 
+    ohscan = None
+    if wl == "c2" and not args.serial_bg:
+        # the device selects candidates with a provisional table while the host builds the exact one
+        ohscan = dev.BackgroundOneHotScan(n, "rna", device, capacity=hb.capacity)
+        hb = ohscan.hb
+
     def all_reduce(t):
         if world > 1:
             dist.all_reduce(t)
@@ -363,6 +371,10 @@ def measure(args, wl, steps, ctx, full=True):
             bgscan.launch(codes, prof, _lib.RS_F32, W_MOTIF, tq_fixed, lambda c: tables(c)[0], THRESHOLD, absmax,
                           all_reduce if world > 1 else None)
             launches[0] += bgscan.launches
+            return
+        if ohscan is not None:
+            ohscan.launch(codes, tables.seq_prob, lambda c: tables(c)[0], THRESHOLD, all_reduce if world > 1 else None)
+            launches[0] += ohscan.launches
             return
         counts.zero_()
         check((lib.rs_hist if wl == "c3" else lib.rs_hist_rna)(_ptr(codes), n, _ptr(counts), sptr)); launches[0] += 1
@@ -434,6 +446,8 @@ def measure(args, wl, steps, ctx, full=True):
     kernel_ms = float(kms[:int(nrec[0])].sum()) / steps if nrec[0] else float("nan")
     n_launch = launches[0]
     hits = int(hb.counters[0].item()) if wl in ("c4", "c2") else None
+    if ohscan is not None and int(hb.counters[1].item()) != 0:
+        raise SystemExit("%d provisional candidates were rejected by the exact table" % int(hb.counters[1].item()))
     if bgscan is not None and int(hb.cand_counters[0].item()) > hb.capacity:
         raise SystemExit("candidate buffer overflowed: %d > %d" % (int(hb.cand_counters[0].item()), hb.capacity))
     if wl == "c5":
@@ -537,7 +551,10 @@ def measure(args, wl, steps, ctx, full=True):
                    "background": ("computed every step: histogram -> all-reduce(int64[8]) -> host log-odds on a side "
                                   "stream, overlapped with the structure-only candidate scan; the sequence PSSM is "
                                   "applied to the candidates afterwards (rs_refine_hits_seq)") if bgscan is not None else
-                                 "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step",
+                                 ("computed every step: histogram -> all-reduce(int64[8]); the device scans with a provisional "
+                                  "log-odds table while the counts go to the host, the exact host table decides and scores "
+                                  "the candidates (rs_scan_onehot_begin/_finish)" if ohscan is not None else
+                                  "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step"),
                    "l2_policy": ("L2 flushed between timed steps (512 MB overwrite, untimed); inputs %.2f GB per GPU"
                                  if flush_l2 else "inputs (%.2f GB per GPU) exceed the 126 MB L2") % (input_bytes / 1e9),
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
@@ -707,7 +724,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e",
                     help="skip the host-buffer end-to-end leg (e.g. for shards too large to pin on the host)")
     ap.add_argument("--serial-bg", action="store_true", dest="serial_bg",
-                    help="c4: histogram -> tables -> one-pass AND scan, strictly in sequence (no overlap)")
+                    help="c4/c2: histogram -> host tables -> scan, strictly in sequence (no overlap)")
     ap.add_argument("--no-others", action="store_true", dest="no_others",
                     help="skip the brief runs of the other configurations (other_workloads)")
     ap.add_argument("--c5-path", default="auto", choices=["auto", "cuda", "tensor"], dest="c5_path")

@@ -189,6 +189,36 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
                   int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
                   uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
 
+/* ---- one-hot threshold scans without waiting for the host's log-odds ---------------------
+ * The exact log-odds need the host's libm (Python's math.log(p / b, 2), called by Biopython's
+ * log_odds at rnascan.py:248) and the background counts (rnascan.py:445-457), i.e. a device ->
+ * host -> device round trip between rs_hist and the scan.  These three calls take it off the
+ * critical path; results are identical to rs_scan_seq / rs_scan_struct_onehot.
+ *
+ * rs_provisional_table : from DEVICE-resident counts (rs_hist output, all-reduced by the caller
+ *     if sharded) and the motif's probabilities prob[W][alphabet] (device column order: A,C,G,U
+ *     or B,E,H,L,M,R,T), writes d_table_margin[0 .. W*alphabet) = log2(p / b) with the device's
+ *     log2 (within a few ulps of the host table) and d_table_margin[W*alphabet] = a bound on
+ *     |exact - provisional| of any window score.
+ * rs_scan_onehot_begin : decision pass with that table; a window is a CANDIDATE when its
+ *     provisional score + margin + extra_margin exceeds the threshold (a superset of the exact
+ *     hits; extra_margin >= 0 is extra slack, 0 in production).  W <= 16.
+ * rs_scan_onehot_finish: with the exact host table: candidates come back in position order with
+ *     their exact scores (float32 for alphabet 4, float64 for 7).  A candidate that is not a hit
+ *     under the exact table has d_hit_pos = -1 (drop it); d_counters2[0] = entries written,
+ *     d_counters2[1] = how many of them are -1 (0 unless a score lies within the margin of the
+ *     threshold).  Same d_work / hit_capacity / stream as rs_scan_onehot_begin.               */
+int rs_provisional_table(const uint64_t *d_counts8, const double *prob, int W, int alphabet,
+                         double *d_table_margin /* W*alphabet + 1 doubles */, void *stream);
+int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n,
+                         const double *d_table_margin, int W, double threshold,
+                         double extra_margin, int64_t hit_capacity, void *d_work,
+                         int64_t work_bytes, void *stream);
+int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64_t n, const double *table,
+                          int W, double threshold, int64_t hit_capacity, int64_t *d_hit_pos,
+                          void *d_hit_score, uint64_t *d_counters2, void *d_work,
+                          int64_t work_bytes, void *stream);
+
 /* ---- sequence half of the combined decision, applied to an ordered candidate list -------
  * combine() (rnascan.py:416-434) joins two result sets thresholded with the same -m, so a
  * combined hit = structure score > m AND sequence score > m.  Only the sequence side depends

@@ -118,7 +118,15 @@ static int hist_launch(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, v
     if ((uintptr_t)d_codes & 15) { rs_set_error("codes pointer must be 16-byte aligned"); return RS_ERR_INVALID; }
     if (n == 0) return RS_OK;
     int64_t blocks = (n / 64 + HI_THREADS - 1) / HI_THREADS;
-    int64_t cap = (int64_t)rs_sm_count() * 8;
+    // exactly one resident wave: the kernel is a grid-stride loop, a partial second wave is pure tail
+    static int per_sm[RS_MAX_DEVICES] = {};
+    const int dev = rs_current_device();
+    if (!per_sm[dev]) {
+        int v = 0;
+        RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hist_kernel<PLANES>, HI_THREADS, 0));
+        per_sm[dev] = v > 0 ? v : 4;
+    }
+    int64_t cap = (int64_t)rs_sm_count() * per_sm[dev];
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     hist_kernel<PLANES><<<(unsigned)blocks, HI_THREADS, 0, (cudaStream_t)stream>>>(d_codes, n,

@@ -75,6 +75,25 @@ __global__ void kmer_lut_kernel(uint8_t *__restrict__ lut, const KmerTable tab, 
     lut[idx] = (uint8_t)bits;
 }
 
+// Same from a device-resident PROVISIONAL table (provisional.cu): tab[W*4] is followed by the margin
+// bounding |exact - provisional| of any window score.  float casts are monotone, so every window the
+// exact table would report has (float)(s + margin) > threshold here: the bits are a superset.
+__global__ void kmer_lut_dev_kernel(uint8_t *__restrict__ lut, const double *__restrict__ tab, int W,
+                                    double threshold, double extra_margin)
+{
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Q = 9 - W;
+    const double margin = tab[W * 4] + extra_margin;
+    unsigned bits = 0;
+    for (int r = 0; r < Q; r++) {
+        double s = 0.0;
+        for (int j = 0; j < W; j++) s = __dadd_rn(s, tab[j * 4 + ((idx >> (2 * (r + j))) & 3u)]);
+        const float f = (float)__dadd_ru(s, margin);
+        if ((double)f > threshold) bits |= 1u << r;
+    }
+    lut[idx] = (uint8_t)bits;
+}
+
 template <int W>
 __global__ void __launch_bounds__(KM_THREADS, 2) kmer_scan_kernel(const __grid_constant__ KmerParams prm)
 {
@@ -185,6 +204,8 @@ struct ExpandParams {
     OrderDest od;
     int W;
     int ppm;                  // positions per mask word: 28 (k-mer scan) or 32 (ballot masks)
+    int verify;               // the masks are CANDIDATES (provisional table): re-decide with the exact score;
+    double threshold;         //   a candidate that is not a hit gets position -1 and counts in counters[1]
     double ta[16 * 8];        // exact table, row stride A_STRIDE
     const uint8_t *codes_b;   // pair mode: structure stream scored with tb (row stride 8) into od.str
     double tb[16 * 8];
@@ -297,7 +318,12 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
             const int64_t pos = q_pos[warp][e];
             if ((int64_t)kk < prm.capacity) {
                 const double sc = fin_window_score<A, TS>(prm.codes, pos, prm.W, prm.ta);
-                prm.od.pos[kk] = pos;
+                bool is_hit = true;
+                if (prm.verify) {
+                    is_hit = (A == 4 ? (double)(float)sc : sc) > prm.threshold;     // _pwm.c:65 / note N1
+                    if (!is_hit) atomicAdd(prm.counters + 1, 1ull);
+                }
+                prm.od.pos[kk] = is_hit ? pos : -1;
                 if (A == 4) prm.od.seq[kk] = (float)sc;                        // _pwm.c:65
                 else        prm.od.str[kk] = sc;                               // matrix.py:34-42
                 if (A == 4 && prm.codes_b)                                     // pair mode: structure score of the same window
@@ -353,6 +379,8 @@ struct MaskScanParams {
     int64_t n, padded, n_tiles;
     double threshold;
     KmerWork wk;
+    const double *d_tab;      // candidates mode: provisional table [W][A] + margin on the device (else NULL)
+    double extra_margin;
     double ta[16 * 8];
     double tb[16 * 8];        // PAIR: structure table
 };
@@ -403,9 +431,12 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
     __shared__ uint64_t bars[STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < W * TS; k += MS_THREADS) {
-        s_ta[k] = prm.ta[k];
+        if (!PAIR && prm.d_tab) s_ta[k] = (k & 7) < A ? prm.d_tab[(k >> 3) * A + (k & 7)] : 0.0;
+        else                    s_ta[k] = prm.ta[k];
         if (PAIR) s_tb[k] = prm.tb[k];
     }
+    // candidates mode: provisional score + margin (rounded up) is compared, a superset of the exact hits
+    const double margin = (!PAIR && prm.d_tab) ? prm.d_tab[W * A] + prm.extra_margin : 0.0;
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
         fence_mbar_init();
@@ -439,7 +470,8 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
         for (int k = 0; k < MS_PER; k++) {
             const int w = warp * (32 * MS_PER) + k * 32 + lane;
             uint32_t bad;
-            const double sum = ms_score<A, W>(words, w, tab, bad);
+            double sum = ms_score<A, W>(words, w, tab, bad);
+            if (!PAIR && prm.d_tab) sum = __dadd_ru(sum, margin);
             const double cmp = A == 4 ? (double)(float)sum : sum;          // _pwm.c:65 / note N1
             bool hit = !bad && cmp > prm.threshold && t0 + w + W <= prm.n;
             if (PAIR && hit) {                                             // both scores must pass (rnascan.py:416-434)
@@ -503,11 +535,13 @@ template <int A>
 static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t n_segs, int n_ctas, int ppm,
                             const double *table, int W, int64_t cap, int64_t *d_hit_pos, float *d_hit_seq,
                             double *d_hit_str, uint64_t *d_counters2, cudaStream_t st,
-                            const uint8_t *d_codes_b = nullptr, const double *table_b = nullptr)
+                            const uint8_t *d_codes_b = nullptr, const double *table_b = nullptr,
+                            bool verify = false, double threshold = 0.0)
 {
     ExpandParams ep = {};
     ep.codes = d_codes; ep.wk = wk; ep.n_segs = n_segs; ep.capacity = cap; ep.W = W; ep.ppm = ppm;
     ep.n_ctas = n_ctas; ep.counters = (unsigned long long *)d_counters2;
+    ep.verify = verify ? 1 : 0; ep.threshold = threshold;
     ep.od = OrderDest{d_hit_pos, d_hit_seq, d_hit_str, nullptr, nullptr, 0};
     constexpr int TS = A == 4 ? 4 : 8;
     for (int j = 0; j < W; j++)
@@ -519,63 +553,6 @@ static int finish_mask_scan(const uint8_t *d_codes, const KmerWork &wk, int64_t 
     kmer_finish_kernel<A><<<(unsigned)n_ctas, FIN_THREADS, 0, st>>>(ep);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
-}
-
-// One-hot threshold scan for W <= 16 (A = 7, or A = 4 beyond the k-mer table); called from onehot_scan.cu.
-template <int A>
-static int mask_scan_impl(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
-                          int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
-                          uint64_t *d_counters2, void *d_work, cudaStream_t st)
-{
-    WorkLayout wl = rs_work_layout(n, cap);
-    MaskScanParams prm = {};
-    prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.threshold = threshold;
-    prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
-    const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
-    const int n_blocks = fin_ctas(n_segs);
-    carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
-    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
-    for (int j = 0; j < W; j++)
-        for (int c = 0; c < 8; c++) prm.ta[j * 8 + c] = c < A ? table[j * A + c] : 0.0;
-    int rc = dispatch_mask_scan<A>(W, prm, st);
-    if (rc) return rc;
-    return finish_mask_scan<A>(d_codes, prm.wk, n_segs, n_blocks, 32, table, W, cap, d_hit_pos, d_hit_seq, d_hit_str,
-                               d_counters2, st);
-}
-
-// Two-stream AND scan (two-FASTA RNASS mode), W <= 16.
-int rs_scan_pair_masks(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes, int64_t n, const double *seq_table,
-                       const double *struct_table, int W, double threshold, int64_t cap, int64_t *d_hit_pos,
-                       float *d_hit_seq, double *d_hit_str, uint64_t *d_counters2, void *d_work, cudaStream_t st)
-{
-    WorkLayout wl = rs_work_layout(n, cap);
-    MaskScanParams prm = {};
-    prm.codes = d_seq_codes; prm.codes_b = d_struct_codes; prm.n = n; prm.padded = rs_padded_count(n);
-    prm.threshold = threshold;
-    prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
-    const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
-    const int n_blocks = fin_ctas(n_segs);
-    carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
-    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
-    for (int j = 0; j < W; j++)
-        for (int c = 0; c < 8; c++) {
-            prm.ta[j * 8 + c] = c < 4 ? seq_table[j * 4 + c] : 0.0;
-            prm.tb[j * 8 + c] = c < 7 ? struct_table[j * 7 + c] : 0.0;
-        }
-    int rc = dispatch_mask_scan<4>(W, prm, st);
-    if (rc) return rc;
-    return finish_mask_scan<4>(d_seq_codes, prm.wk, n_segs, n_blocks, 32, seq_table, W, cap, d_hit_pos, d_hit_seq,
-                               d_hit_str, d_counters2, st, d_struct_codes, struct_table);
-}
-
-int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
-                         int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
-                         uint64_t *d_counters2, void *d_work, cudaStream_t st)
-{
-    if (A == 4) return mask_scan_impl<4>(d_codes, n, table, W, threshold, cap, d_hit_pos, d_hit_seq, nullptr,
-                                         d_counters2, d_work, st);
-    return mask_scan_impl<7>(d_codes, n, table, W, threshold, cap, d_hit_pos, nullptr, d_hit_str, d_counters2,
-                             d_work, st);
 }
 
 template <int W>
@@ -606,37 +583,175 @@ int64_t rs_kmer_work_bytes(int64_t n)
            rs_roundup(16 + n_ctas * 8, 256) + 256;
 }
 
-// Called by rs_scan_seq (onehot_scan.cu) when W <= 8.
+// ---- single-stream one-hot threshold scans, W <= 16, in two halves -------------------------------------
+// begin : decision masks + segment counts into the workspace (k-mer table scan for A = 4, W <= 8, ballot
+//         mask scan otherwise), from the exact host table or from a device-resident provisional table;
+// finish: segment prefix + expansion with the exact host table (verify = the masks were only candidates).
+struct OneHotGeom {
+    bool kmer;
+    int64_t n_tiles, n_segs, n_masks;
+    int n_ctas, ppm;
+};
+static OneHotGeom onehot_geom(int A, int W, int64_t n)
+{
+    OneHotGeom g;
+    g.kmer = A == 4 && W <= 8;
+    if (g.kmer) {
+        g.n_tiles = (n + KM_TILE - 1) / KM_TILE;
+        g.n_segs = g.n_tiles * KM_WARPS;
+        g.n_masks = g.n_tiles * KM_CONSUMERS;
+        g.ppm = KM_P;
+    } else {
+        g.n_tiles = (n + MS_TILE - 1) / MS_TILE;
+        g.n_segs = g.n_tiles * (MS_THREADS / 32);
+        g.n_masks = g.n_segs * 32;
+        g.ppm = 32;
+    }
+    g.n_ctas = fin_ctas(g.n_segs);
+    return g;
+}
+
+template <int A>
+static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, const double *d_tab,
+                        double extra_margin, int W, double threshold, uint8_t *wk_lut, cudaStream_t st)
+{
+    const OneHotGeom g = onehot_geom(A, W, n);
+    KmerWork wk;
+    carve_work(wk_lut, g.n_masks, g.n_segs, g.n_ctas, wk);
+    RS_CUDA(fin_arm(wk, g.n_ctas, st));
+    if (g.kmer) {
+        KmerParams prm = {};
+        prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.n_tiles = g.n_tiles; prm.wk = wk;
+        if (d_tab) {
+            kmer_lut_dev_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, d_tab, W, threshold, extra_margin);
+        } else {
+            KmerTable kt = {};
+            for (int k = 0; k < W * 4; k++) kt.t[k] = table[k];
+            kmer_lut_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, kt, W, threshold);
+        }
+        RS_CUDA(cudaGetLastError());
+        switch (W) {
+        case 1: return launch_kmer<1>(prm, st);
+        case 2: return launch_kmer<2>(prm, st);
+        case 3: return launch_kmer<3>(prm, st);
+        case 4: return launch_kmer<4>(prm, st);
+        case 5: return launch_kmer<5>(prm, st);
+        case 6: return launch_kmer<6>(prm, st);
+        case 7: return launch_kmer<7>(prm, st);
+        case 8: return launch_kmer<8>(prm, st);
+        default: rs_set_error("internal: k-mer scan needs W <= 8"); return RS_ERR_INVALID;
+        }
+    }
+    MaskScanParams prm = {};
+    prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.threshold = threshold;
+    prm.n_tiles = g.n_tiles; prm.wk = wk; prm.d_tab = d_tab; prm.extra_margin = extra_margin;
+    if (table)
+        for (int j = 0; j < W; j++)
+            for (int c = 0; c < 8; c++) prm.ta[j * 8 + c] = c < A ? table[j * A + c] : 0.0;
+    return dispatch_mask_scan<A>(W, prm, st);
+}
+
+template <int A>
+static int onehot_finish(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold, bool verify,
+                         int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str, uint64_t *d_counters2,
+                         uint8_t *wk_lut, cudaStream_t st)
+{
+    const OneHotGeom g = onehot_geom(A, W, n);
+    KmerWork wk;
+    carve_work(wk_lut, g.n_masks, g.n_segs, g.n_ctas, wk);
+    return finish_mask_scan<A>(d_codes, wk, g.n_segs, g.n_ctas, g.ppm, table, W, cap, d_hit_pos, d_hit_seq, d_hit_str,
+                               d_counters2, st, nullptr, nullptr, verify, threshold);
+}
+
+// Called by rs_scan_seq / rs_scan_struct_onehot (onehot_scan.cu) for W <= 16.
+int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
+                         int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
+                         uint64_t *d_counters2, void *d_work, cudaStream_t st)
+{
+    uint8_t *wk = (uint8_t *)d_work + rs_work_layout(n, cap).off_lut;
+    int rc = A == 4 ? onehot_begin<4>(d_codes, n, table, nullptr, 0.0, W, threshold, wk, st)
+                    : onehot_begin<7>(d_codes, n, table, nullptr, 0.0, W, threshold, wk, st);
+    if (rc) return rc;
+    return A == 4 ? onehot_finish<4>(d_codes, n, table, W, threshold, false, cap, d_hit_pos, d_hit_seq, nullptr,
+                                     d_counters2, wk, st)
+                  : onehot_finish<7>(d_codes, n, table, W, threshold, false, cap, d_hit_pos, nullptr, d_hit_str,
+                                     d_counters2, wk, st);
+}
 int rs_scan_seq_kmer(const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold, int64_t cap,
                      int64_t *d_hit_pos, float *d_hit_score, uint64_t *d_counters2, void *d_work, cudaStream_t st)
 {
-    WorkLayout wl = rs_work_layout(n, cap);
-    uint8_t *wk = (uint8_t *)d_work + wl.off_lut;
-    KmerParams prm = {};
-    prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n);
-    prm.n_tiles = (n + KM_TILE - 1) / KM_TILE;
-    const int64_t n_segs = prm.n_tiles * KM_WARPS;
-    const int n_blocks = fin_ctas(n_segs);
-    carve_work(wk, prm.n_tiles * KM_CONSUMERS, n_segs, n_blocks, prm.wk);
-    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
+    return rs_scan_onehot_masks(4, d_codes, n, table, W, threshold, cap, d_hit_pos, d_hit_score, nullptr, d_counters2,
+                                d_work, st);
+}
 
-    KmerTable kt = {};
-    for (int k = 0; k < W * 4; k++) kt.t[k] = table[k];
-    kmer_lut_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(prm.wk.lut, kt, W, threshold);
-    RS_CUDA(cudaGetLastError());
-    int rc;
-    switch (W) {
-    case 1: rc = launch_kmer<1>(prm, st); break;
-    case 2: rc = launch_kmer<2>(prm, st); break;
-    case 3: rc = launch_kmer<3>(prm, st); break;
-    case 4: rc = launch_kmer<4>(prm, st); break;
-    case 5: rc = launch_kmer<5>(prm, st); break;
-    case 6: rc = launch_kmer<6>(prm, st); break;
-    case 7: rc = launch_kmer<7>(prm, st); break;
-    case 8: rc = launch_kmer<8>(prm, st); break;
-    default: rs_set_error("internal: k-mer scan needs W <= 8"); return RS_ERR_INVALID;
-    }
+static int begin_finish_args(int alphabet, const uint8_t *d_codes, int64_t n, int W, double threshold)
+{
+    if (alphabet != 4 && alphabet != 7) { rs_set_error("alphabet must be 4 (A,C,G,U) or 7 (B,E,H,L,M,R,T)"); return RS_ERR_INVALID; }
+    if (!d_codes || ((uintptr_t)d_codes & 15)) { rs_set_error("codes pointer null or not 16-byte aligned"); return RS_ERR_INVALID; }
+    if (W < 1 || W > 16) { rs_set_error("the two-call scan covers motif widths 1..16 (got %d): use the one-call scan", W); return RS_ERR_INVALID; }
+    if (n < 0) { rs_set_error("negative length"); return RS_ERR_INVALID; }
+    if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
+    return RS_OK;
+}
+
+extern "C" int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n, const double *d_table_margin,
+                                    int W, double threshold, double extra_margin, int64_t hit_capacity,
+                                    void *d_work, int64_t work_bytes, void *stream)
+{
+    int rc = begin_finish_args(alphabet, d_codes, n, W, threshold);
     if (rc) return rc;
-    return finish_mask_scan<4>(d_codes, prm.wk, n_segs, n_blocks, KM_P, table, W, cap, d_hit_pos, d_hit_score, nullptr,
-                               d_counters2, st);
+    if (!d_table_margin) { rs_set_error("null provisional table"); return RS_ERR_INVALID; }
+    if (!(extra_margin >= 0)) { rs_set_error("extra_margin must be >= 0"); return RS_ERR_INVALID; }
+    if (n < W) return RS_OK;
+    WorkLayout wl = rs_work_layout(n, hit_capacity);
+    if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+    uint8_t *wk = (uint8_t *)d_work + wl.off_lut;
+    return alphabet == 4 ? onehot_begin<4>(d_codes, n, nullptr, d_table_margin, extra_margin, W, threshold, wk, (cudaStream_t)stream)
+                         : onehot_begin<7>(d_codes, n, nullptr, d_table_margin, extra_margin, W, threshold, wk, (cudaStream_t)stream);
+}
+
+extern "C" int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64_t n, const double *table, int W,
+                                     double threshold, int64_t hit_capacity, int64_t *d_hit_pos, void *d_hit_score,
+                                     uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = begin_finish_args(alphabet, d_codes, n, W, threshold);
+    if (rc) return rc;
+    if (!table || !d_counters2 || hit_capacity < 0 || (hit_capacity > 0 && (!d_hit_pos || !d_hit_score))) {
+        rs_set_error("rs_scan_onehot_finish: bad argument"); return RS_ERR_INVALID;
+    }
+    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    if (n < W) return RS_OK;
+    WorkLayout wl = rs_work_layout(n, hit_capacity);
+    if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+    uint8_t *wk = (uint8_t *)d_work + wl.off_lut;
+    return alphabet == 4 ? onehot_finish<4>(d_codes, n, table, W, threshold, true, hit_capacity, d_hit_pos,
+                                            (float *)d_hit_score, nullptr, d_counters2, wk, st)
+                         : onehot_finish<7>(d_codes, n, table, W, threshold, true, hit_capacity, d_hit_pos, nullptr,
+                                            (double *)d_hit_score, d_counters2, wk, st);
+}
+
+// Two-stream AND scan (two-FASTA RNASS mode), W <= 16.
+int rs_scan_pair_masks(const uint8_t *d_seq_codes, const uint8_t *d_struct_codes, int64_t n, const double *seq_table,
+                       const double *struct_table, int W, double threshold, int64_t cap, int64_t *d_hit_pos,
+                       float *d_hit_seq, double *d_hit_str, uint64_t *d_counters2, void *d_work, cudaStream_t st)
+{
+    WorkLayout wl = rs_work_layout(n, cap);
+    MaskScanParams prm = {};
+    prm.codes = d_seq_codes; prm.codes_b = d_struct_codes; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.threshold = threshold;
+    prm.n_tiles = (n + MS_TILE - 1) / MS_TILE;
+    const int64_t n_segs = prm.n_tiles * (MS_THREADS / 32);
+    const int n_blocks = fin_ctas(n_segs);
+    carve_work((uint8_t *)d_work + wl.off_lut, n_segs * 32, n_segs, n_blocks, prm.wk);
+    RS_CUDA(fin_arm(prm.wk, n_blocks, st));
+    for (int j = 0; j < W; j++)
+        for (int c = 0; c < 8; c++) {
+            prm.ta[j * 8 + c] = c < 4 ? seq_table[j * 4 + c] : 0.0;
+            prm.tb[j * 8 + c] = c < 7 ? struct_table[j * 7 + c] : 0.0;
+        }
+    int rc = dispatch_mask_scan<4>(W, prm, st);
+    if (rc) return rc;
+    return finish_mask_scan<4>(d_seq_codes, prm.wk, n_segs, n_blocks, 32, seq_table, W, cap, d_hit_pos, d_hit_seq,
+                               d_hit_str, d_counters2, st, d_struct_codes, struct_table);
 }

@@ -447,6 +447,95 @@ def scan_fused_bg(stream, profile, struct_table, seq_table_fn, threshold, all_re
         job.grow()
 
 
+class BackgroundOneHotScan(object):
+    """Thresholded one-hot scan (sequence or structure contexts, W <= 16) whose background is computed
+    from the same data (BASELINE config 2: default `rnascan -p pfm seqs.fa`).
+
+    Reference order: compute_background -> log-odds -> scan (rnascan.py:507-521).  The exact log-odds
+    need the host (Python's math.log); waiting for them would idle the device between the histogram and
+    the scan.  Here the device derives a provisional table from the counts itself and selects candidate
+    windows with a safety margin (rs_provisional_table, rs_scan_onehot_begin) while the counts travel to
+    the host and `table_fn` builds the exact table; rs_scan_onehot_finish then decides and scores every
+    candidate with the exact table.  Results are identical to histogram -> table -> rs_scan_seq."""
+
+    def __init__(self, n, kind, device=None, capacity=None):
+        require_cuda()
+        self.device = torch.device(device or "cuda")
+        self.n, self.kind = int(n), kind
+        self.A = 4 if kind == "rna" else 7
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.counted = torch.cuda.Event()
+        self.ready = torch.cuda.Event()
+        self.prov = torch.zeros(_lib.RS_MAX_W * 7 + 1, dtype=torch.float64, device=self.device)
+        self.hb = HitBuffers(self.n, int(capacity) if capacity else max(1 << 16, self.n // 256), self.device,
+                             kind == "rna", kind != "rna")
+        self.launches = 5          # hist, provisional table, decision table / mask scan (2 for k-mers), finish
+
+    def launch(self, codes, prob, table_fn, threshold, all_reduce=None, extra_margin=0.0):
+        """codes: device tensor (padded); prob: (W, A) probabilities in device column order;
+        table_fn(counts int64[8]) -> exact (W, A) log-odds table.  Returns that table."""
+        n, hb, A = self.n, self.hb, self.A
+        prob = _table(prob, A)
+        W = prob.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        self.counts.zero_()
+        check((lib.rs_hist_rna if A == 4 else lib.rs_hist)(_ptr(codes), n, _ptr(self.counts), main.cuda_stream))
+        if all_reduce is not None:
+            all_reduce(self.counts)                         # the path's only collective
+        self.counted.record(main)
+        with torch.cuda.stream(self.side):                  # counts -> host without waiting for the scan
+            self.side.wait_event(self.counted)
+            self.counts_host.copy_(self.counts, non_blocking=True)
+            self.ready.record(self.side)
+        check(lib.rs_provisional_table(_ptr(self.counts), prob.ctypes.data, W, A, _ptr(self.prov), main.cuda_stream))
+        check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.prov), W, float(threshold), float(extra_margin),
+                                       hb.capacity, _ptr(hb.work), hb.work_bytes, main.cuda_stream))
+        self.ready.synchronize()
+        table = _table(table_fn(self.counts_host.numpy()), A)
+        if table.shape[0] != W:
+            raise ValueError("table_fn returned a table of another width")
+        check(lib.rs_scan_onehot_finish(A, _ptr(codes), n, table.ctypes.data, W, float(threshold), hb.capacity,
+                                        _ptr(hb.pos), _ptr(hb.seq if A == 4 else hb.struct), _ptr(hb.counters),
+                                        _ptr(hb.work), hb.work_bytes, main.cuda_stream))
+        main.wait_stream(self.side)
+        return table
+
+    def results(self):
+        """(pos, scores, n_false_candidates) on the host, or None when the hit buffer overflowed
+        (grow() and launch again)."""
+        hb = self.hb
+        found, false_cand = (int(v) for v in hb.counters.cpu().numpy())
+        if found > hb.capacity:
+            return None
+        pos = hb.pos[:found].cpu().numpy()
+        sc = (hb.seq if self.A == 4 else hb.struct)[:found].cpu().numpy()
+        if false_cand:                                      # candidates the exact table rejected
+            keep = pos >= 0
+            pos, sc = pos[keep], sc[keep]
+        return pos, sc, false_cand
+
+    def grow(self):
+        found = int(self.hb.counters[0].item())
+        self.hb = HitBuffers(self.n, max(found, 2 * self.hb.capacity), self.device, self.A == 4, self.A != 4)
+
+
+def scan_onehot_bg(stream, prob, table_fn, threshold, all_reduce=None, capacity=None, extra_margin=0.0):
+    """histogram + thresholded one-hot scan with the host round trip hidden (see BackgroundOneHotScan).
+    Returns (pos, scores, counts int64[8], n_false_candidates)."""
+    if float(threshold) == float("-inf"):
+        raise ValueError("scan_onehot_bg needs a finite threshold")
+    kind = stream.kind or "struct"
+    job = BackgroundOneHotScan(stream.n, kind, stream.codes.device, capacity)
+    while True:
+        job.launch(stream.codes, prob, table_fn, threshold, all_reduce, extra_margin)
+        res = job.results()
+        if res is not None:
+            return res[0], res[1], job.counts_host.numpy().copy(), res[2]
+        job.grow()
+
+
 def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity=None, path=0):
     """Many motif pairs over the same resident streams (BASELINE config 5).
 

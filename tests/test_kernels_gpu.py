@@ -322,6 +322,77 @@ def test_fused_filter_is_used_and_rare(dev):
     assert resc < 0.02 * len(codes)
 
 
+# ----------------------------------------------------------------------------- provisional tables / two-call one-hot scans
+def _bg_table_fn(prob, A):
+    from rnascan_b200 import synth
+
+    def fn(counts8):
+        c = np.asarray(counts8[:A], np.float64)
+        bg = (c + 1) / (float(c.sum()) + A)
+        return synth.pssm_table(prob, background=list(bg / bg.sum()), pseudocount=0.0)
+    return fn
+
+
+@pytest.mark.parametrize("kind,W,thr,zero", [("rna", 7, "q0.999", False), ("rna", 3, "q0.9", False), ("rna", 8, 6.0, False),
+                                             ("rna", 12, "q0.999", False), ("rna", 7, "q0.99", True),
+                                             ("struct", 7, "q0.999", False), ("struct", 16, "q0.99", False),
+                                             ("struct", 4, "q0.9", True)])
+def test_scan_onehot_bg_equals_serial_path(dev, oracle, kind, W, thr, zero):
+    """provisional device table -> candidates -> exact finish == histogram -> host table -> one-call scan."""
+    from rnascan_b200 import synth
+    from rnascan_b200.device import lib, _ptr
+    A = 4 if kind == "rna" else 7
+    st0, codes, lengths = make_stream(dev, 900_000, 250, seed=300 + W, kind=kind)
+    st = dev.SymbolStream(codes, st0.offsets, lengths, kind=kind)
+    rng = np.random.default_rng(400 + W)
+    pfm = synth.pfm_rows(W, A, rng) + (0.0 if zero else 0.01)
+    if zero:
+        pfm[pfm < 0.03] = 0.0
+    prob = pfm / pfm.sum(axis=1, keepdims=True)
+    fn = _bg_table_fn(prob, A)
+    counts = dev.histogram(st).cpu().numpy()
+    table = fn(counts)
+    # the provisional table is within its own margin of the exact one
+    buf = torch.zeros(W * A + 1, dtype=torch.float64, device="cuda")
+    cdev = torch.from_numpy(counts).cuda()
+    assert lib.rs_provisional_table(_ptr(cdev), np.ascontiguousarray(prob).ctypes.data, W, A, _ptr(buf), 0) == 0
+    got = buf.cpu().numpy()
+    pt, margin = got[:-1].reshape(W, A), got[-1]
+    assert np.array_equal(np.isinf(pt), np.isinf(table))
+    fin = np.isfinite(table)
+    assert 0 < margin < 1e-7 and np.abs(pt[fin] - table[fin]).max() * W < margin / 16
+    if kind == "rna":
+        want = oracle.seq_scores(synth.to_text(codes, "rna"), table)
+    else:
+        want = oracle.alpha_scores(synth.to_text(codes, "struct"), table, "BEHLMRT")
+    thr = pick_threshold(want, thr)
+    wpos = oracle.search_hits(want, thr)
+    assert len(wpos) > 0
+    pos, sc, cnt, false_cand = dev.scan_onehot_bg(st, prob, fn, thr, capacity=64)      # tiny capacity -> regrow
+    assert np.array_equal(cnt, counts)
+    # candidates the exact table rejects: exactly the windows that TIE with the threshold (strict >), plus
+    # at most those within the margin of it
+    w64 = np.asarray(want, np.float64)
+    with np.errstate(invalid="ignore"):
+        ties = int(np.sum(w64 == thr))
+        near = int(np.sum(np.abs(w64 - thr) <= 1e-6))
+    # (a float32 tie is not borderline: the double sum sits inside the float's rounding interval)
+    assert (ties if kind == "struct" else 0) <= false_cand <= near, (ties, false_cand, near, thr)
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+    # extra slack makes many candidates that the exact table rejects: same hits, in order
+    pos2, sc2, _, false2 = dev.scan_onehot_bg(st, prob, fn, thr, extra_margin=0.75)
+    assert false2 > 0
+    assert np.array_equal(pos2, wpos)
+    assert_same_float(sc2, want[wpos])
+
+
+def test_scan_onehot_begin_rejects_wide_motifs(dev):
+    st = dev.SymbolStream(np.zeros(5000, np.uint8), kind="rna")
+    with pytest.raises(ValueError):
+        dev.scan_onehot_bg(st, np.full((17, 4), 0.25), lambda c: np.zeros((17, 4)), 1.0)
+
+
 # ----------------------------------------------------------------------------- error behaviour
 def test_bad_arguments(dev):
     st = dev.SymbolStream(np.zeros(100, np.uint8))
