@@ -200,9 +200,10 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
  *     or B,E,H,L,M,R,T), writes d_table_margin[0 .. W*alphabet) = log2(p / b) with the device's
  *     log2 (within a few ulps of the host table) and d_table_margin[W*alphabet] = a bound on
  *     |exact - provisional| of any window score.
- * rs_scan_onehot_begin : decision pass with that table; a window is a CANDIDATE when its
- *     provisional score + margin + extra_margin exceeds the threshold (a superset of the exact
- *     hits; extra_margin >= 0 is extra slack, 0 in production).  W <= 16.
+ *     A stand-alone utility (W <= 16): the scan below derives the same table itself.
+ * rs_scan_onehot_begin : decision pass with the provisional table of (d_counts8, prob); a window
+ *     is a CANDIDATE when its provisional score + margin + extra_margin exceeds the threshold (a
+ *     superset of the exact hits; extra_margin >= 0 is extra slack, 0 in production).  W <= 16.
  * rs_scan_onehot_finish: with the exact host table: candidates come back in position order with
  *     their exact scores (float32 for alphabet 4, float64 for 7).  A candidate that is not a hit
  *     under the exact table has d_hit_pos = -1 (drop it); d_counters2[0] = entries written,
@@ -211,7 +212,7 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
 int rs_provisional_table(const uint64_t *d_counts8, const double *prob, int W, int alphabet,
                          double *d_table_margin /* W*alphabet + 1 doubles */, void *stream);
 int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n,
-                         const double *d_table_margin, int W, double threshold,
+                         const uint64_t *d_counts8, const double *prob, int W, double threshold,
                          double extra_margin, int64_t hit_capacity, void *d_work,
                          int64_t work_bytes, void *stream);
 int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64_t n, const double *table,

@@ -27,6 +27,7 @@
 // the segment counts, then the non-empty segments are expanded (popc/shuffle prefix inside the
 // segment) with positions and exact scores written straight to their final, position-sorted place.
 #include "common.cuh"
+#include "provisional.cuh"
 
 #define KM_CONSUMERS   256                         // consumer threads (8 warps)
 #define KM_THREADS     (KM_CONSUMERS + 32)         // + one producer warp
@@ -75,15 +76,17 @@ __global__ void kmer_lut_kernel(uint8_t *__restrict__ lut, const KmerTable tab, 
     lut[idx] = (uint8_t)bits;
 }
 
-// Same from a device-resident PROVISIONAL table (provisional.cu): tab[W*4] is followed by the margin
-// bounding |exact - provisional| of any window score.  float casts are monotone, so every window the
-// exact table would report has (float)(s + margin) > threshold here: the bits are a superset.
-__global__ void kmer_lut_dev_kernel(uint8_t *__restrict__ lut, const double *__restrict__ tab, int W,
-                                    double threshold, double extra_margin)
+// Same from a PROVISIONAL table (provisional.cuh) that every CTA derives from the device-resident counts.
+// float casts are monotone, so every window the exact table would report has
+// (float)(s + margin) > threshold here: the bits are a superset.
+__global__ void kmer_lut_dev_kernel(uint8_t *__restrict__ lut, const unsigned long long *__restrict__ counts8,
+                                    const __grid_constant__ ProvProb prob, double threshold, double extra_margin)
 {
+    __shared__ double tab[RS_PROV_MAX_W * 4];
+    const int W = prob.W;
+    const double margin = rs_prov_table_cta<4>(counts8, prob, tab) + extra_margin;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int Q = 9 - W;
-    const double margin = tab[W * 4] + extra_margin;
     unsigned bits = 0;
     for (int r = 0; r < Q; r++) {
         double s = 0.0;
@@ -379,8 +382,9 @@ struct MaskScanParams {
     int64_t n, padded, n_tiles;
     double threshold;
     KmerWork wk;
-    const double *d_tab;      // candidates mode: provisional table [W][A] + margin on the device (else NULL)
+    const unsigned long long *d_counts8;   // candidates mode: provisional table from these counts (else NULL)
     double extra_margin;
+    ProvProb prob;
     double ta[16 * 8];
     double tb[16 * 8];        // PAIR: structure table
 };
@@ -430,13 +434,17 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
     __shared__ __align__(16) double s_tb[PAIR ? W * TS : 1];
     __shared__ uint64_t bars[STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < W * TS; k += MS_THREADS) {
-        if (!PAIR && prm.d_tab) s_ta[k] = (k & 7) < A ? prm.d_tab[(k >> 3) * A + (k & 7)] : 0.0;
-        else                    s_ta[k] = prm.ta[k];
-        if (PAIR) s_tb[k] = prm.tb[k];
-    }
     // candidates mode: provisional score + margin (rounded up) is compared, a superset of the exact hits
-    const double margin = (!PAIR && prm.d_tab) ? prm.d_tab[W * A] + prm.extra_margin : 0.0;
+    double margin = 0.0;
+    const bool provisional = !PAIR && prm.d_counts8 != nullptr;
+    if (provisional) {
+        margin = rs_prov_table_cta<TS>(prm.d_counts8, prm.prob, s_ta) + prm.extra_margin;
+    } else {
+        for (int k = tid; k < W * TS; k += MS_THREADS) {
+            s_ta[k] = prm.ta[k];
+            if (PAIR) s_tb[k] = prm.tb[k];
+        }
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
         fence_mbar_init();
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
             const int w = warp * (32 * MS_PER) + k * 32 + lane;
             uint32_t bad;
             double sum = ms_score<A, W>(words, w, tab, bad);
-            if (!PAIR && prm.d_tab) sum = __dadd_ru(sum, margin);
+            if (provisional) sum = __dadd_ru(sum, margin);
             const double cmp = A == 4 ? (double)(float)sum : sum;          // _pwm.c:65 / note N1
             bool hit = !bad && cmp > prm.threshold && t0 + w + W <= prm.n;
             if (PAIR && hit) {                                             // both scores must pass (rnascan.py:416-434)
@@ -612,18 +620,25 @@ static OneHotGeom onehot_geom(int A, int W, int64_t n)
 }
 
 template <int A>
-static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, const double *d_tab,
-                        double extra_margin, int W, double threshold, uint8_t *wk_lut, cudaStream_t st)
+static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, const uint64_t *d_counts8,
+                        const double *prob, double extra_margin, int W, double threshold, uint8_t *wk_lut,
+                        cudaStream_t st)
 {
     const OneHotGeom g = onehot_geom(A, W, n);
     KmerWork wk;
     carve_work(wk_lut, g.n_masks, g.n_segs, g.n_ctas, wk);
     RS_CUDA(fin_arm(wk, g.n_ctas, st));
+    ProvProb pp = {};
+    if (d_counts8) {
+        pp.W = W; pp.A = A;
+        for (int k = 0; k < W * A; k++) pp.p[k] = prob[k];
+    }
     if (g.kmer) {
         KmerParams prm = {};
         prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.n_tiles = g.n_tiles; prm.wk = wk;
-        if (d_tab) {
-            kmer_lut_dev_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, d_tab, W, threshold, extra_margin);
+        if (d_counts8) {
+            kmer_lut_dev_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, (const unsigned long long *)d_counts8, pp,
+                                                                    threshold, extra_margin);
         } else {
             KmerTable kt = {};
             for (int k = 0; k < W * 4; k++) kt.t[k] = table[k];
@@ -644,7 +659,8 @@ static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, 
     }
     MaskScanParams prm = {};
     prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.threshold = threshold;
-    prm.n_tiles = g.n_tiles; prm.wk = wk; prm.d_tab = d_tab; prm.extra_margin = extra_margin;
+    prm.n_tiles = g.n_tiles; prm.wk = wk; prm.extra_margin = extra_margin;
+    prm.d_counts8 = (const unsigned long long *)d_counts8; prm.prob = pp;
     if (table)
         for (int j = 0; j < W; j++)
             for (int c = 0; c < 8; c++) prm.ta[j * 8 + c] = c < A ? table[j * A + c] : 0.0;
@@ -669,8 +685,8 @@ int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double 
                          uint64_t *d_counters2, void *d_work, cudaStream_t st)
 {
     uint8_t *wk = (uint8_t *)d_work + rs_work_layout(n, cap).off_lut;
-    int rc = A == 4 ? onehot_begin<4>(d_codes, n, table, nullptr, 0.0, W, threshold, wk, st)
-                    : onehot_begin<7>(d_codes, n, table, nullptr, 0.0, W, threshold, wk, st);
+    int rc = A == 4 ? onehot_begin<4>(d_codes, n, table, nullptr, nullptr, 0.0, W, threshold, wk, st)
+                    : onehot_begin<7>(d_codes, n, table, nullptr, nullptr, 0.0, W, threshold, wk, st);
     if (rc) return rc;
     return A == 4 ? onehot_finish<4>(d_codes, n, table, W, threshold, false, cap, d_hit_pos, d_hit_seq, nullptr,
                                      d_counters2, wk, st)
@@ -694,20 +710,20 @@ static int begin_finish_args(int alphabet, const uint8_t *d_codes, int64_t n, in
     return RS_OK;
 }
 
-extern "C" int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n, const double *d_table_margin,
-                                    int W, double threshold, double extra_margin, int64_t hit_capacity,
-                                    void *d_work, int64_t work_bytes, void *stream)
+extern "C" int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n, const uint64_t *d_counts8,
+                                    const double *prob, int W, double threshold, double extra_margin,
+                                    int64_t hit_capacity, void *d_work, int64_t work_bytes, void *stream)
 {
     int rc = begin_finish_args(alphabet, d_codes, n, W, threshold);
     if (rc) return rc;
-    if (!d_table_margin) { rs_set_error("null provisional table"); return RS_ERR_INVALID; }
+    if (!d_counts8 || !prob) { rs_set_error("null counts or probabilities"); return RS_ERR_INVALID; }
     if (!(extra_margin >= 0)) { rs_set_error("extra_margin must be >= 0"); return RS_ERR_INVALID; }
     if (n < W) return RS_OK;
     WorkLayout wl = rs_work_layout(n, hit_capacity);
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
     uint8_t *wk = (uint8_t *)d_work + wl.off_lut;
-    return alphabet == 4 ? onehot_begin<4>(d_codes, n, nullptr, d_table_margin, extra_margin, W, threshold, wk, (cudaStream_t)stream)
-                         : onehot_begin<7>(d_codes, n, nullptr, d_table_margin, extra_margin, W, threshold, wk, (cudaStream_t)stream);
+    return alphabet == 4 ? onehot_begin<4>(d_codes, n, nullptr, d_counts8, prob, extra_margin, W, threshold, wk, (cudaStream_t)stream)
+                         : onehot_begin<7>(d_codes, n, nullptr, d_counts8, prob, extra_margin, W, threshold, wk, (cudaStream_t)stream);
 }
 
 extern "C" int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64_t n, const double *table, int W,

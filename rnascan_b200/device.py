@@ -454,7 +454,7 @@ class BackgroundOneHotScan(object):
     Reference order: compute_background -> log-odds -> scan (rnascan.py:507-521).  The exact log-odds
     need the host (Python's math.log); waiting for them would idle the device between the histogram and
     the scan.  Here the device derives a provisional table from the counts itself and selects candidate
-    windows with a safety margin (rs_provisional_table, rs_scan_onehot_begin) while the counts travel to
+    windows with a safety margin (rs_scan_onehot_begin) while the counts travel to
     the host and `table_fn` builds the exact table; rs_scan_onehot_finish then decides and scores every
     candidate with the exact table.  Results are identical to histogram -> table -> rs_scan_seq."""
 
@@ -468,10 +468,9 @@ class BackgroundOneHotScan(object):
         self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
         self.counted = torch.cuda.Event()
         self.ready = torch.cuda.Event()
-        self.prov = torch.zeros(_lib.RS_MAX_W * 7 + 1, dtype=torch.float64, device=self.device)
         self.hb = HitBuffers(self.n, int(capacity) if capacity else max(1 << 16, self.n // 256), self.device,
                              kind == "rna", kind != "rna")
-        self.launches = 5          # hist, provisional table, decision table / mask scan (2 for k-mers), finish
+        self.launches = 4          # hist, decision table (k-mers), scan, finish
 
     def launch(self, codes, prob, table_fn, threshold, all_reduce=None, extra_margin=0.0):
         """codes: device tensor (padded); prob: (W, A) probabilities in device column order;
@@ -489,9 +488,9 @@ class BackgroundOneHotScan(object):
             self.side.wait_event(self.counted)
             self.counts_host.copy_(self.counts, non_blocking=True)
             self.ready.record(self.side)
-        check(lib.rs_provisional_table(_ptr(self.counts), prob.ctypes.data, W, A, _ptr(self.prov), main.cuda_stream))
-        check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.prov), W, float(threshold), float(extra_margin),
-                                       hb.capacity, _ptr(hb.work), hb.work_bytes, main.cuda_stream))
+        check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.counts), prob.ctypes.data, W, float(threshold),
+                                       float(extra_margin), hb.capacity, _ptr(hb.work), hb.work_bytes,
+                                       main.cuda_stream))
         self.ready.synchronize()
         table = _table(table_fn(self.counts_host.numpy()), A)
         if table.shape[0] != W:
