@@ -312,7 +312,7 @@ def run_b200(args):
     if rank == 0:
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_port_baseline(args.workload)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -709,10 +709,27 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "Gpos/s", "cores": cores,
                             "kind": ref_driver.kind(), "sample": sample},
            "e2e": {"value": value, "unit": "Gpos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    # native libraries (NCCL's version banner, for one) write to fd 1: keep stdout for the JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -389,7 +389,14 @@ class BackgroundFusedScan(object):
         n, hb = self.n, self.hb
         tq = _table(struct_table, 7)
         main = torch.cuda.current_stream(self.device)
-        self.side.wait_stream(main)
+        self.side.wait_stream(main)                         # inputs ready; previous pass finished with the buffers
+        # the big kernel first, so that the host-side cost of the side-stream calls (the collective above
+        # all) is spent while the device is already busy
+        tiles = ctypes.c_int64(0)
+        check(lib.rs_scan_fused_candidates(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,
+                                           float(threshold), float(absrow_max), hb.capacity,
+                                           _ptr(hb.cand_counters), _ptr(hb.work), hb.work_bytes,
+                                           ctypes.addressof(tiles), main.cuda_stream))
         with torch.cuda.stream(self.side):
             self.counts.zero_()
             check(lib.rs_hist_rna(_ptr(codes), n, _ptr(self.counts), self.side.cuda_stream))
@@ -397,11 +404,6 @@ class BackgroundFusedScan(object):
                 all_reduce(self.counts)                     # the path's only collective
             self.counts_host.copy_(self.counts, non_blocking=True)
             self.ready.record(self.side)
-        tiles = ctypes.c_int64(0)
-        check(lib.rs_scan_fused_candidates(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,
-                                           float(threshold), float(absrow_max), hb.capacity,
-                                           _ptr(hb.cand_counters), _ptr(hb.work), hb.work_bytes,
-                                           ctypes.addressof(tiles), main.cuda_stream))
         self.ready.synchronize()
         ts = _table(seq_table_fn(self.counts_host.numpy()), 4)
         if ts.shape[0] != W:
@@ -447,6 +449,20 @@ def scan_fused_bg(stream, profile, struct_table, seq_table_fn, threshold, all_re
         job.grow()
 
 
+def _background_shift(local8, global8, A):
+    """max over letters of |log2(b_local / b_global)| for backgrounds b = (count + 1) / (sum + A) renormalised
+    (rnascan.py:445-457): a window score computed with one background differs from the other by at most W
+    times this."""
+    import math
+    worst = 0.0
+    bl = [(float(local8[c]) + 1) / (float(sum(int(v) for v in local8[:A])) + A) for c in range(A)]
+    bg = [(float(global8[c]) + 1) / (float(sum(int(v) for v in global8[:A])) + A) for c in range(A)]
+    sl, sg = sum(bl), sum(bg)
+    for c in range(A):
+        worst = max(worst, abs(math.log2((bl[c] / sl) / (bg[c] / sg))))
+    return worst * (1 + 1e-9) + 1e-12
+
+
 class BackgroundOneHotScan(object):
     """Thresholded one-hot scan (sequence or structure contexts, W <= 16) whose background is computed
     from the same data (BASELINE config 2: default `rnascan -p pfm seqs.fa`).
@@ -465,14 +481,16 @@ class BackgroundOneHotScan(object):
         self.A = 4 if kind == "rna" else 7
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
         self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
-        self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.counts_global = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.counts_host = torch.zeros(16, dtype=torch.int64).pin_memory()      # [0:8] global, [8:16] this shard
         self.counted = torch.cuda.Event()
+        self.rescanned = False
         self.ready = torch.cuda.Event()
         self.hb = HitBuffers(self.n, int(capacity) if capacity else max(1 << 16, self.n // 256), self.device,
                              kind == "rna", kind != "rna")
         self.launches = 4          # hist, decision table (k-mers), scan, finish
 
-    def launch(self, codes, prob, table_fn, threshold, all_reduce=None, extra_margin=0.0):
+    def launch(self, codes, prob, table_fn, threshold, all_reduce=None, extra_margin=0.0, shard_margin=0.05):
         """codes: device tensor (padded); prob: (W, A) probabilities in device column order;
         table_fn(counts int64[8]) -> exact (W, A) log-odds table.  Returns that table."""
         n, hb, A = self.n, self.hb, self.A
@@ -481,20 +499,37 @@ class BackgroundOneHotScan(object):
         main = torch.cuda.current_stream(self.device)
         self.counts.zero_()
         check((lib.rs_hist_rna if A == 4 else lib.rs_hist)(_ptr(codes), n, _ptr(self.counts), main.cuda_stream))
-        if all_reduce is not None:
-            all_reduce(self.counts)                         # the path's only collective
         self.counted.record(main)
-        with torch.cuda.stream(self.side):                  # counts -> host without waiting for the scan
-            self.side.wait_event(self.counted)
-            self.counts_host.copy_(self.counts, non_blocking=True)
-            self.ready.record(self.side)
+        # Sharded runs: the decision pass starts from THIS shard's counts with `shard_margin` of extra slack
+        # while the all-reduce and the trip to the host run beside it; the slack is verified below against
+        # the global counts (a shard whose composition differs more is re-scanned from the global counts).
+        sharded = all_reduce is not None
+        slack = float(extra_margin) + (float(shard_margin) if sharded else 0.0)
         check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.counts), prob.ctypes.data, W, float(threshold),
-                                       float(extra_margin), hb.capacity, _ptr(hb.work), hb.work_bytes,
-                                       main.cuda_stream))
+                                       slack, hb.capacity, _ptr(hb.work), hb.work_bytes, main.cuda_stream))
+        with torch.cuda.stream(self.side):                  # counts -> (all ranks) -> host, beside the scan
+            self.side.wait_event(self.counted)
+            self.counts_host[8:].copy_(self.counts, non_blocking=True)          # local
+            if sharded:
+                self.counts_global.copy_(self.counts)
+                all_reduce(self.counts_global)              # the path's only collective
+                self.counts_host[:8].copy_(self.counts_global, non_blocking=True)
+            else:
+                self.counts_host[:8].copy_(self.counts, non_blocking=True)
+            self.ready.record(self.side)
         self.ready.synchronize()
-        table = _table(table_fn(self.counts_host.numpy()), A)
+        ch = self.counts_host.numpy()
+        table = _table(table_fn(ch[:8]), A)
         if table.shape[0] != W:
             raise ValueError("table_fn returned a table of another width")
+        self.rescanned = False
+        if sharded and W * _background_shift(ch[8:], ch[:8], A) > float(shard_margin) * 0.999:
+            # this shard's composition is too far from the global one for the slack: decide from global counts
+            main.wait_stream(self.side)
+            check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.counts_global), prob.ctypes.data, W,
+                                           float(threshold), float(extra_margin), hb.capacity, _ptr(hb.work),
+                                           hb.work_bytes, main.cuda_stream))
+            self.rescanned = True
         check(lib.rs_scan_onehot_finish(A, _ptr(codes), n, table.ctypes.data, W, float(threshold), hb.capacity,
                                         _ptr(hb.pos), _ptr(hb.seq if A == 4 else hb.struct), _ptr(hb.counters),
                                         _ptr(hb.work), hb.work_bytes, main.cuda_stream))
@@ -531,7 +566,7 @@ def scan_onehot_bg(stream, prob, table_fn, threshold, all_reduce=None, capacity=
         job.launch(stream.codes, prob, table_fn, threshold, all_reduce, extra_margin)
         res = job.results()
         if res is not None:
-            return res[0], res[1], job.counts_host.numpy().copy(), res[2]
+            return res[0], res[1], job.counts_host.numpy()[:8].copy(), res[2]
         job.grow()
 
 

@@ -387,6 +387,34 @@ def test_scan_onehot_bg_equals_serial_path(dev, oracle, kind, W, thr, zero):
     assert_same_float(sc2, want[wpos])
 
 
+@pytest.mark.parametrize("other,expect_rescan", [([270_000, 220_000, 220_000, 290_000], False),
+                                                 ([900_000, 10_000, 10_000, 80_000], True)])
+def test_scan_onehot_bg_sharded_starts_from_local_counts(dev, oracle, other, expect_rescan):
+    """Sharded runs decide from the shard's own counts + a verified slack while the all-reduce is in flight;
+    a shard whose composition is too far from the global one is re-scanned.  Either way the hits are those
+    of the exact table built from the GLOBAL counts."""
+    from rnascan_b200 import synth
+    W = 7
+    st0, codes, lengths = make_stream(dev, 900_000, 250, seed=511, kind="rna")
+    st = dev.SymbolStream(codes, st0.offsets, lengths, kind="rna")
+    pfm = synth.pfm_rows(W, 4, np.random.default_rng(512)) + 0.01
+    prob = pfm / pfm.sum(axis=1, keepdims=True)
+    fn = _bg_table_fn(prob, 4)
+    extra = torch.tensor(other + [0, 0, 0, 0], dtype=torch.int64, device="cuda")     # "the other shard"
+    job = dev.BackgroundOneHotScan(st.n, "rna", st.codes.device, capacity=st.n)
+    table = job.launch(st.codes, prob, fn, 2.0, all_reduce=lambda t: t.add_(extra))
+    pos, sc, _ = job.results()
+    assert job.rescanned == expect_rescan
+    local = np.array([(codes == k).sum() for k in range(4)], np.int64)
+    assert np.array_equal(job.counts_host.numpy()[:4], local + np.array(other))
+    assert np.array_equal(table, fn(np.concatenate([local + np.array(other), np.zeros(4, np.int64)])))
+    want = oracle.seq_scores(synth.to_text(codes, "rna"), table)
+    wpos = oracle.search_hits(want, 2.0)
+    assert len(wpos) > 100
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sc, want[wpos])
+
+
 def test_scan_onehot_begin_rejects_wide_motifs(dev):
     st = dev.SymbolStream(np.zeros(5000, np.uint8), kind="rna")
     with pytest.raises(ValueError):
