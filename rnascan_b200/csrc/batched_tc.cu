@@ -339,8 +339,22 @@ __device__ __forceinline__ bool tc_exact(const RescoreParams &prm, int m, int64_
     return s > prm.threshold;
 }
 
-__global__ void batched_rescore_kernel(const RescoreParams prm)
+// SMEM: the sequence tables of all motifs ([M][stride][4] doubles, 96 KB for 256 x 12) and the per-motif
+// counters live in shared memory: the sequence condition -- which turns down ~99.7 % of the structure
+// candidates -- then costs one global round trip (the window's symbols, five aligned words fetched
+// together) instead of W dependent L2 accesses, and the counters are flushed once per CTA.
+template <bool SMEM>
+__global__ void __launch_bounds__(256) batched_rescore_kernel(const RescoreParams prm, int n_motifs)
 {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    double *s_seq = reinterpret_cast<double *>(rs_smem);
+    const int seq_doubles = SMEM ? n_motifs * prm.stride_rows * 4 : 0;
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(rs_smem + (size_t)seq_doubles * 8);      // [2M]: hits, re-scored
+    if (SMEM) {
+        for (int k = threadIdx.x; k < seq_doubles; k += blockDim.x) s_seq[k] = prm.seq_tables[k];
+        for (int k = threadIdx.x; k < 2 * n_motifs; k += blockDim.x) s_cnt[k] = 0u;
+        __syncthreads();
+    }
     unsigned long long total = *prm.cand_count;
     if ((int64_t)total > prm.cand_capacity) total = (unsigned long long)prm.cand_capacity;
     for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < total;
@@ -349,13 +363,83 @@ __global__ void batched_rescore_kernel(const RescoreParams prm)
         const int m = (int)(key >> 40);
         const int64_t pos = (int64_t)(key & ((1ull << 40) - 1));
         float sq; double st;
-        atomicAdd(&prm.motif_counters2[2 * m + 1], 1ull);
-        if (tc_exact(prm, m, pos, sq, st)) {
-            atomicAdd(&prm.motif_counters2[2 * m], 1ull);
+        bool hit;
+        if (SMEM) {
+            atomicAdd(&s_cnt[2 * m + 1], 1u);
+            const int W = prm.widths[m];
+            hit = pos + W <= prm.n;
+            if (hit) {
+                // the window's symbols: W <= 12 bytes from five aligned words (stream padding covers the over-read)
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(prm.codes + (pos & ~(int64_t)3));
+                const unsigned sh = (unsigned)(pos & 3) * 8u;
+                uint32_t w[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) w[i] = q[i];
+                const double *tab = s_seq + (size_t)m * prm.stride_rows * 4;
+                double qd = 0.0;
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < TC_WMAX; j++) {
+                    if (j < W) {
+                        const uint32_t c = (__funnelshift_r(w[j >> 2], w[(j >> 2) + 1], sh) >> (8 * (j & 3))) & 0xFFu;
+                        ok = ok && (c & 7u) < 4u;
+                        qd = __dadd_rn(qd, tab[j * 4 + (c & 3u)]);
+                    }
+                }
+                const float qf = (float)qd;                                  // _pwm.c:65
+                sq = qf;
+                hit = ok && (double)qf > prm.threshold;                      // SURVEY.md note N1
+                if (hit) {
+                    st = rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS,
+                                                        prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS, W);
+                    hit = st > prm.threshold;
+                }
+            }
+            if (hit) atomicAdd(&s_cnt[2 * m], 1u);
+        } else {
+            atomicAdd(&prm.motif_counters2[2 * m + 1], 1ull);
+            hit = tc_exact(prm, m, pos, sq, st);
+            if (hit) atomicAdd(&prm.motif_counters2[2 * m], 1ull);
+        }
+        if (hit) {
             const unsigned long long slot = atomicAdd(prm.hit_count, 1ull);
             if ((int64_t)slot < prm.hit_capacity) prm.hitkeys[slot] = key;
         }
     }
+    if (SMEM) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < 2 * n_motifs; k += blockDim.x)
+            if (s_cnt[k]) atomicAdd(&prm.motif_counters2[k], (unsigned long long)s_cnt[k]);
+    }
+}
+
+// Ordering the hits by (motif, position).  The per-motif hit counts are known (bases[]), so the keys are
+// first dropped into their motif's slice in arrival order (one atomic cursor per motif) and then ranked
+// INSIDE the slice: keys are unique, the final index of a key is the number of smaller keys of its motif.
+// Slices hold ~100 keys, so this is two small launches instead of a ~100-step bitonic network, which
+// remains for very large hit lists.
+#define SLICE_SORT_MAX 262144
+__global__ void tc_bucket_kernel(const unsigned long long *__restrict__ keys, int64_t n_keys,
+                                 const unsigned long long *__restrict__ bases, unsigned long long *cursor,
+                                 unsigned long long *__restrict__ bucketed)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_keys) return;
+    const unsigned long long key = keys[i];
+    const int m = (int)(key >> 40);
+    bucketed[bases[m] + atomicAdd(&cursor[m], 1ull)] = key;
+}
+__global__ void tc_slice_rank_kernel(const unsigned long long *__restrict__ bucketed, int64_t n_keys,
+                                     const unsigned long long *__restrict__ bases, unsigned long long *__restrict__ sorted)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_keys) return;
+    const unsigned long long key = bucketed[i];
+    const int m = (int)(key >> 40);
+    const unsigned long long lo = bases[m], hi = bases[m + 1];
+    unsigned long long rank = 0;
+    for (unsigned long long k = lo; k < hi; k++) rank += bucketed[k] < key;
+    sorted[lo + rank] = key;
 }
 
 // bitonic sort of 64-bit keys (padded to a power of two with ~0)
@@ -397,11 +481,30 @@ __global__ void batched_finalize_kernel(const RescoreParams prm, const unsigned 
         out_str[k] = st;
     }
 }
-__global__ void batched_bases_kernel(unsigned long long *bases, const unsigned long long *counters2, int n_motifs)
+__global__ void __launch_bounds__(256) batched_bases_kernel(unsigned long long *bases, const unsigned long long *counters2,
+                                                            int n_motifs)
 {
-    unsigned long long acc = 0;
-    for (int m = 0; m < n_motifs; m++) { bases[m] = acc; acc += counters2[2 * m]; }
-    bases[n_motifs] = acc;
+    __shared__ unsigned long long s_scan[256];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int m0 = 0; m0 < n_motifs; m0 += 256) {
+        const int m = m0 + threadIdx.x;
+        const unsigned long long v = m < n_motifs ? counters2[2 * m] : 0ull;
+        s_scan[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            const unsigned long long t = threadIdx.x >= d ? s_scan[threadIdx.x - d] : 0ull;
+            __syncthreads();
+            s_scan[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (m < n_motifs) bases[m] = s_carry + s_scan[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry += s_scan[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bases[n_motifs] = s_carry;
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -510,7 +613,7 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     if (seq_tables)
         RS_CUDA(cudaMemcpyAsync(d_ts, seq_tables, (size_t)n_motifs * stride_rows * 4 * 8, cudaMemcpyHostToDevice, st));
     RS_CUDA(cudaMemcpyAsync(d_w, widths, (size_t)n_motifs * 4, cudaMemcpyHostToDevice, st));
-    RS_CUDA(cudaStreamSynchronize(st));          // the host vectors above go out of scope
+    // (pageable sources: cudaMemcpyAsync returns once they are staged, so `bmat` may go out of scope)
 
     // ---- tensor-core filter, one launch per group of 256 motifs
     // 160 KB of dynamic shared memory: more than half an SM's, so exactly one CTA (which owns all
@@ -554,19 +657,43 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     rp.hitkeys = hitkeys; rp.hit_count = hit_count; rp.motif_counters2 = (unsigned long long *)d_motif_counters2;
     rp.hit_capacity = hit_capacity;
     if (h_cand > 0) {
-        int blocks = (int)fmin((double)((h_cand + 255) / 256), (double)rs_sm_count() * 8);
-        batched_rescore_kernel<<<blocks, 256, 0, st>>>(rp);
+        const size_t tab_smem = (size_t)n_motifs * stride_rows * 4 * 8 + (size_t)n_motifs * 2 * 4;
+        if (mode == RS_MODE_AND && tab_smem <= 100 * 1024) {
+            static bool rs_configured[RS_MAX_DEVICES] = {};
+            if (!rs_configured[dev]) {
+                RS_CUDA(cudaFuncSetAttribute(batched_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             100 * 1024));
+                rs_configured[dev] = true;
+            }
+            int blocks = (int)fmin((double)((h_cand + 255) / 256), (double)rs_sm_count() * 2);
+            batched_rescore_kernel<true><<<blocks, 256, tab_smem, st>>>(rp, n_motifs);
+        } else {
+            int blocks = (int)fmin((double)((h_cand + 255) / 256), (double)rs_sm_count() * 8);
+            batched_rescore_kernel<false><<<blocks, 256, 0, st>>>(rp, n_motifs);
+        }
         RS_CUDA(cudaGetLastError());
     }
-    batched_bases_kernel<<<1, 1, 0, st>>>((unsigned long long *)d_bases, (const unsigned long long *)d_motif_counters2,
+    batched_bases_kernel<<<1, 256, 0, st>>>((unsigned long long *)d_bases, (const unsigned long long *)d_motif_counters2,
                                           n_motifs);
     RS_CUDA(cudaGetLastError());
     unsigned long long h_hits = 0;
     RS_CUDA(cudaMemcpyAsync(&h_hits, hit_count, 8, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
     if (h_hits == 0 || hit_capacity == 0) return RS_OK;
-    int64_t nsort = 1;
     const int64_t stored = (int64_t)h_hits < hit_capacity ? (int64_t)h_hits : hit_capacity;
+    if ((int64_t)h_hits <= hit_capacity && stored <= SLICE_SORT_MAX && stored + n_motifs + 1 <= cand_cap) {
+        // the candidate list is no longer needed: it holds the bucketed keys and the per-motif cursors
+        unsigned long long *bucketed = cand, *cursor = cand + stored;
+        RS_CUDA(cudaMemsetAsync(cursor, 0, (size_t)n_motifs * 8, st));
+        const int blocks = (int)((stored + 255) / 256);
+        tc_bucket_kernel<<<blocks, 256, 0, st>>>(hitkeys, stored, (const unsigned long long *)d_bases, cursor, bucketed);
+        tc_slice_rank_kernel<<<blocks, 256, 0, st>>>(bucketed, stored, (const unsigned long long *)d_bases, hitkeys);
+        RS_CUDA(cudaGetLastError());
+        batched_finalize_kernel<<<blocks, 256, 0, st>>>(rp, hitkeys, d_hit_motif, d_hit_pos, d_hit_seq, d_hit_struct);
+        RS_CUDA(cudaGetLastError());
+        return RS_OK;
+    }
+    int64_t nsort = 1;
     while (nsort < stored) nsort <<= 1;
     const int sort_blocks = (int)fmin((double)((nsort + 255) / 256), (double)rs_sm_count() * 8);
     tc_pad_keys_kernel<<<sort_blocks, 256, 0, st>>>(hitkeys, hit_count, hit_capacity, nsort);
