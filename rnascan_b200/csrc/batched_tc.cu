@@ -92,6 +92,32 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// the same load without the wait, and the wait as a separate step that "touches" the destination
+// registers (so no use of them can be scheduled before it): lets the next chunk's load fly while the
+// current chunk is being processed
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ float tc_max3(float a, float b, float c)
 {
     float d;
@@ -220,10 +246,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * TC_N;
             const int64_t pos = (first + it * stride) * TC_M + q * 32 + lane;
             const bool in_range = pos < prm.n;
-#pragma unroll 1
-            for (int c = half * (TC_N / 64); c < (half + 1) * (TC_N / 64); c++) {
-                uint32_t v[32];
-                tc_ld32(taddr + 32u * c, v);
+            // four chunks of 32 motif columns per warp and tile; the load of chunk i+1 is in flight while
+            // chunk i is processed (two register buffers)
+            constexpr int NCH = TC_N / 64;
+            const int c_first = half * NCH;
+            uint32_t va[32], vb[32];
+            auto process = [&](uint32_t (&v)[32], int c) {
                 // sign bits of the 32 accumulators, one funnel shift each: candidate <=> sign clear
                 // (accumulator >= +0; unused motif columns carry a -1 bias so they never qualify)
                 uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;           // four independent chains of 8
@@ -255,6 +283,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
                     }
                     cnt += total;
                     __syncwarp();
+                }
+            };
+            tc_ld32_issue(taddr + 32u * c_first, va);
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                if ((i & 1) == 0) {
+                    tc_ld_wait(va);
+                    if (i + 1 < NCH) tc_ld32_issue(taddr + 32u * (c_first + i + 1), vb);
+                    process(va, c_first + i);
+                } else {
+                    tc_ld_wait(vb);
+                    if (i + 1 < NCH) tc_ld32_issue(taddr + 32u * (c_first + i + 1), va);
+                    process(vb, c_first + i);
                 }
             }
             tc_fence_before();
