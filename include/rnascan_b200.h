@@ -85,6 +85,24 @@ int rs_host_fasta_index(const uint8_t *buf, int64_t n, int64_t *n_records, int64
 int rs_host_fasta_fill(const uint8_t *buf, int64_t n, int kind, uint8_t *text, uint8_t *codes,
                        int64_t *rec_off, int64_t *rec_len, char *titles, int64_t *title_off);
 
+/* ---- averaged-profile text -> float64 rows (replaces the per-file pd.read_table + del struct['PO'] of
+ * rnascan.py:296-297 for plain pfmutil.format_pfm files: header PO + B,E,H,L,M,R,T in any order, one
+ * tab-separated row per position).  Numbers are converted with pandas' own default algorithm
+ * (precise_xstrtod of its C tokenizer: NOT correctly rounded), restated in profile_ingest.cpp, so the
+ * rows -- and every score computed from them -- are bit-identical to what the reference reads.
+ * rs_host_profiles_open reads and indexes all files on `threads` host threads: rows_per_file[i] = number
+ * of rows, or -1 when file i is outside the plain format (the caller parses it with pandas);
+ * rs_host_profiles_fill writes file i's rows, channels in B,E,H,L,M,R,T order, at out + 7*row_offsets[i]
+ * and sets status[i] = RS_OK, or RS_ERR_INVALID when a field turns out not to be a plain number (again:
+ * pandas).  rs_host_profiles_close frees the batch.  rs_host_parse_doubles exposes the converter alone
+ * ('\n'-separated tokens; ok[k] = 0 where it declines).                                               */
+int rs_host_profiles_open(const char *const *paths, int64_t n_files, int threads, void **handle,
+                          int64_t *rows_per_file);
+int rs_host_profiles_fill(void *handle, int threads, double *out, const int64_t *row_offsets, int *status);
+int rs_host_profiles_close(void *handle);
+int rs_host_parse_doubles(const char *text, int64_t n_bytes, double *out, int64_t capacity, int64_t *n_out,
+                          uint8_t *ok);
+
 /* ---- host-side encoding (CPU threads; replaces str.upper()/transcribe() + the char
  *      switch of _pwm.c:41-63 and the dict lookup of matrix.py:36-41) ---------------- */
 int rs_host_encode_rna(const uint8_t *text, int64_t n, uint8_t *codes);

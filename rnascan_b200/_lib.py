@@ -41,6 +41,10 @@ _SIGS = {
     "rs_prof_end": ([_vp, _int, _vp], _int),
     "rs_host_fasta_index": ([_vp, _i64, _vp, _vp, _vp], _int),
     "rs_host_fasta_fill": ([_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp], _int),
+    "rs_host_profiles_open": ([_vp, _i64, _int, _vp, _vp], _int),
+    "rs_host_profiles_fill": ([_vp, _int, _vp, _vp, _vp], _int),
+    "rs_host_profiles_close": ([_vp], _int),
+    "rs_host_parse_doubles": ([ctypes.c_char_p, _i64, _vp, _i64, _vp, _vp], _int),
     "rs_host_encode_rna": ([_vp, _i64, _vp], _int),
     "rs_host_encode_struct": ([_vp, _i64, _vp], _int),
     "rs_host_log_odds": ([_vp, _vp, _int, _int, _vp], _int),

@@ -448,6 +448,48 @@ def _read_profile(struct_file):
     return np.ascontiguousarray(table[list(device.CHANNELS)].to_numpy(dtype=np.float64))
 
 
+def _read_profiles_packed(files, threads=None):
+    """All profiles of `files` as ONE packed (sum L + len(files), 7) float64 array in B,E,H,L,M,R,T order
+    (a zero separator row after each profile, the layout device.ProfileStream uploads) plus their lengths.
+    Plain files are read and converted natively on host threads (rs_host_profiles_*: pandas' own number
+    conversion restated, bit-identical rows); anything else goes through `_read_profile` (pandas)."""
+    import ctypes
+    from . import _lib
+    n = len(files)
+    lengths = np.zeros(n, np.int64)
+    if n == 0:
+        return np.zeros((0, 7), np.float64), lengths
+    threads = int(threads or min(32, os.cpu_count() or 1))
+    arr = (ctypes.c_char_p * n)(*[os.fsencode(f) for f in files])
+    handle = ctypes.c_void_p()
+    rows = np.zeros(n, np.int64)
+    _lib.check(_lib.lib.rs_host_profiles_open(ctypes.cast(arr, ctypes.c_void_p), n, threads, ctypes.byref(handle),
+                                              rows.ctypes.data))
+    try:
+        fallback = {k: _read_profile(files[k]) for k in np.nonzero(rows < 0)[0].tolist()}
+        for k, prof in fallback.items():
+            rows[k] = prof.shape[0]
+        offsets = np.zeros(n, np.int64)
+        if n > 1:
+            np.cumsum(rows[:-1] + 1, out=offsets[1:])
+        packed = np.zeros((int(rows.sum()) + n, 7), np.float64)
+        status = np.zeros(n, np.int32)
+        _lib.check(_lib.lib.rs_host_profiles_fill(handle, threads, packed.ctypes.data, offsets.ctypes.data,
+                                                  status.ctypes.data))
+    finally:
+        _lib.lib.rs_host_profiles_close(handle)
+    for k in range(n):
+        if k in fallback:
+            packed[offsets[k]:offsets[k] + rows[k]] = fallback[k]
+        elif status[k] != 0:                  # a field pandas must judge: re-read this one file with pandas
+            prof = _read_profile(files[k])
+            if prof.shape[0] != rows[k]:
+                raise ValueError("%s: pandas sees %d rows, the native reader %d" % (files[k], prof.shape[0], rows[k]))
+            packed[offsets[k]:offsets[k] + rows[k]] = prof
+    lengths[:] = rows
+    return packed, lengths
+
+
 def _averaged_frame(motif_id, starts, width, scores):
     """Frame built the way pd.DataFrame(list of Series) builds it in the reference
     (rnascan.py:311-315): object columns; no columns at all when there is no hit."""
@@ -804,12 +846,12 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     for path in files:
         match = re.search(r"^structure\.(.*)\.txt$", os.path.basename(path))
         names.append(path if debug else match.group(1))
-    profiles = [_read_profile(path) for path in files]
-    lengths = np.array([p.shape[0] for p in profiles], dtype=np.int64)
-    offsets = np.zeros(len(profiles), np.int64)
-    if len(profiles) > 1:
+    packed, lengths = _read_profiles_packed(files)
+    n_prof = len(files)
+    offsets = np.zeros(n_prof, np.int64)
+    if n_prof > 1:
         np.cumsum(lengths[:-1] + 1, out=offsets[1:])
-    codes = np.zeros(int(lengths.sum() + len(profiles)), np.uint8)
+    codes = np.zeros(int(lengths.sum() + n_prof), np.uint8)
     seq_table = None
     if seq_batches is not None:
         # sequence symbols of the record with the same id, aligned row by row; rows beyond the
@@ -827,11 +869,11 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
                 sym = device.pack_texts([text], "rna")[0][:-1]
                 m = min(len(sym), len(seg))
                 seg[:m] = sym[:m]
-    if len(profiles):
+    if n_prof:
         codes[offsets + lengths] = device._lib.RS_SEP
     if len(codes):
         stream = device.SymbolStream(codes, offsets, lengths)
-        profile = device.ProfileStream(device.pack_profiles(profiles, dtype=np.float64))
+        profile = device.ProfileStream(packed)
         pos, seq_scores, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
         rec, start0 = stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
     else:

@@ -521,3 +521,132 @@ def test_native_fasta_ingest_equals_the_python_parser(tmp_path):
             got_desc = [blob[a:b] for a, b in zip(toff[:-1].tolist(), toff[1:].tolist())]
             assert got_desc == descs
             assert [(d.split(None, 1) or [""])[0] for d in got_desc] == ids
+
+
+# ----------------------------------------------------------------------------- native profile ingest
+def _pandas_column(tokens):
+    """What pandas.read_csv makes of the tokens as ONE tab-separated float column (its default converter)."""
+    import io
+    import pandas as pd
+    return pd.read_csv(io.StringIO("x\n" + "\n".join(tokens) + "\n"), sep="\t", dtype={"x": np.float64})["x"].to_numpy()
+
+
+def test_native_number_conversion_equals_pandas_default_converter():
+    """rs_host_parse_doubles restates pandas' precise_xstrtod (not correctly rounded!): bit-identical to
+    pd.read_csv on profile-like values, random doubles of every magnitude and over-long digit strings."""
+    import random
+    from rnascan_b200 import _lib
+    rng = np.random.default_rng(20261018)
+    vals = []
+    counts = rng.integers(0, 21, size=(60_000, 7)).astype(float)
+    counts /= np.maximum(counts.sum(1, keepdims=True), 1)               # what run_folding writes: normalised counts
+    vals += counts.ravel().tolist()
+    vals += rng.random(150_000).tolist()
+    vals += (10.0 ** rng.uniform(-320, 308, 100_000)).tolist()
+    vals += (-(10.0 ** rng.uniform(-30, 30, 20_000))).tolist()
+    vals += [0.0, -0.0, 1.0, 1e-5, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 0.1, 0.2, 0.3, 1 / 3]
+    tokens = [repr(v) for v in vals]
+    rnd = random.Random(7)
+    for _ in range(60_000):
+        tokens.append("0." + "".join(rnd.choice("0123456789") for _ in range(rnd.randint(1, 25))))
+    for _ in range(30_000):
+        tokens.append("".join(rnd.choice("0123456789") for _ in range(rnd.randint(1, 15))) + "." +
+                      "".join(rnd.choice("0123456789") for _ in range(rnd.randint(0, 9))))
+    tokens += ["1e5", "1E-3", "+.5", "5.", "-12.50e+2", "007", "123456789012345", ".000000000000000000001", "1e-400", "3e-700"]
+    want = _pandas_column(tokens)
+    text = "\n".join(tokens).encode()
+    got = np.zeros(len(tokens), np.float64)
+    ok = np.zeros(len(tokens), np.uint8)
+    n_out = np.zeros(1, np.int64)
+    _lib.check(_lib.lib.rs_host_parse_doubles(text, len(text), got.ctypes.data, len(got), n_out.ctypes.data,
+                                              ok.ctypes.data))
+    assert int(n_out[0]) == len(tokens) and ok.all()
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # the converter is genuinely pandas', not strtod: a large share of these tokens convert differently
+    exact = np.array([float(t) for t in tokens])
+    assert (got.view(np.uint64) != exact.view(np.uint64)).mean() > 0.2
+    # tokens the native converter must decline (pandas decides what they are)
+    bad = ["", "-", "e5", "1e", "nan", "inf", "1,5", " 1.0", "1.0 ", "0x10", "1e999999", "1234567890123456", "1e400", "--1"]
+    text = "\n".join(bad).encode()
+    ok = np.ones(len(bad), np.uint8)
+    got = np.zeros(len(bad), np.float64)
+    _lib.check(_lib.lib.rs_host_parse_doubles(text, len(text), got.ctypes.data, len(got), n_out.ctypes.data,
+                                              ok.ctypes.data))
+    assert int(n_out[0]) == len(bad) and not ok.any()
+
+
+def test_native_profile_reader_equals_pandas(tmp_path):
+    """rs_host_profiles_* (through rnascan._read_profiles_packed) == pd.read_csv per file (rnascan._read_profile),
+    bit for bit, on plain files, permuted/extra columns, CRLF / CR line ends, blank lines, no final newline;
+    hostile files (quotes, NaN words, ragged rows, duplicate columns, blanks) fall back to pandas."""
+    from rnascan_b200 import pfmutil, rnascan
+    rng = np.random.default_rng(5)
+    files, kinds = [], []
+
+    def write(name, text, kind, binary=False):
+        path = str(tmp_path / ("structure.%s.txt" % name))
+        with open(path, "wb") as fh:
+            fh.write(text if binary else text.encode())
+        files.append(path)
+        kinds.append(kind)
+
+    def table(L, order="BEHLMRT", extra=None, eol="\n", final_eol=True, blank_every=0):
+        rows = rng.integers(0, 30, size=(L, 7)).astype(float)
+        rows /= np.maximum(rows.sum(1, keepdims=True), 1)
+        cols = ["PO"] + list(order) + ([extra] if extra else [])
+        lines = ["\t".join(cols)]
+        for i in range(L):
+            vals = {c: repr(float(rows[i, "BEHLMRT".index(c)])) for c in "BEHLMRT"}
+            f = [str(i)] + [vals[c] for c in order] + (["7"] if extra else [])
+            lines.append("\t".join(f))
+            if blank_every and i % blank_every == 0:
+                lines.append("")
+        return eol.join(lines) + (eol if final_eol else "")
+
+    for k in range(6):                                            # what pfmutil.write_pfm produces
+        rows = rng.random((int(rng.integers(1, 400)), 7))
+        pfm = {c: [float(v) for v in rows[:, j]] for j, c in enumerate("BEHLMRT")}
+        path = str(tmp_path / ("structure.w%d.txt" % k))
+        pfmutil.write_pfm(pfm, path)
+        files.append(path); kinds.append("native")
+    write("perm", table(50, order="TRMLHEB"), "native")
+    write("extra", table(40, extra="Z"), "native")
+    write("crlf", table(30, eol="\r\n"), "native")
+    write("cr", table(30, eol="\r"), "native")
+    write("noeol", table(20, final_eol=False), "native")
+    write("blank", "\n\n" + table(25, blank_every=4), "native")
+    write("ints", "PO\tB\tE\tH\tL\tM\tR\tT\n0\t1\t0\t0\t0\t0\t0\t0\n1\t0\t0\t1\t0\t0\t0\t0\n", "native")
+    write("exp", "PO\tB\tE\tH\tL\tM\tR\tT\n0\t1e-05\t2.5E-3\t0.1\t0.2\t0.3\t.25\t5.\n", "native")
+    write("quoted", 'PO\tB\tE\tH\tL\tM\tR\tT\n0\t"0.25"\t0.2\t0.3\t0.1\t0.1\t0.05\t0.0\n1\t0.5\t0.5\t0\t0\t0\t0\t0\n', "pandas")
+    write("nanword", "PO\tB\tE\tH\tL\tM\tR\tT\n0\tnan\t0.2\t0.3\t0.1\t0.1\t0.05\t0.0\n1\t0.5\tNA\t0\t0\t0\t0\tinf\n", "pandas")
+    write("missing", "PO\tB\tE\tH\tL\tM\tR\tT\n0\t0.1\t\t0.3\t0.1\t0.1\t0.1\t0.3\n", "pandas")
+    write("short", "PO\tB\tE\tH\tL\tM\tR\tT\n0\t0.1\t0.2\t0.3\t0.1\t0.1\t0.1\n", "pandas")
+    write("spaces", "PO\tB\tE\tH\tL\tM\tR\tT\n0\t 0.1\t0.2 \t0.3\t0.1\t0.1\t0.1\t0.1\n", "pandas")
+    write("bigint", "PO\tB\tE\tH\tL\tM\tR\tT\n0\t12345678901234567\t0\t0\t0\t0\t0\t0\n", "pandas")
+    packed, lengths = rnascan._read_profiles_packed(files, threads=4)
+    off = 0
+    for path, L in zip(files, lengths.tolist()):
+        want = rnascan._read_profile(path)
+        assert want.shape == (L, 7), path
+        got = packed[off:off + L]
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan), path
+        assert np.array_equal(got[~nan].view(np.uint64), want[~nan].view(np.uint64)), path
+        assert not packed[off + L].any()                           # separator row
+        off += L + 1
+    assert off == packed.shape[0]
+    # which files the native reader really took (the others went through pandas)
+    import ctypes
+    from rnascan_b200 import _lib
+    arr = (ctypes.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+    handle = ctypes.c_void_p()
+    rows = np.zeros(len(files), np.int64)
+    _lib.check(_lib.lib.rs_host_profiles_open(ctypes.cast(arr, ctypes.c_void_p), len(files), 2, ctypes.byref(handle),
+                                              rows.ctypes.data))
+    offs = np.concatenate([[0], np.cumsum(np.maximum(rows, 0)[:-1] + 1)]).astype(np.int64)
+    out = np.zeros((int(np.maximum(rows, 0).sum()) + len(files), 7))
+    status = np.zeros(len(files), np.int32)
+    _lib.check(_lib.lib.rs_host_profiles_fill(handle, 2, out.ctypes.data, offs.ctypes.data, status.ctypes.data))
+    _lib.lib.rs_host_profiles_close(handle)
+    took = [(r >= 0 and s == 0) for r, s in zip(rows.tolist(), status.tolist())]
+    assert took == [k == "native" for k in kinds], list(zip(files, took, kinds))
