@@ -12,8 +12,15 @@
 //     blanks removed;
 //   * RNA target alphabet: T->U, t->u, then ASCII upper-casing; structure alphabet: unchanged.
 // The caller guarantees ASCII input (rnascan.py falls back to its Python parser otherwise).
+//
+// Both passes run on host threads: the buffer is cut at record starts ('>' at the beginning of a line)
+// into one chunk per thread, the chunks are counted independently, and a prefix sum over the counts
+// gives every chunk its place in the outputs.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 #include "../../include/rnascan_b200.h"
 
 namespace {
@@ -68,6 +75,65 @@ void walk(const uint8_t *buf, int64_t n, OnRecord on_record, OnSymbols on_symbol
     }
 }
 
+struct Chunk {
+    int64_t begin, end;                  // byte range; every chunk but the first starts at a record's '>'
+    int64_t recs, syms, title_bytes;     // counts of the chunk
+};
+
+// first record start at or after `from`: a '>' that begins a line
+int64_t next_record_start(const uint8_t *buf, int64_t n, int64_t from)
+{
+    for (int64_t i = from; i < n; i++)
+        if (buf[i] == '>' && (i == 0 || buf[i - 1] == '\n' || buf[i - 1] == '\r')) return i;
+    return n;
+}
+
+std::vector<Chunk> make_chunks(const uint8_t *buf, int64_t n)
+{
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("RNASCAN_HOST_THREADS")) threads = atoi(e);
+    if (threads < 1) threads = 1;
+    if (threads > 32) threads = 32;
+    int64_t min_chunk = 4 << 20;                                     // below this a thread is not worth starting
+    if (const char *e = getenv("RNASCAN_FASTA_MIN_CHUNK")) min_chunk = atoll(e) > 0 ? atoll(e) : min_chunk;   // tests
+    int64_t parts = n / min_chunk;
+    if (parts > threads) parts = threads;
+    if (parts < 1) parts = 1;
+    std::vector<Chunk> chunks;
+    int64_t begin = 0;
+    for (int64_t k = 1; k <= parts && begin < n; k++) {
+        int64_t end = k == parts ? n : next_record_start(buf, n, n / parts * k);
+        if (end <= begin) continue;
+        chunks.push_back(Chunk{begin, end, 0, 0, 0});
+        begin = end;
+    }
+    if (chunks.empty()) chunks.push_back(Chunk{0, n, 0, 0, 0});
+    return chunks;
+}
+
+template <typename F>
+void run_chunks(std::vector<Chunk> &chunks, F fn)
+{
+    if (chunks.size() == 1) { fn(0); return; }
+    std::vector<std::thread> pool;
+    for (size_t k = 0; k < chunks.size(); k++) pool.emplace_back(fn, k);
+    for (auto &t : pool) t.join();
+}
+
+// A chunk that starts at a record start is a FASTA text of its own; the first chunk keeps the file's
+// leading junk, which walk() skips.
+void count_chunks(const uint8_t *buf, std::vector<Chunk> &chunks)
+{
+    run_chunks(chunks, [&](size_t k) {
+        Chunk &c = chunks[k];
+        int64_t recs = 0, syms = 0, tb = 0;
+        const uint8_t *b = buf + c.begin;
+        walk(b, c.end - c.begin, [&](int64_t a, int64_t e) { recs++; tb += e - a; },
+             [&](int64_t a, int64_t e) { for (int64_t i = a; i < e; i++) syms += b[i] != ' '; });
+        c.recs = recs; c.syms = syms; c.title_bytes = tb;
+    });
+}
+
 }  // namespace
 
 // Pass 1: number of records, symbols (sequence letters after blank removal) and title bytes.
@@ -76,8 +142,9 @@ extern "C" int rs_host_fasta_index(const uint8_t *buf, int64_t n, int64_t *n_rec
 {
     if (n < 0 || (n > 0 && !buf) || !n_records || !n_symbols || !title_bytes) return RS_ERR_INVALID;
     int64_t recs = 0, syms = 0, tb = 0;
-    walk(buf, n, [&](int64_t a, int64_t b) { recs++; tb += b - a; },
-         [&](int64_t a, int64_t b) { for (int64_t k = a; k < b; k++) syms += buf[k] != ' '; });
+    std::vector<Chunk> chunks = make_chunks(buf, n);
+    count_chunks(buf, chunks);
+    for (const Chunk &c : chunks) { recs += c.recs; syms += c.syms; tb += c.title_bytes; }
     *n_records = recs; *n_symbols = syms; *title_bytes = tb;
     return RS_OK;
 }
@@ -94,35 +161,48 @@ extern "C" int rs_host_fasta_fill(const uint8_t *buf, int64_t n, int kind, uint8
         return RS_ERR_INVALID;
     const uint8_t *tl = kind == 0 ? g.rna_text : nullptr;
     const uint8_t *cl = kind == 0 ? g.rna_code : g.ss_code;
-    int64_t r = -1, w = 0, tw = 0;
-    auto close_record = [&]() {
-        if (r >= 0) {
-            rec_len[r] = w - rec_off[r];
-            text[w] = '\n';
-            if (codes) codes[w] = RS_SEP;
-            w++;
-        }
-    };
+    std::vector<Chunk> chunks = make_chunks(buf, n);
+    count_chunks(buf, chunks);
+    // where each chunk writes: records, symbols (+1 separator per record), title bytes before it
+    std::vector<int64_t> r0(chunks.size()), w0(chunks.size()), t0(chunks.size());
+    int64_t racc = 0, wacc = 0, tacc = 0;
+    for (size_t k = 0; k < chunks.size(); k++) {
+        r0[k] = racc; w0[k] = wacc; t0[k] = tacc;
+        racc += chunks[k].recs; wacc += chunks[k].syms + chunks[k].recs; tacc += chunks[k].title_bytes;
+    }
     title_off[0] = 0;
-    walk(buf, n,
-         [&](int64_t a, int64_t b) {
-             close_record();
-             r++;
-             rec_off[r] = w;
-             if (titles && b > a) memcpy(titles + tw, buf + a, (size_t)(b - a));
-             tw += b - a;
-             title_off[r + 1] = tw;
-         },
-         [&](int64_t a, int64_t b) {
-             for (int64_t k = a; k < b; k++) {
-                 const uint8_t c = buf[k];
-                 if (c == ' ') continue;
-                 const uint8_t t = tl ? tl[c] : c;
-                 text[w] = t;
-                 if (codes) codes[w] = cl[t];
-                 w++;
-             }
-         });
-    close_record();
+    run_chunks(chunks, [&](size_t k) {
+        const uint8_t *b = buf + chunks[k].begin;
+        int64_t r = r0[k] - 1, w = w0[k], tw = t0[k];
+        const int64_t first = r0[k];
+        auto close_record = [&]() {
+            if (r >= first) {
+                rec_len[r] = w - rec_off[r];
+                text[w] = '\n';
+                if (codes) codes[w] = RS_SEP;
+                w++;
+            }
+        };
+        walk(b, chunks[k].end - chunks[k].begin,
+             [&](int64_t a, int64_t e) {
+                 close_record();
+                 r++;
+                 rec_off[r] = w;
+                 if (titles && e > a) memcpy(titles + tw, b + a, (size_t)(e - a));
+                 tw += e - a;
+                 title_off[r + 1] = tw;
+             },
+             [&](int64_t a, int64_t e) {
+                 for (int64_t i = a; i < e; i++) {
+                     const uint8_t c = b[i];
+                     if (c == ' ') continue;
+                     const uint8_t t = tl ? tl[c] : c;
+                     text[w] = t;
+                     if (codes) codes[w] = cl[t];
+                     w++;
+                 }
+             });
+        close_record();
+    });
     return RS_OK;
 }

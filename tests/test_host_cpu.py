@@ -460,10 +460,15 @@ def test_native_writer_text_equals_pandas_to_csv():
 
 
 # ----------------------------------------------------------------------------- native FASTA ingest
-def test_native_fasta_ingest_equals_the_python_parser(tmp_path):
+@pytest.mark.parametrize("min_chunk", [None, "48"], ids=["one-chunk", "many-chunks"])
+def test_native_fasta_ingest_equals_the_python_parser(tmp_path, monkeypatch, min_chunk):
     """rs_host_fasta_index/_fill vs the Biopython-semantics Python parser (seq.iter_fasta + preprocess_seq +
     pack_texts) on hostile FASTA text: CRLF / lone CR, blank lines, leading junk, blanks inside lines,
-    lower case, T/U, ambiguity codes, empty records, empty titles, no trailing newline, gzip."""
+    lower case, T/U, ambiguity codes, empty records, empty titles, no trailing newline, gzip.
+    "many-chunks": the buffer is cut into up to 8 pieces at record starts and parsed on threads."""
+    if min_chunk:
+        monkeypatch.setenv("RNASCAN_FASTA_MIN_CHUNK", min_chunk)
+        monkeypatch.setenv("RNASCAN_HOST_THREADS", "8")
     import gzip
     import random
     from rnascan_b200 import rnascan as ms, device
