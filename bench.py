@@ -48,6 +48,19 @@ def env_int(name, default):
         return default
 
 
+def recorded_traffic(workload, n_symbols):
+    """DRAM bytes per launch of the workload's dominant kernel from the committed ncu capture
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic), for the same shard size; else None."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
+            rec = json.load(fh)[workload]
+        if abs(rec["symbols_per_gpu"] - n_symbols) <= 0.001 * n_symbols:
+            return rec["traffic"], rec["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     try:
@@ -570,7 +583,8 @@ def measure(args, wl, steps, ctx, full=True):
                                                "c5": "fused_filter_kernel<W> x %d motifs" % N_MOTIFS_C5}[wl],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],
-                     "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step, "traffic": None},
+                     "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step,
+                     "traffic": recorded_traffic(wl, n)[0], "traffic_source": recorded_traffic(wl, n)[1]},
         "clocks": clocks,
     }
     if hits is not None:
@@ -594,7 +608,8 @@ def measure(args, wl, steps, ctx, full=True):
             out["roofline"] = {"bound": "tensor", "kernel": "batched_tc_kernel", "achieved": tf, "peak": tpeak,
                                "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": src,
                                "flop_per_position": 2.0 * 96 * 256, "kernel_ms": kernel_ms,
-                               "kernel_share_of_step": kernel_ms / ms_step, "traffic": None,
+                               "kernel_share_of_step": kernel_ms / ms_step, "traffic": recorded_traffic(wl, n)[0],
+                               "traffic_source": recorded_traffic(wl, n)[1],
                                "hbm_GBps_algorithmic": 29.0 * positions / (kernel_ms * 1e-3) / 1e9}
         else:
             out["roofline"]["note"] = ("CUDA-core path re-reads the streams once per motif: physical traffic is %d x "

@@ -21,6 +21,13 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_membar_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
+# python tools/ncu_summary.py <rep> [<launches.csv>] [--traffic <json> <workload> <symbols>]: also records the kernel's
+# DRAM bytes per launch in <json> (bench.py reports them as roofline.traffic for the same workload size)
+traffic_args = None
+if "--traffic" in sys.argv:
+    k = sys.argv.index("--traffic")
+    traffic_args = sys.argv[k + 1:k + 4]
+    del sys.argv[k:k + 4]
 rep = sys.argv[1]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -37,6 +44,18 @@ for r in rows[2:]:
         if k not in KEYS and r[H.index(k)] not in ('', '0', 'n/a') and not any(x in k for x in ('.min', '.max', '.sum', 'ops_path', 'attribute')):
             print("| %s | %s | %s |" % (k, r[H.index(k)], U[H.index(k)]))
     print()
+if traffic_args:
+    import json, os
+    def gb(v, unit):
+        return float(v.replace(',', '')) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[unit]
+    r = rows[2]
+    rd = gb(r[H.index('dram__bytes_read.sum')], U[H.index('dram__bytes_read.sum')])
+    wr = gb(r[H.index('dram__bytes_write.sum')], U[H.index('dram__bytes_write.sum')])
+    path, wl, nsym = traffic_args
+    db = json.load(open(path)) if os.path.exists(path) else {}
+    db[wl] = {"kernel": r[H.index('Kernel Name')], "symbols_per_gpu": int(nsym), "dram_bytes_read": rd,
+              "dram_bytes_write": wr, "traffic": rd + wr, "source": rep.split('/')[-1] + " (ncu --set full, one launch)"}
+    json.dump(db, open(path, "w"), indent=1, sort_keys=True)
 if len(sys.argv) > 2:
     rows = list(csv.reader(open(sys.argv[2])))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
