@@ -68,6 +68,11 @@ int         rs_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int64_t     rs_padded_count(int64_t n);                /* elements/rows to allocate     */
 int64_t     rs_scan_workspace_bytes(int64_t n, int64_t hit_capacity);
 
+/* SMs the persistent scan kernels leave unoccupied (default 0).  Set it to 1 while a collective runs
+ * beside a scan (the all-reduce of the background counts in sharded runs): a persistent kernel that fills
+ * every SM's shared memory would otherwise make the collective's kernel wait for the scan to end.      */
+int rs_set_reserved_sms(int n);
+
 /* ---- measurement hook (bench.py; no reference counterpart) --------------------------
  * Between rs_prof_begin and rs_prof_end every scan entry point records a CUDA event pair
  * tightly around its main kernel on the caller's stream (at most max_records pairs);

@@ -37,6 +37,7 @@ _SIGS = {
     "rs_device_info": ([_vp, _vp, _vp], _int),
     "rs_padded_count": ([_i64], _i64),
     "rs_scan_workspace_bytes": ([_i64, _i64], _i64),
+    "rs_set_reserved_sms": ([_int], _int),
     "rs_prof_begin": ([_int], _int),
     "rs_prof_end": ([_vp, _int, _vp], _int),
     "rs_host_fasta_index": ([_vp, _i64, _vp, _vp, _vp], _int),

@@ -41,6 +41,22 @@ int rs_sm_count()
     return cached;
 }
 
+// SMs the persistent scan kernels leave free (rs_set_reserved_sms): a collective that runs BESIDE a scan
+// (the all-reduce of the background counts, device.BackgroundFusedScan) needs somewhere to be scheduled --
+// a persistent kernel that fills every SM's shared memory would make it wait for the scan to end.
+static int g_reserved_sms = 0;
+extern "C" int rs_set_reserved_sms(int n)
+{
+    if (n < 0 || n > 64) { rs_set_error("rs_set_reserved_sms: 0..64"); return RS_ERR_INVALID; }
+    g_reserved_sms = n;
+    return RS_OK;
+}
+int rs_grid_sms()
+{
+    const int sms = rs_sm_count() - g_reserved_sms;
+    return sms > 1 ? sms : 1;
+}
+
 // --------------------------------------------------------------------------- profiling hook
 // A ring of CUDA event pairs recorded tightly around the main scan kernel of each entry
 // point, on the caller's stream, so bench.py can report that kernel's own duration inside

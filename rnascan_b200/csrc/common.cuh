@@ -20,6 +20,7 @@ int  rs_cuda_fail(cudaError_t e, const char *what);
 
 static inline int64_t rs_roundup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 int rs_sm_count();               // SMs of the current device (cached)
+int rs_grid_sms();               // SMs the persistent scan kernels may fill (rs_set_reserved_sms)
 #define RS_MAX_DEVICES 64
 int rs_current_device();         // cudaGetDevice clamped to [0, RS_MAX_DEVICES)
 void rs_prof_start(cudaStream_t s);   // profiling hook (capi.cu): event pair around the main kernel

@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_scan_kernel(const __grid_cons
 template <int A, int W>
 static int launch_mask_scan(const MaskScanParams &prm, cudaStream_t stream)
 {
-    int64_t grid = (int64_t)rs_sm_count() * (prm.codes_b ? 4 : 6);
+    int64_t grid = (int64_t)rs_grid_sms() * (prm.codes_b ? 4 : 6);
     if (grid > prm.n_tiles) grid = prm.n_tiles;
     rs_prof_start(stream);
     if (A == 4 && prm.codes_b) mask_scan_kernel<4, W, true><<<(unsigned)grid, MS_THREADS, 0, stream>>>(prm);
@@ -573,7 +573,7 @@ static int launch_kmer(const KmerParams &prm, cudaStream_t stream)
         RS_CUDA(cudaFuncSetAttribute(kmer_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    int64_t grid = (int64_t)rs_sm_count() * 2;
+    int64_t grid = (int64_t)rs_grid_sms() * 2;
     if (grid > prm.n_tiles) grid = prm.n_tiles;
     rs_prof_start(stream);
     kmer_scan_kernel<W><<<(unsigned)grid, KM_THREADS, smem, stream>>>(prm);

@@ -350,7 +350,7 @@ static int launch_filter(const ProfileParams &prm, cudaStream_t stream)
         RS_CUDA(cudaFuncSetAttribute(fused_filter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    int64_t grid = (int64_t)rs_sm_count() * 2;
+    int64_t grid = (int64_t)rs_grid_sms() * 2;
     if (grid > prm.n_tiles) grid = prm.n_tiles;
     rs_prof_start(stream);
     fused_filter_kernel<W><<<(unsigned)grid, FT_THREADS, smem, stream>>>(prm);
@@ -388,7 +388,7 @@ static int launch_exact(const ProfileParams &prm, cudaStream_t stream)
         RS_CUDA(cudaFuncSetAttribute(profile_exact_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    int64_t grid = (int64_t)rs_sm_count() * (sizeof(PT) == 4 ? 3 : 1);
+    int64_t grid = (int64_t)rs_grid_sms() * (sizeof(PT) == 4 ? 3 : 1);
     if (grid > prm.n_tiles) grid = prm.n_tiles;
     rs_prof_start(stream);
     profile_exact_kernel<PT><<<(unsigned)grid, EX_THREADS, smem, stream>>>(prm);
