@@ -655,3 +655,26 @@ def test_native_profile_reader_equals_pandas(tmp_path):
     _lib.lib.rs_host_profiles_close(handle)
     took = [(r >= 0 and s == 0) for r, s in zip(rows.tolist(), status.tolist())]
     assert took == [k == "native" for k in kinds], list(zip(files, took, kinds))
+
+
+def test_background_shift_bounds_the_score_difference_between_two_backgrounds():
+    """device._background_shift: W x it bounds |score(b_local) - score(b_global)| for every window (the slack the
+    sharded one-hot scan verifies before trusting a decision pass started from the shard's own counts)."""
+    import math
+    from rnascan_b200 import device
+    rng = np.random.default_rng(11)
+    for A in (4, 7):
+        for _ in range(50):
+            local = np.zeros(8, np.int64); glob = np.zeros(8, np.int64)
+            local[:A] = rng.integers(0, 10_000, A)
+            glob[:A] = local[:A] + rng.integers(0, 50_000, A)
+            shift = device._background_shift(local, glob, A)
+            def bg(c):
+                b = [(float(c[k]) + 1) / (float(sum(int(v) for v in c[:A])) + A) for k in range(A)]
+                t = sum(b)
+                return [v / t for v in b]
+            bl, bgl = bg(local), bg(glob)
+            worst = max(abs(math.log2(bl[k]) - math.log2(bgl[k])) for k in range(A))
+            assert worst <= shift <= worst * 1.001 + 1e-9
+    same = np.array([5, 6, 7, 8, 0, 0, 0, 0], np.int64)
+    assert device._background_shift(same, same, 4) < 1e-9
