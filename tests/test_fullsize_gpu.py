@@ -160,3 +160,36 @@ def test_batched_paths_agree_full_size(env):
     motif, pos = a[0], a[1]
     key = motif.astype(np.int64) * (1 << 40) + pos
     assert np.all(np.diff(key) > 0)                 # grouped by motif, sorted by position
+
+
+@pytest.mark.parametrize("wl,kind,A,W,thr", [("c2", "rna", 4, 7, 6.0), ("c3", "struct", 7, 7, 7.5), ("c2", "rna", 4, 12, 5.0)])
+def test_look_back_kernels_beyond_one_resident_wave(wl, kind, A, W, thr):
+    """300 M symbols: the single-pass finish kernel runs 327 CTAs of 1024 threads (148 fit on the device at once), so
+    its ticket + look-back chain is exercised with CTAs that start only after earlier ones have retired.
+    Thresholded scan == thresholding the dense scores of a different kernel: same positions, same scores, sorted."""
+    import bench
+    from rnascan_b200 import device as dev, synth
+    device = torch.device("cuda", 0)
+    torch.cuda.empty_cache()
+    shard = bench.make_device_shard(300_000_000, 77, wl, device)
+
+    class Stream(object):
+        pass
+    st = Stream()
+    st.codes, st.n, st.kind = shard["codes"], shard["n"], kind
+    st.offsets, st.lengths = shard["offsets"], shard["lengths"]
+    tab = synth.pssm_table(synth.pfm_rows(W, A, np.random.default_rng(5 + W)))
+    if A == 4:
+        pos, sc = dev.scan_seq(st, tab, thr, capacity=st.n // 64)
+        dense = dev.dense_seq(st, tab)
+        want = torch.nonzero(dense.double() > thr).flatten()
+    else:
+        pos, sc = dev.scan_struct_onehot(st, tab, thr, capacity=st.n // 64)
+        dense = dev.dense_struct(st, tab)
+        want = torch.nonzero(dense > thr).flatten()
+    assert len(pos) > 100_000
+    assert torch.equal(torch.from_numpy(pos).to(device), want)
+    assert torch.equal(torch.from_numpy(sc).to(device), dense[want])
+    assert np.all(np.diff(pos) > 0)
+    del shard, dense, want
+    torch.cuda.empty_cache()
