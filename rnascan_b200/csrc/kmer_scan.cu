@@ -229,13 +229,13 @@ __device__ __forceinline__ unsigned long long fin_block_scan(unsigned long long 
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long x = s_w[lane], xi = x;
+        unsigned long long x = lane < FIN_THREADS / 32 ? s_w[lane] : 0ull, xi = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, xi, d);
             if (lane >= d) xi += t;
         }
-        s_w[lane] = xi - x;
+        if (lane < FIN_THREADS / 32) s_w[lane] = xi - x;
         if (lane == 31) s_total = xi;
     }
     __syncthreads();

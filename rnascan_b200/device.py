@@ -394,11 +394,13 @@ class BackgroundFusedScan(object):
         # all) is spent while the device is already busy
         tiles = ctypes.c_int64(0)
         check(lib.rs_set_reserved_sms(1 if all_reduce is not None else 0))    # room for the collective's kernel
-        check(lib.rs_scan_fused_candidates(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,
-                                           float(threshold), float(absrow_max), hb.capacity,
-                                           _ptr(hb.cand_counters), _ptr(hb.work), hb.work_bytes,
-                                           ctypes.addressof(tiles), main.cuda_stream))
-        check(lib.rs_set_reserved_sms(0))
+        try:
+            check(lib.rs_scan_fused_candidates(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,
+                                               float(threshold), float(absrow_max), hb.capacity,
+                                               _ptr(hb.cand_counters), _ptr(hb.work), hb.work_bytes,
+                                               ctypes.addressof(tiles), main.cuda_stream))
+        finally:
+            lib.rs_set_reserved_sms(0)
         with torch.cuda.stream(self.side):
             self.counts.zero_()
             check(lib.rs_hist_rna(_ptr(codes), n, _ptr(self.counts), self.side.cuda_stream))
@@ -508,9 +510,11 @@ class BackgroundOneHotScan(object):
         sharded = all_reduce is not None
         slack = float(extra_margin) + (float(shard_margin) if sharded else 0.0)
         check(lib.rs_set_reserved_sms(1 if sharded else 0))                   # room for the collective's kernel
-        check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.counts), prob.ctypes.data, W, float(threshold),
-                                       slack, hb.capacity, _ptr(hb.work), hb.work_bytes, main.cuda_stream))
-        check(lib.rs_set_reserved_sms(0))
+        try:
+            check(lib.rs_scan_onehot_begin(A, _ptr(codes), n, _ptr(self.counts), prob.ctypes.data, W, float(threshold),
+                                           slack, hb.capacity, _ptr(hb.work), hb.work_bytes, main.cuda_stream))
+        finally:
+            lib.rs_set_reserved_sms(0)
         with torch.cuda.stream(self.side):                  # counts -> (all ranks) -> host, beside the scan
             self.side.wait_event(self.counted)
             self.counts_host[8:].copy_(self.counts, non_blocking=True)          # local
