@@ -29,10 +29,10 @@
 #include "common.cuh"
 #include "provisional.cuh"
 
-#define KM_CONSUMERS   256                         // consumer threads (8 warps)
+#define KM_CONSUMERS   512                         // consumer threads (16 warps share one table; 2 CTAs per SM)
 #define KM_THREADS     (KM_CONSUMERS + 32)         // + one producer warp
 #define KM_P           28                          // positions per thread
-#define KM_TILE        (KM_CONSUMERS * KM_P)       // 7168 = 28 * 256
+#define KM_TILE        (KM_CONSUMERS * KM_P)       // 14336 = 28 * 512
 #define KM_STAGES      3
 #define KM_STAGE_BYTES (KM_TILE + 16)              // +8 symbols of halo, rounded to 16
 #define KM_LUT_BYTES   65536
