@@ -297,12 +297,16 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
     if (prm.capacity <= 0) return;
     // Expansion.  A lane owns one segment: its 32 mask words (128 contiguous bytes) are fetched with eight
     // independent 16-byte loads.  Hits are sparse across (lane, word), so instead of scoring them where
-    // they are found (a few active lanes per pass) every lane pushes (output index, position) into a
-    // per-warp queue and the warp scores queue entries 32 at a time with all lanes busy.
-    __shared__ unsigned long long q_k[FIN_THREADS / 32][64];
-    __shared__ long long q_pos[FIN_THREADS / 32][64];
+    // they are found (a few active lanes per pass) every lane pushes its hits into a per-warp queue and the
+    // warp scores queue entries 32 at a time with all lanes busy.  A queue entry is 32 bits: output index and
+    // position, both relative to the warp's first (a warp's 32 segments cover < 2^15 positions and its
+    // output slots are contiguous).
+    constexpr unsigned QCAP = 256;
+    __shared__ uint32_t q[FIN_THREADS / 32][QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long k = before + excl + (prm.od.out_base ? *prm.od.out_base : 0ull);
+    const unsigned long long my_k = before + excl + (prm.od.out_base ? *prm.od.out_base : 0ull);
+    const unsigned long long warp_k = __shfl_sync(0xffffffffu, my_k, 0);
+    const int64_t warp_pos = (seg - lane) * 32 * (int64_t)prm.ppm;
     uint4 m[8];
     if (segcnt) {
         const uint4 *mv = reinterpret_cast<const uint4 *>(prm.wk.mask + seg * 32);
@@ -312,28 +316,56 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 8; i++) m[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    unsigned head = 0, count = 0;                  // warp-uniform ring state
-    auto drain = [&](unsigned n_take) {
-        __syncwarp();
-        if ((unsigned)lane < n_take) {
-            const unsigned e = (head + lane) & 63u;
-            const unsigned long long kk = q_k[warp][e];
-            const int64_t pos = q_pos[warp][e];
-            if ((int64_t)kk < prm.capacity) {
-                const double sc = fin_window_score<A, TS>(prm.codes, pos, prm.W, prm.ta);
-                bool is_hit = true;
-                if (prm.verify) {
-                    is_hit = (A == 4 ? (double)(float)sc : sc) > prm.threshold;     // _pwm.c:65 / note N1
-                    if (!is_hit) atomicAdd(prm.counters + 1, 1ull);
-                }
-                prm.od.pos[kk] = is_hit ? pos : -1;
-                if (A == 4) prm.od.seq[kk] = (float)sc;                        // _pwm.c:65
-                else        prm.od.str[kk] = sc;                               // matrix.py:34-42
-                if (A == 4 && prm.codes_b)                                     // pair mode: structure score of the same window
-                    prm.od.str[kk] = fin_window_score<7, 8>(prm.codes_b, pos, prm.W, prm.tb);
-                if (prm.od.out_motif) prm.od.out_motif[kk] = prm.od.motif_id;
+    auto score_entry = [&](uint32_t e) {
+        const unsigned long long kk = warp_k + (e >> 16);
+        const int64_t pos = warp_pos + (e & 0xFFFFu);
+        if ((int64_t)kk < prm.capacity) {
+            const double sc = fin_window_score<A, TS>(prm.codes, pos, prm.W, prm.ta);
+            bool is_hit = true;
+            if (prm.verify) {
+                is_hit = (A == 4 ? (double)(float)sc : sc) > prm.threshold;     // _pwm.c:65 / note N1
+                if (!is_hit) atomicAdd(prm.counters + 1, 1ull);
+            }
+            prm.od.pos[kk] = is_hit ? pos : -1;
+            if (A == 4) prm.od.seq[kk] = (float)sc;                        // _pwm.c:65
+            else        prm.od.str[kk] = sc;                               // matrix.py:34-42
+            if (A == 4 && prm.codes_b)                                     // pair mode: structure score of the same window
+                prm.od.str[kk] = fin_window_score<7, 8>(prm.codes_b, pos, prm.W, prm.tb);
+            if (prm.od.out_motif) prm.od.out_motif[kk] = prm.od.motif_id;
+        }
+    };
+    // queue slots by a warp prefix over the lanes' hit counts (== segcnt): no per-slot coordination
+    unsigned incl = segcnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const unsigned warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (warp_total == 0) return;
+    const unsigned koff0 = (unsigned)(my_k - warp_k);       // == incl - segcnt
+    if (warp_total <= QCAP) {
+        // the usual case: every lane writes its own hits (position order), then full-lane scoring rounds
+        unsigned e = incl - segcnt, koff = koff0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t w4[4] = {m[i].x, m[i].y, m[i].z, m[i].w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const unsigned poff = (unsigned)((lane * 32 + i * 4 + t) * prm.ppm);
+                for (uint32_t h = w4[t]; h; h &= h - 1)
+                    q[warp][e++] = (koff++ << 16) | (poff + (unsigned)(__ffs(h) - 1));
             }
         }
+        __syncwarp();
+        for (unsigned r = lane; r < warp_total; r += 32) score_entry(q[warp][r]);
+        return;
+    }
+    // dense segments: word by word through a 64-entry ring of the same queue
+    unsigned head = 0, count = 0, koff = koff0;            // head, count: warp-uniform ring state
+    auto drain = [&](unsigned n_take) {
+        __syncwarp();
+        if ((unsigned)lane < n_take) score_entry(q[warp][(head + lane) & 63u]);
         __syncwarp();
         head = (head + n_take) & 63u;
         count -= n_take;
@@ -344,15 +376,14 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             uint32_t h = w4[t];
-            const int64_t g0 = (seg * 32 + i * 4 + t) * (int64_t)prm.ppm;      // segments tile the stream contiguously
+            const unsigned poff = (unsigned)((lane * 32 + i * 4 + t) * prm.ppm);
             for (;;) {
                 const unsigned has = __ballot_sync(0xffffffffu, h != 0);
                 if (!has) break;
                 if (count > 32u) drain(32u);
                 if (h) {
                     const unsigned e = (head + count + __popc(has & ((1u << lane) - 1u))) & 63u;
-                    q_k[warp][e] = k++;
-                    q_pos[warp][e] = g0 + (__ffs(h) - 1);
+                    q[warp][e] = (koff++ << 16) | (poff + (unsigned)(__ffs(h) - 1));
                     h &= h - 1;
                 }
                 count += __popc(has);
