@@ -139,6 +139,21 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_by
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128
 #define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24))
 
+// Diagnostic (compile with -DRS_TC_TIMELINE, read with tools/tc_timeline.py): clock64 stamps of the stage hand-offs of
+// CTA 0's first 96 tiles.  [tile][0] MMA warp: operands ready, [1] accumulator stage free, [2] MMAs issued,
+// [3] epilogue warp 4: accumulator full, [4] its chunks done, [5] converter warp 8: raw rows landed, [6] rows converted.
+#ifdef RS_TC_TIMELINE
+#define TC_TL_TILES 96
+__device__ long long g_tc_timeline[TC_TL_TILES * 8];
+#define TC_STAMP(it, k) do { if (blockIdx.x == 0 && (it) < TC_TL_TILES) g_tc_timeline[(it) * 8 + (k)] = clock64(); } while (0)
+extern "C" int rs_debug_tc_timeline(long long *out)
+{
+    return cudaMemcpyFromSymbol(out, g_tc_timeline, sizeof(long long) * TC_TL_TILES * 8) == cudaSuccess ? 0 : 2;
+}
+#else
+#define TC_STAMP(it, k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_constant__ TcParams prm)
 {
@@ -203,7 +218,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             for (int64_t it = 0; it < my_tiles; it++) {
                 const int s = (int)(it % TC_STAGES), t = (int)(it & 1);
                 mbar_wait(&a_full[s], (uint32_t)((it / TC_STAGES) & 1));
+                TC_STAMP(it, 0);
                 if (it >= 2) mbar_wait(&acc_empty[t], (uint32_t)(((it >> 1) - 1) & 1));
+                TC_STAMP(it, 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(s_a + s * TC_A_BYTES);
                 const uint32_t d_tmem = tmem_base + (uint32_t)t * TC_N;
@@ -217,6 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
                 }
                 tc_commit(&a_empty[s]);          // A stage reusable once these MMAs have read it
                 tc_commit(&acc_full[t]);         // accumulator complete
+                TC_STAMP(it, 2);
             }
         }
     } else if ((warp >= 4 && warp < 8) || warp >= 12) {
@@ -242,6 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
         for (int64_t it = 0; it < my_tiles; it++) {
             const int t = (int)(it & 1);
             mbar_wait(&acc_full[t], (uint32_t)((it >> 1) & 1));
+            if (warp == 4 && lane == 0) TC_STAMP(it, 3);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * TC_N;
             const int64_t pos = (first + it * stride) * TC_M + q * 32 + lane;
@@ -300,6 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             }
             tc_fence_before();
             __syncwarp();
+            if (warp == 4 && lane == 0) TC_STAMP(it, 4);
             if (lane == 0) tc_mbar_arrive(&acc_empty[t]);
         }
         if (cnt) flush();
@@ -310,6 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             const int s = (int)(it % TC_STAGES);
             mbar_wait(&raw_full[s], (uint32_t)((it / TC_STAGES) & 1));
             if (it >= TC_STAGES) mbar_wait(&a_empty[s], (uint32_t)(((it / TC_STAGES) - 1) & 1));
+            if (warp == 8 && lane == 0) TC_STAMP(it, 5);
             const float *raw = reinterpret_cast<const float *>(s_raw + s * TC_RAW_BYTES);
             uint4 *arow = reinterpret_cast<uint4 *>(s_a + s * TC_A_BYTES);
             for (int r = ct; r < TC_ROWS; r += 128) {
@@ -327,6 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             }
             fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
+            if (warp == 8 && lane == 0) TC_STAMP(it, 6);
             if (lane == 0) { tc_mbar_arrive(&a_full[s]); tc_mbar_arrive(&raw_empty[s]); }
         }
     }
