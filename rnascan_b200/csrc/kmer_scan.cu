@@ -285,7 +285,11 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
     unsigned long long part = 0;
     for (unsigned p = threadIdx.x; p < vb; p += FIN_THREADS) {
         unsigned long long v;
-        while ((v = ((volatile unsigned long long *)prm.wk.agg)[p]) == 0ull) __nanosleep(20);
+        unsigned spins = 0;
+        while ((v = ((volatile unsigned long long *)prm.wk.agg)[p]) == 0ull) {
+            __nanosleep(20);
+            if (++spins > (1u << 27)) __trap();          // seconds without the predecessor's aggregate: fail, do not hang
+        }
         part += v - 1ull;
     }
     unsigned long long before;

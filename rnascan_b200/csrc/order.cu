@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(OR_THREADS) order_kernel(HitStage st, int64_t 
     unsigned long long part = 0;
     for (unsigned p = threadIdx.x; p < vb; p += OR_THREADS) {
         unsigned long long v;
-        while ((v = ((volatile unsigned long long *)tmp->agg)[p]) == 0ull) __nanosleep(20);
+        unsigned spins = 0;
+        while ((v = ((volatile unsigned long long *)tmp->agg)[p]) == 0ull) {
+            __nanosleep(20);
+            if (++spins > (1u << 27)) __trap();          // seconds without the predecessor's aggregate: fail, do not hang
+        }
         part += v - 1ull;
     }
     unsigned long long before;
