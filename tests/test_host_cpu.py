@@ -678,3 +678,23 @@ def test_background_shift_bounds_the_score_difference_between_two_backgrounds():
             assert worst <= shift <= worst * 1.001 + 1e-9
     same = np.array([5, 6, 7, 8, 0, 0, 0, 0], np.int64)
     assert device._background_shift(same, same, 4) < 1e-9
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU call pattern on a bounded sample) prints exactly ONE JSON
+    line on stdout with the contract's keys; no GPU involved."""
+    import json
+    env = dict(os.environ, RNASCAN_REF_STEP_SECONDS="0.3")
+    proc = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0", "--workload", "c2"], capture_output=True, text=True, env=env, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, proc.stdout
+    out = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "gpu_launches", "cpu_baseline", "e2e"):
+        assert key in out, key
+    assert out["impl"] == "reference" and out["gpu_launches"] == 0 and out["value"] > 0
+    assert out["cpu_baseline"]["kind"] in ("reference", "port") and out["cpu_baseline"]["cores"] >= 1
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["value"] == out["value"]
+    assert "workload" in out["config"]
