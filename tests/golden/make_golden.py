@@ -117,6 +117,39 @@ def author_fixtures():
     open(os.path.join(INP, "empty.fa"), "w").close()
     with open(os.path.join(INP, "bg_seq_custom.txt"), "w") as fh:
         fh.write(repr({"A": 0.3, "C": 0.2, "G": 0.2, "U": 0.3}) + "\n")
+    # (added later; drawn after everything above so that the earlier fixtures stay byte-identical)
+    # many records: ordering of hits across records, Match_ID, descriptions with tabs/blanks, DNA letters,
+    # lower case, runs of N, records shorter than the motif, and matching one-hot structure contexts
+    import gzip
+    many = []
+    for r in range(300):
+        n = int(rng.integers(2, 600))
+        seq = rng.choice(list("ACGU"), size=n, p=[.27, .22, .22, .29])
+        if r % 7 == 0:
+            a = int(rng.integers(0, max(1, n - 5)))
+            seq[a:a + int(rng.integers(1, 30))] = "N"
+        seq = "".join(seq)
+        if r % 5 == 0:
+            seq = seq.replace("U", "T")
+        if r % 11 == 0:
+            seq = seq.lower()
+        title = "tx%d" % r + ("" if r % 3 else " gene=G%d  note with  blanks" % (r // 3)) + ("\textra" if r % 13 == 0 else "")
+        many.append((title, seq))
+    with open(os.path.join(INP, "many.fa"), "w") as fh:
+        for title, seq in many:
+            fh.write(">%s\n" % title)
+            for k in range(0, len(seq), 70):
+                fh.write(seq[k:k + 70] + "\n")
+    with open(os.path.join(INP, "many_struct.fa"), "w") as fh:
+        for title, seq in many:
+            st, cur = [], "E"
+            for _ in range(len(seq)):
+                if rng.random() > 0.8:
+                    cur = str(rng.choice(list("EHTBLRM")))
+                st.append(cur)
+            fh.write(">%s\n%s\n" % (title, "".join(st)))
+    with open(os.path.join(INP, "mixed.fa"), "rb") as src, gzip.GzipFile(os.path.join(INP, "mixed.fa.gz"), "wb", mtime=0) as dst:
+        dst.write(src.read())
 
 
 # ----------------------------------------------------------------------------- CLI cases
@@ -158,6 +191,13 @@ CLI_CASES = {
                            "-m", "50", P("mixed.fa"), P("mixed_struct.fa")],
     "rnass_testseq": ["-p", P("test_seq_pfm.txt"), "-q", P("test_struct_pfm.txt"), "-m", "-2",
                       "-t", "AGUUCCGGUCCGG,EEELLLHHHRRRE"],
+    # --- many records / compressed input (added later)
+    "rna_many_thr": ["-p", P("test_seq_pfm.txt"), "-C", "0.05", "-m", "2", P("many.fa")],
+    "rna_many_slbp": ["-p", P("SLBP_pfm_assembled_normalized_seq.txt"), "-C", "0.01", "-m", "0", P("many.fa")],
+    "ss_many_thr": ["-q", P("test_struct_pfm.txt"), "-m", "1.5", P("many_struct.fa")],
+    "rnass_many_thr": ["-p", P("test_seq_pfm.txt"), "-q", P("test_struct_pfm.txt"), "-m", "0.5",
+                       P("many.fa"), P("many_struct.fa")],
+    "rna_gz_input": ["-p", P("test_seq_pfm.txt"), "-m", "0", P("mixed.fa.gz")],
 }
 # Averaged-structure CLI runs of the reference on py>=3.6 use the label-MISALIGNED
 # np.dot.  They are stored to document the divergence; the canonical
