@@ -278,6 +278,58 @@ int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_t
                           int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
                           uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
 
+/* ---- filter + gather + resolve: averaged-profile scans whose EXACT rows stay in host memory ------
+ * The reference scores the float64 rows pd.read_table gives it (rnascan.py:296-297, :302-307).  At
+ * 56 B/row those rows are the whole end-to-end cost of a scan (PCIe), and the hit decision only needs
+ * them for the few windows near the threshold.  So the device gets a FILTER FORM of the rows,
+ *     RS_ROWS_F32         float32[n][7]  -- the rows themselves are float32 (exact rows == filter rows)
+ *     RS_ROWS_F32_SHADOW  float32[n][7]  -- round-to-nearest shadow of float64 rows (guard band widened)
+ *     RS_ROWS_Q8          uint8[n][8]    -- {q_B..q_T, symbol code}; p ~ q * q8_scale / 255, 0 <= p <= q8_scale
+ *                                           (rs_host_quantize_q8); d_codes is ignored (may be NULL)
+ * rs_filter_profile returns, in position order, every window whose exact score COULD exceed the
+ * threshold (and, when seq_table is given, whose sequence score does: _pwm.c:34-68 arithmetic) as
+ * d_cand_pos[k] = pos_base + window start; d_counters2[0] = candidates found (above cand_capacity the
+ * excess is dropped: re-run larger), [1] = windows that passed the fp32 filter.  With RS_ROWS_Q8 and
+ * d_counts8 != NULL the letters A,C,G,U (codes 0..3) of rows [0, count_rows) are ADDED to
+ * d_counts8[0..3] in the same pass (the background counts of rnascan.py:450-453; not zeroed here).
+ * The host then gathers each candidate's W rows and W symbols (rs_host_gather_windows) and
+ * rs_resolve_candidates decides and scores them exactly as rs_scan_fused does (same arithmetic, same
+ * strict `>`; seq_table NULL = RS_MODE_STRUCT, else RS_MODE_AND): hits in order, d_counters2[0] = hits.
+ * Results are identical to rs_scan_fused on the exact rows.  W <= 24; the tables must be finite or
+ * -inf and the threshold finite (else RS_ERR_INVALID: use rs_scan_fused).                          */
+#define RS_ROWS_F32        0
+#define RS_ROWS_F32_SHADOW 1
+#define RS_ROWS_Q8         2
+int64_t rs_filter_workspace_bytes(int64_t n, int64_t cand_capacity);
+int rs_filter_profile(const uint8_t *d_codes, const void *d_rows, int row_format, double q8_scale, int64_t n,
+                      const double *seq_table_Wx4 /* NULL: no sequence check in this pass */,
+                      const double *struct_table_Wx7, int W, double threshold, double absrow_max,
+                      int64_t pos_base, int64_t count_rows, uint64_t *d_counts8 /* may be NULL */,
+                      int64_t cand_capacity, int64_t *d_cand_pos, uint64_t *d_counters2, void *d_work,
+                      int64_t work_bytes, void *stream);
+int64_t rs_resolve_workspace_bytes(int64_t n_cand);
+int rs_resolve_candidates(const int64_t *d_cand_pos, int64_t n_cand,
+                          const void *d_win_rows /* [n_cand][W][7] */, int rows_dtype /* RS_F32 | RS_F64 */,
+                          const uint8_t *d_win_codes /* [n_cand][W] */, const double *seq_table_Wx4,
+                          const double *struct_table_Wx7, int W, double threshold, int64_t *d_hit_pos,
+                          float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
+                          int64_t work_bytes, void *stream);
+/* Host helpers of the same protocol (host threads, no CUDA):
+ * rs_host_rows_stats      out4 = {max_r sum_c |p|, #non-finite, #negative, max |p|} over float rows;
+ * rs_host_rows_to_f32     float64 -> float32, round to nearest (the RS_ROWS_F32_SHADOW form);
+ * rs_host_quantize_q8     the RS_ROWS_Q8 form: q = rint(p * 255 / scale), byte 7 = codes[r] (0 if NULL);
+ *                         *n_out_of_range = entries outside [0, scale] or non-finite (then the form must
+ *                         not be used);
+ * rs_host_gather_windows  rows [pos[k], pos[k] + W) and their symbols (codes[(pos + j) * code_stride], so
+ *                         byte 7 of quantised rows serves with stride 8; NULL = none) for every candidate. */
+int rs_host_rows_stats(const void *rows, int rows_dtype, int64_t n_rows, int threads, double *out4);
+int rs_host_rows_to_f32(const double *rows, int64_t n_values, float *out, int threads);
+int rs_host_quantize_q8(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes, double scale,
+                        uint8_t *out_rows8, int threads, int64_t *n_out_of_range);
+int rs_host_gather_windows(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes,
+                           int64_t code_stride, const int64_t *pos, int64_t n_cand, int W, void *out_rows,
+                           uint8_t *out_codes, int threads);
+
 /* ---- batched many-PFM scan (BASELINE config 5: 256 RNAcompete-style motif pairs) -------
  * The reference scans one PFM (pair) per process run; a motif collection means running
  * rnascan.py:490-576 once per motif.  Here all motifs are scanned over the SAME resident

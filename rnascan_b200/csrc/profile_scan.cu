@@ -18,35 +18,7 @@
 //       non-finite PSSM entries: everything in fp64 in the reference's order.
 #include "common.cuh"
 
-#define RS_FAST_W   24
-#define FT_THREADS  128
-#define FT_P        9                       // windows per thread; odd => 7*P-word stride is bank-conflict free
-#define FT_TILE     (FT_THREADS * FT_P)     // 1152 positions, 1152*28 B is a multiple of 16
-#define FT_STAGES   3
-
-#define EX_THREADS  128
-#define EX_TILE     1024
-#define EX_STAGES   2
-
-struct ProfileParams {
-    const uint8_t *codes;        // may be NULL in the exact kernel (no separators)
-    const void    *profile;
-    double        *dense_out;    // exact kernel, dense mode
-    int64_t        n;            // rows == symbols
-    int64_t        padded;       // rs_padded_count(n)
-    int64_t        n_tiles;
-    double         threshold;
-    float          filt_thr;     // threshold - guard band (fp32, rounded down)
-    int            mode;         // RS_MODE_*
-    int            W;
-    int            dense;
-    HitStage       st;
-    float          sf[RS_MAX_W * RS_CHANNELS];   // filter table: fp32, rounded up
-    double         sd[RS_MAX_W * RS_CHANNELS];   // exact structure table
-    double         qd[RS_MAX_W * 4];             // exact sequence table (A,C,G,U)
-};
-
-__host__ __device__ constexpr uint32_t ru16(uint32_t x) { return (x + 15u) & ~15u; }
+#include "profile_params.cuh"
 
 // Exact evaluation of window `i` (tile-relative) from the staged tile; returns whether it
 // is a hit and its scores.  Shared by the filter kernel's rare path and the exact kernel.
@@ -68,6 +40,22 @@ __device__ __forceinline__ bool exact_window(const ProfileParams &prm, const PT 
     }
     seq_out = 0.f;
     return codes == nullptr || rs_no_separator(codes + i, W);
+}
+
+// Candidate test of the DEFERRED scans (rs_filter_profile): the exact rows are not on the device, so a
+// window that passed the fp32 filter is kept unless the symbols alone rule it out -- it runs over the
+// end of the stream, holds a separator, or (when the sequence table is already known) its sequence
+// score fails.  rs_resolve_candidates decides from the exact rows.
+__device__ __forceinline__ bool deferred_window(const ProfileParams &prm, const uint8_t *codes, int i, int64_t gpos)
+{
+    const int W = prm.W;
+    if (gpos + W > prm.n) return false;
+    if (prm.mode == RS_MODE_AND) {
+        double q;
+        if (!rs_exact_onehot_window<4, 4>(codes + i, prm.qd, W, q)) return false;
+        return (double)(float)q > prm.threshold;
+    }
+    return rs_no_separator(codes + i, W);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -148,7 +136,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __gri
             if (!(acc[i] <= prm.filt_thr)) {
                 float sq; double st;
                 nexact++;
-                if (exact_window<float>(prm, prof, codes, tid * FT_P + i, t0 + tid * FT_P + i, sq, st))
+                if (prm.defer ? deferred_window(prm, codes, tid * FT_P + i, t0 + tid * FT_P + i)
+                              : exact_window<float>(prm, prof, codes, tid * FT_P + i, t0 + tid * FT_P + i, sq, st))
                     hitmask |= 1u << i;
             }
         }
@@ -159,8 +148,9 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __gri
             emit_tile_hits<FT_THREADS>(prm.st, tile, hitmask, FT_P, [&](int i, int64_t k) {
                 float sq; double st;
                 const int w = tid * FT_P + i;
+                prm.st.pos[k] = prm.pos_base + t0 + w;
+                if (prm.defer) return;
                 exact_window<float>(prm, prof, codes, w, t0 + w, sq, st);
-                prm.st.pos[k] = t0 + w;
                 prm.st.str[k] = st;
                 if (prm.st.seq) prm.st.seq[k] = sq;
             });
@@ -325,17 +315,50 @@ __global__ void stats_finish_kernel(double *stats)
 
 // ------------------------------------------------------------------------------------------------
 // host side
-static float f32_round_up(double v)
+// Filter table + lowered threshold of the fp32 filter kernels.  Returns false when the filter cannot be
+// used (non-finite threshold / row bound, +inf or NaN table entries): the exact kernel then runs.
+//   rows of the table that hold -inf (zero-probability letters with pseudocount 0) are replaced by a
+//   non-negative upper bound (nan_to_num makes such a row contribute 0 or -DBL_MAX, never more than
+//   max(0, finite part));
+//   value_scale: the device multiplies stored values by this to get p (1 for float rows, scale/255 for
+//   quantised rows) -- folded into the table; quant_step: largest |p - stored * value_scale| per entry
+//   (0 for float rows; the float32 shadow of float64 rows is covered by `shadow`).
+static bool build_filter(ProfileParams &prm, const double *struct_table, int W, double threshold,
+                         double profile_absrow_max, double value_scale, double quant_step, bool shadow)
 {
-    float f = (float)v;
-    if ((double)f < v) f = nextafterf(f, INFINITY);
-    return f;
-}
-static float f32_round_down(double v)
-{
-    float f = (float)v;
-    if ((double)f > v) f = nextafterf(f, -INFINITY);
-    return f;
+    if (!(isfinite(threshold) && isfinite(profile_absrow_max) && profile_absrow_max >= 0 && profile_absrow_max < 1e30))
+        return false;
+    double S = 0.0, Sf = 0.0, A = 0.0;
+    for (int j = 0; j < W; j++) {
+        bool row_nonfinite = false;
+        double rowmax = 0.0, rowmax_f = 0.0;
+        for (int c = 0; c < RS_CHANNELS; c++) {
+            double v = struct_table[j * RS_CHANNELS + c];
+            if (v != v || v == INFINITY) return false;           // NaN / +inf: exact kernel only
+            if (v == -INFINITY) row_nonfinite = true;
+        }
+        for (int c = 0; c < RS_CHANNELS; c++) {
+            double v = struct_table[j * RS_CHANNELS + c];
+            double f = row_nonfinite ? ((isfinite(v) && v > 0) ? v : 0.0) : v;
+            const float sf = f32_round_up(f * value_scale);
+            prm.sf[j * RS_CHANNELS + c] = sf;
+            if (!isfinite((double)sf)) return false;
+            rowmax = fmax(rowmax, fabs(f));
+            rowmax_f = fmax(rowmax_f, fabs((double)sf));
+            A += fabs(f);
+        }
+        S += rowmax;
+        Sf += rowmax_f;
+    }
+    // |fp32 result - real value of sum(stored * sf)| <= gamma * sum|stored * sf| <= gamma * (R / value_scale + 4) * Sf
+    // (a row of stored values sums to at most R / value_scale + 3.5 after rounding), and sf >= table * value_scale
+    // entry wise for stored values >= 0; negative p are covered by the generous constant.
+    const double R = fmax(profile_absrow_max, 1.0);
+    double tol = ldexp(1.0, -23) * (double)(RS_CHANNELS * W + 8) * Sf * (R / value_scale + (quant_step > 0 ? 4.0 : 0.0));
+    if (quant_step > 0) tol += quant_step * A * (1.0 + 1e-9);          // |p - p~| <= quant_step per entry
+    if (shadow) tol += ldexp(1.0, -24) * R * S * 1.001 + ldexp(1.0, -149) * A;   // float32 rounding of float64 rows
+    prm.filt_thr = f32_round_down(threshold - tol);
+    return isfinite((double)prm.filt_thr);
 }
 
 template <int W>
@@ -481,42 +504,12 @@ static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int pr
     prm.st.counters = (unsigned long long *)d_counters2;
     prm.st.capacity = hit_capacity;
 
-    // Can the fp32 filter be used?  It needs float profiles, W <= RS_FAST_W, a finite
-    // threshold and a finite guard band; rows of the table that hold -inf (zero-probability
-    // letters with pseudocount 0) are replaced by a non-negative upper bound
-    // (nan_to_num makes such a row contribute 0 or -DBL_MAX, never more than max(0, finite part)).
-    bool fast = profile_dtype == RS_F32 && W <= RS_FAST_W && isfinite(threshold) &&
-                isfinite(profile_absrow_max) && profile_absrow_max >= 0;
-    double S = 0.0;
-    for (int j = 0; j < W && fast; j++) {
-        bool row_nonfinite = false;
-        double rowmax = 0.0;
-        for (int c = 0; c < RS_CHANNELS; c++) {
-            double v = struct_table[j * RS_CHANNELS + c];
-            if (v != v || v == INFINITY) fast = false;           // NaN / +inf: exact kernel only
-            else if (v == -INFINITY) row_nonfinite = true;
-        }
-        for (int c = 0; c < RS_CHANNELS; c++) {
-            double v = struct_table[j * RS_CHANNELS + c];
-            double f = row_nonfinite ? ((isfinite(v) && v > 0) ? v : 0.0) : v;
-            prm.sf[j * RS_CHANNELS + c] = f32_round_up(f);
-            if (!isfinite((double)prm.sf[j * RS_CHANNELS + c])) fast = false;
-            rowmax = fmax(rowmax, fabs(f));
-        }
-        S += rowmax;
-    }
+    bool fast = profile_dtype == RS_F32 && W <= RS_FAST_W &&
+                build_filter(prm, struct_table, W, threshold, profile_absrow_max, 1.0, 0.0, false);
     for (int k = 0; k < W * RS_CHANNELS; k++) prm.sd[k] = struct_table[k];
     if (seq_table) for (int k = 0; k < W * 4; k++) prm.qd[k] = seq_table[k];
 
     int64_t n_tiles;
-    if (fast) {
-        // |fp32 result - real value of sum(p * sf)| <= gamma * sum|p*sf| <= gamma * R * S, and sf >= table
-        // entry wise for p >= 0; negative p are covered by the +2 ulp term.  Generous constant.
-        const double R = fmax(profile_absrow_max, 1.0);
-        const double tol = ldexp(1.0, -23) * (double)(RS_CHANNELS * W + 8) * S * R;
-        prm.filt_thr = f32_round_down(threshold - tol);
-        if (!isfinite((double)prm.filt_thr)) fast = false;
-    }
     if (fast) {
         n_tiles = (n + FT_TILE - 1) / FT_TILE;
         prm.n_tiles = n_tiles;
@@ -587,6 +580,60 @@ extern "C" int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int 
     return scan_fused_impl(d_codes, d_profile, profile_dtype, n, seq_table, struct_table, W, threshold,
                            profile_absrow_max, mode, hit_capacity, d_hit_pos, d_hit_seq, d_hit_struct, d_counters2,
                            d_work, work_bytes, stream, nullptr, nullptr, 0);
+}
+
+// ---- filter + gather + resolve: candidate positions only; the exact rows live on the host (resolve.cu)
+extern "C" int64_t rs_filter_workspace_bytes(int64_t n, int64_t cand_capacity)
+{
+    return rs_filter_layout(n, cand_capacity).total;
+}
+
+extern "C" int rs_filter_profile(const uint8_t *d_codes, const void *d_rows, int row_format, double q8_scale,
+                                 int64_t n, const double *seq_table, const double *struct_table, int W,
+                                 double threshold, double absrow_max, int64_t pos_base, int64_t count_rows,
+                                 uint64_t *d_counts8, int64_t cand_capacity, int64_t *d_cand_pos,
+                                 uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (row_format != RS_ROWS_F32 && row_format != RS_ROWS_F32_SHADOW && row_format != RS_ROWS_Q8) {
+        rs_set_error("row_format must be RS_ROWS_F32, RS_ROWS_F32_SHADOW or RS_ROWS_Q8"); return RS_ERR_INVALID;
+    }
+    const bool q8 = row_format == RS_ROWS_Q8;
+    if (!d_rows || ((uintptr_t)d_rows & 15) || !struct_table) { rs_set_error("rows pointer null or not 16-byte aligned, or null table"); return RS_ERR_INVALID; }
+    if (!q8 && (!d_codes || ((uintptr_t)d_codes & 15))) { rs_set_error("codes pointer null or not 16-byte aligned"); return RS_ERR_INVALID; }
+    if (W < 1 || W > RS_FAST_W) { rs_set_error("filter scans need 1 <= W <= %d", RS_FAST_W); return RS_ERR_INVALID; }
+    if (n < 0 || cand_capacity < 0 || !d_counters2 || (cand_capacity > 0 && !d_cand_pos)) { rs_set_error("bad candidate buffers"); return RS_ERR_INVALID; }
+    if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
+    if (d_counts8 && !q8) { rs_set_error("background counts are taken in the quantised scan only (use rs_hist_rna)"); return RS_ERR_INVALID; }
+    if (q8 && !(q8_scale > 0.0 && isfinite(q8_scale))) { rs_set_error("q8_scale must be positive and finite"); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    if (n == 0 || (n < W && !d_counts8)) return RS_OK;
+    const FilterWork wl = rs_filter_layout(n, cand_capacity);
+    if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
+
+    ProfileParams prm = {};
+    prm.codes = d_codes; prm.profile = d_rows; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.threshold = threshold; prm.mode = seq_table ? RS_MODE_AND : RS_MODE_STRUCT; prm.W = W;
+    prm.defer = 1; prm.pos_base = pos_base;
+    prm.count_on = d_counts8 ? 1 : 0; prm.counts8 = (unsigned long long *)d_counts8;
+    prm.count_rows = d_counts8 ? (count_rows < n ? count_rows : n) : 0;
+    uint8_t *wk = (uint8_t *)d_work;
+    prm.st.pos = (int64_t *)(wk + wl.off_pos);
+    prm.st.tile_seg = (ulonglong2 *)(wk + wl.off_seg);
+    prm.st.counters = (unsigned long long *)d_counters2;
+    prm.st.capacity = cand_capacity;
+    const double vs = q8 ? q8_scale / 255.0 : 1.0;
+    if (!build_filter(prm, struct_table, W, threshold, absrow_max, vs, q8 ? 0.5 * vs : 0.0,
+                      row_format == RS_ROWS_F32_SHADOW)) {
+        rs_set_error("the fp32 filter does not apply (non-finite threshold, table or row bound): use the exact scan");
+        return RS_ERR_INVALID;
+    }
+    if (seq_table) for (int k = 0; k < W * 4; k++) prm.qd[k] = seq_table[k];
+    prm.n_tiles = (n + FT_TILE - 1) / FT_TILE;
+    int rc = q8 ? rs_filter_q8_launch(prm, W, st) : FilterDispatch<RS_FAST_W>::run(W, prm, st);
+    if (rc) return rc;
+    OrderDest od = {d_cand_pos, nullptr, nullptr, nullptr, nullptr, 0};
+    return rs_order_hits(prm.st, prm.n_tiles, od, wk + wl.off_scan, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ Layout in HBM:
   hits            int64 pos[], float32 seq[], float64 struct[]   (structure of arrays)
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -743,3 +744,307 @@ class HostFusedScanner(object):
         st = np.concatenate(str_l) if str_l else np.zeros(0, np.float64)
         sq = (np.concatenate(seq_l) if seq_l else np.zeros(0, np.float32)) if ts is not None else None
         return pos, sq, st
+
+
+# --------------------------------------------------------------------------- exact rows on the host: filter + gather + resolve
+HOST_THREADS = max(1, min(32, os.cpu_count() or 1))
+
+
+def _np_ptr(a):
+    return 0 if a is None else a.ctypes.data
+
+
+class HostProfile(object):
+    """Averaged-profile rows that stay in HOST memory, row-aligned with a symbol stream.
+
+    `rows`: (n, 7) float64 (what pd.read_table gives the reference, rnascan.py:296-297) or float32,
+    C-contiguous numpy array or memmap, channels B,E,H,L,M,R,T, separator rows zero.  Only a FILTER
+    FORM of them travels to the device (include/rnascan_b200.h, rs_filter_profile): the rows themselves
+    when they are float32, their float32 shadow when they are float64, or the 8-byte quantised form
+    `q8` (n, 8) uint8 with `q8_scale` when one is supplied (profile packs) or built with make_q8()."""
+
+    def __init__(self, rows, q8=None, q8_scale=None, stats=None):
+        if rows.dtype not in (np.float32, np.float64):
+            rows = np.ascontiguousarray(rows, dtype=np.float64)
+        if rows.ndim != 2 or rows.shape[1] != len(CHANNELS):
+            raise ValueError("profile must have shape (L, 7) in channel order %s" % CHANNELS)
+        if not rows.flags["C_CONTIGUOUS"]:
+            rows = np.ascontiguousarray(rows)
+        self.rows = rows
+        self.n = int(rows.shape[0])
+        self.dtype = _lib.RS_F32 if rows.dtype == np.float32 else _lib.RS_F64
+        self.q8, self.q8_scale = q8, q8_scale
+        self._stats = None if stats is None else tuple(float(v) for v in stats)
+
+    def stats(self):
+        """(max abs row sum, #non-finite, #negative, max |value|), computed once on host threads."""
+        if self._stats is None:
+            out = np.zeros(4, np.float64)
+            check(lib.rs_host_rows_stats(_np_ptr(self.rows), self.dtype, self.n, HOST_THREADS, out.ctypes.data))
+            self._stats = tuple(float(v) for v in out)
+        return self._stats
+
+    def absrow_max(self):
+        mx, bad, neg, _ = self.stats()
+        return float("nan") if (bad or neg) else mx
+
+    def make_q8(self, codes=None, out=None):
+        """Build the quantised filter form (byte 7 = codes[r], 0 when codes is None).  Returns False --
+        and leaves q8 unset -- when the rows do not fit it (negative / non-finite entries)."""
+        mx, bad, neg, vmax = self.stats()
+        if bad or neg or self.n == 0:
+            return False
+        scale = vmax if vmax > 0 else 1.0
+        q8 = np.empty((self.n, 8), np.uint8) if out is None else out
+        n_bad = ctypes.c_int64(0)
+        check(lib.rs_host_quantize_q8(_np_ptr(self.rows), self.dtype, self.n, _np_ptr(codes), float(scale),
+                                      q8.ctypes.data, HOST_THREADS, ctypes.byref(n_bad)))
+        if n_bad.value:
+            return False
+        self.q8, self.q8_scale = q8, float(scale)
+        return True
+
+
+def filter_applies(struct_table, threshold, absrow_max):
+    """Can the fp32 filter kernels decide candidates for this scan?  (Else: the exact fp64 kernel.)"""
+    t = np.asarray(struct_table, np.float64)
+    return bool(t.shape[0] <= 24 and np.isfinite(float(threshold)) and np.isfinite(absrow_max) and
+                0 <= absrow_max < 1e30 and not np.isnan(t).any() and not (t == np.inf).any())
+
+
+class HostProfileScanner(object):
+    """Averaged-profile scan (optionally AND the sequence PSSM) of HOST-resident streams through
+    rs_filter_profile -> rs_host_gather_windows -> rs_resolve_candidates.
+
+    Chunks of the filter form go to the device double-buffered on a copy stream while the previous chunk is
+    being filtered; candidate positions come back, their exact rows are gathered from host memory and one
+    small launch decides and scores them in the reference's arithmetic.  Bytes over the link per position:
+    8 (quantised rows, symbol included) or 1 + 28 (float32 rows / shadow) instead of 1 + 56.  All device and
+    pinned buffers are allocated once; run() may be called repeatedly (bench.py) and regrows the candidate
+    buffers when a threshold lets more windows through than they hold."""
+
+    def __init__(self, n, W, form, chunk_rows=1 << 23, device=None, cand_per_row=1.0 / 256):
+        require_cuda()
+        if form not in ("f32", "shadow", "q8"):
+            raise ValueError("form must be 'f32', 'shadow' or 'q8'")
+        self.device = torch.device(device or "cuda")
+        self.n, self.W, self.form = int(n), int(W), form
+        self.chunk = max(256, int(chunk_rows) // 256 * 256)
+        self.starts = list(range(0, max(self.n - self.W + 1, 1), self.chunk)) if self.n >= self.W else []
+        if form == "q8" and not self.starts and self.n > 0:
+            self.starts = [0]                       # nothing to scan, but the symbols still count
+        self.rows_max = padded_count(min(self.chunk + self.W - 1, max(self.n, 1))) + 256
+        cols, tdt = (8, torch.uint8) if form == "q8" else (len(CHANNELS), torch.float32)
+        self.cols, self.tdt = cols, tdt
+        self.dbuf = [torch.empty((self.rows_max, cols), dtype=tdt, device=self.device) for _ in range(2)]
+        self.stage = None                           # pinned staging, made on first use with a pageable source
+        self.codes = None if form == "q8" else torch.empty(padded_count(self.n) + 1024, dtype=torch.uint8,
+                                                           device=self.device)
+        self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.loaded = [torch.cuda.Event() for _ in range(2)]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+        self.cap = max(4096, int(self.chunk * cand_per_row))
+        self._alloc_cand()
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.n_candidates = self.n_filter_pass = 0
+        self.launches = 0
+
+    def _alloc_cand(self):
+        k = max(len(self.starts), 1)
+        self.cand = torch.empty((k, self.cap), dtype=torch.int64, device=self.device)
+        self.cand_counters = torch.zeros((k, 2), dtype=torch.int64, device=self.device)
+        self.cand_counters_host = torch.zeros((k, 2), dtype=torch.int64).pin_memory()
+        self.work_bytes = int(lib.rs_filter_workspace_bytes(self.chunk + self.W + 256, self.cap))
+        self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=self.device)
+
+    # -- chunk k of the filter form -> device buffer k & 1 (copy stream)
+    def _load(self, k, src):
+        c0 = self.starts[k]
+        rows = min(self.chunk + self.W - 1, self.n - c0)
+        slot = k & 1
+        if isinstance(src, torch.Tensor):           # pinned host tensor of the filter form: straight from it
+            piece = src[c0:c0 + rows]
+        else:                                       # numpy / memmap: through pinned staging (and, for float64
+            if self.stage is None:                  # rows, the conversion to the float32 shadow on the way)
+                self.stage = [torch.empty((self.rows_max, self.cols), dtype=self.tdt).pin_memory()
+                              for _ in range(2)]
+            if k >= 2:
+                self.loaded[slot].synchronize()     # the previous copy out of this staging buffer is done
+            st = self.stage[slot].numpy()
+            part = src[c0:c0 + rows]
+            if part.dtype == np.float64:
+                part = np.ascontiguousarray(part)
+                check(lib.rs_host_rows_to_f32(part.ctypes.data, rows * self.cols, st.ctypes.data, HOST_THREADS))
+            else:
+                np.copyto(st[:rows], part)
+            piece = self.stage[slot][:rows]
+        with torch.cuda.stream(self.copy_stream):
+            if k >= 2:
+                self.copy_stream.wait_event(self.freed[slot])
+            self.dbuf[slot][:rows].copy_(piece, non_blocking=True)
+            if self.form == "q8":                   # rows past the end of the stream read as separators
+                self.dbuf[slot][rows:rows + 512].fill_(0xFF)
+            self.loaded[slot].record(self.copy_stream)
+        self.h2d_bytes += rows * self.cols * (1 if self.form == "q8" else 4)
+        return rows
+
+    def run(self, codes, filt_src, exact_rows, struct_table, seq, threshold, absrow_max, q8_scale=1.0,
+            all_reduce=None, exact_codes=None):
+        """codes: uint8[n] host symbols (numpy or pinned tensor; ignored for 'q8', whose rows carry them);
+        filt_src: the filter form on the host -- float32 / float64 (n, 7) or uint8 (n, 8), numpy, memmap or
+        pinned tensor; exact_rows: (n, 7) float32 | float64 numpy array or memmap the candidates are gathered
+        from; seq: None (structure only), a (W, 4) table, or a callable counts int64[8] -> table (background
+        computed from the data, rnascan.py:507-511: the counts are taken on the device in the same pass);
+        exact_codes: host symbols for the gather when `codes` is None ('q8': byte 7 of filt_src serves).
+        Returns (pos int64[], seq float32[] | None, struct float64[]), positions ascending."""
+        n, W = self.n, self.W
+        tq = _table(struct_table, 7)
+        if tq.shape[0] != W:
+            raise ValueError("structure table width differs from the scanner's")
+        threshold = float(threshold)
+        comp = torch.cuda.current_stream(self.device)
+        deferred_seq = callable(seq)
+        ts = None if (seq is None or deferred_seq) else _table(seq, 4)
+        fmt = {"f32": _lib.RS_ROWS_F32, "shadow": _lib.RS_ROWS_F32_SHADOW, "q8": _lib.RS_ROWS_Q8}[self.form]
+        while True:
+            self.h2d_bytes = self.d2h_bytes = 0
+            self.launches = 0
+            self.copy_stream.wait_stream(comp)
+            if self.form != "q8":
+                h = codes if isinstance(codes, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(codes))
+                self.codes[:n].copy_(h[:n], non_blocking=True)
+                self.codes[n:].fill_(_lib.RS_SEP)
+                self.h2d_bytes += n
+            if deferred_seq:
+                self.counts.zero_()
+                if self.form != "q8":
+                    check(lib.rs_hist_rna(_ptr(self.codes), n, _ptr(self.counts), comp.cuda_stream))
+                    self.launches += 1
+            pending = {}
+            for k in range(min(2, len(self.starts))):
+                pending[k] = self._load(k, filt_src)
+            for k, c0 in enumerate(self.starts):
+                rows = pending.pop(k)
+                slot = k & 1
+                comp.wait_event(self.loaded[slot])
+                count_rows = min(self.chunk, n - c0)
+                want_counts = deferred_seq and self.form == "q8"
+                check(lib.rs_filter_profile(0 if self.form == "q8" else _ptr(self.codes) + c0, _ptr(self.dbuf[slot]),
+                                            fmt, float(q8_scale), rows, 0 if ts is None else ts.ctypes.data,
+                                            tq.ctypes.data, W, threshold, float(absrow_max), c0, count_rows,
+                                            _ptr(self.counts) if want_counts else 0, self.cap, _ptr(self.cand[k]),
+                                            _ptr(self.cand_counters[k]), _ptr(self.work), self.work_bytes,
+                                            comp.cuda_stream))
+                self.launches += 2                  # filter + ordering
+                self.freed[slot].record(comp)
+                if k + 2 < len(self.starts):
+                    pending[k + 2] = self._load(k + 2, filt_src)
+            if deferred_seq:
+                if all_reduce is not None:
+                    all_reduce(self.counts)         # the path's only collective
+                self.counts_host.copy_(self.counts, non_blocking=True)
+                self.d2h_bytes += 64
+            self.cand_counters_host.copy_(self.cand_counters, non_blocking=True)
+            comp.synchronize()
+            cc = self.cand_counters_host.numpy()[:len(self.starts)]
+            self.d2h_bytes += cc.size * 8
+            found = cc[:, 0] if len(self.starts) else np.zeros(0, np.int64)
+            if len(found) and int(found.max()) > self.cap:
+                self.cap = int(found.max() * 1.25) + 1024
+                self._alloc_cand()
+                continue
+            break
+        self.n_filter_pass = int(cc[:, 1].sum()) if len(self.starts) else 0
+        parts = [self.cand[k, :int(f)].cpu().numpy() for k, f in enumerate(found.tolist()) if f]
+        cand = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+        self.d2h_bytes += cand.size * 8
+        self.n_candidates = int(cand.size)
+        if deferred_seq:
+            ts = _table(seq(self.counts_host.numpy()), 4)
+        if ts is not None and ts.shape[0] != W:
+            raise ValueError("sequence and structure motifs must have the same width")
+        return self._resolve(cand, codes if exact_codes is None else exact_codes, filt_src, exact_rows, ts, tq,
+                             threshold)
+
+    RESOLVE_BATCH = 1 << 20
+
+    def _resolve(self, cand, codes, filt_src, exact_rows, ts, tq, threshold):
+        W = self.W
+        dtype = _lib.RS_F32 if exact_rows.dtype == np.float32 else _lib.RS_F64
+        ftype = torch.float32 if dtype == _lib.RS_F32 else torch.float64
+        if codes is None and self.form == "q8":     # the symbols ride in byte 7 of the quantised rows
+            q = filt_src.numpy() if isinstance(filt_src, torch.Tensor) else filt_src
+            code_ptr, code_stride = q.ctypes.data + 7, 8
+        elif codes is None:
+            code_ptr, code_stride = 0, 1
+        else:
+            c = codes.numpy() if isinstance(codes, torch.Tensor) else np.ascontiguousarray(codes)
+            code_ptr, code_stride = c.ctypes.data, 1
+        pos_l, seq_l, str_l = [], [], []
+        comp = torch.cuda.current_stream(self.device)
+        for a in range(0, len(cand), self.RESOLVE_BATCH):
+            part = np.ascontiguousarray(cand[a:a + self.RESOLVE_BATCH])
+            k = len(part)
+            h_rows = torch.empty((k, W, len(CHANNELS)), dtype=ftype).pin_memory()
+            h_codes = torch.empty((k, W), dtype=torch.uint8).pin_memory()
+            check(lib.rs_host_gather_windows(exact_rows.ctypes.data, dtype, exact_rows.shape[0], code_ptr, code_stride,
+                                             part.ctypes.data, k, W, h_rows.numpy().ctypes.data,
+                                             h_codes.numpy().ctypes.data, HOST_THREADS))
+            d_rows = h_rows.to(self.device, non_blocking=True)
+            d_codes = h_codes.to(self.device, non_blocking=True)
+            d_pos = torch.from_numpy(part).to(self.device, non_blocking=True)
+            self.h2d_bytes += h_rows.numel() * h_rows.element_size() + h_codes.numel() + k * 8
+            out_pos = torch.empty(k, dtype=torch.int64, device=self.device)
+            out_seq = torch.empty(k, dtype=torch.float32, device=self.device) if ts is not None else None
+            out_str = torch.empty(k, dtype=torch.float64, device=self.device)
+            counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+            wb = int(lib.rs_resolve_workspace_bytes(k))
+            work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            check(lib.rs_resolve_candidates(_ptr(d_pos), k, _ptr(d_rows), dtype, _ptr(d_codes),
+                                            0 if ts is None else ts.ctypes.data, tq.ctypes.data, W, threshold,
+                                            _ptr(out_pos), _ptr(out_seq), _ptr(out_str), _ptr(counters), _ptr(work),
+                                            wb, comp.cuda_stream))
+            self.launches += 2
+            hits = int(counters[0].item())
+            pos_l.append(out_pos[:hits].cpu().numpy())
+            str_l.append(out_str[:hits].cpu().numpy())
+            if ts is not None:
+                seq_l.append(out_seq[:hits].cpu().numpy())
+            self.d2h_bytes += 16 + hits * (20 if ts is not None else 16)
+        pos = np.concatenate(pos_l) if pos_l else np.zeros(0, np.int64)
+        st = np.concatenate(str_l) if str_l else np.zeros(0, np.float64)
+        sq = (np.concatenate(seq_l) if seq_l else np.zeros(0, np.float32)) if ts is not None else None
+        return pos, sq, st
+
+
+def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 23, form=None,
+                      return_scanner=False):
+    """Averaged-profile scan of host-resident rows (a HostProfile) through the filter + gather + resolve
+    path; same results as scan_fused(SymbolStream(codes), ProfileStream(hp.rows), ...).  `codes`: uint8[n]
+    host symbols (None: no separators, structure-only).  Falls back to the exact fp64 kernel when the fp32
+    filter does not apply (-m -inf, W > 24, +inf / NaN tables, negative or non-finite rows)."""
+    tq = _table(struct_table, 7)
+    W = tq.shape[0]
+    n = hp.n
+    threshold = float(threshold)
+    if codes is None:
+        codes = np.zeros(n, np.uint8)
+    if not filter_applies(tq, threshold, hp.absrow_max()) or n < W:
+        stream = SymbolStream(codes, kind="rna")
+        profile = ProfileStream(hp.rows)
+        if callable(seq):
+            counts = histogram(stream)
+            if all_reduce is not None:
+                all_reduce(counts)
+            seq = seq(counts.cpu().numpy())
+        out = scan_fused(stream, profile, seq, tq, threshold)
+        return out + (None,) if return_scanner else out
+    if form is None:
+        form = "q8" if hp.q8 is not None else ("f32" if hp.dtype == _lib.RS_F32 else "shadow")
+    sc = HostProfileScanner(n, W, form, chunk_rows=min(int(chunk_rows), max(n, 256)))
+    src = hp.q8 if form == "q8" else hp.rows
+    out = sc.run(codes, src, hp.rows, tq, seq, threshold, hp.absrow_max(),
+                 q8_scale=hp.q8_scale if form == "q8" else 1.0, all_reduce=all_reduce)
+    return out + (sc,) if return_scanner else out

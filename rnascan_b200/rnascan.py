@@ -516,9 +516,9 @@ def scan_averaged_structure(struct_file, pssm, minscore):
     width = tq.shape[0]
     if rows.shape[0] < width:
         return pd.DataFrame([])
-    profile = device.ProfileStream(rows)
-    stream = device.SymbolStream(np.zeros(rows.shape[0], np.uint8))
-    pos, _, scores = device.scan_fused(stream, profile, None, tq, minscore)
+    # the float64 rows stay on the host: a float32 shadow is filtered on the device, the few windows near
+    # the threshold are re-scored from the exact rows (device.scan_profile_host)
+    pos, _, scores = device.scan_profile_host(None, device.HostProfile(rows), None, tq, minscore)
     return _averaged_frame(motif_id, pos, width, scores)
 
 
@@ -872,10 +872,9 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     if n_prof:
         codes[offsets + lengths] = device._lib.RS_SEP
     if len(codes):
-        stream = device.SymbolStream(codes, offsets, lengths)
-        profile = device.ProfileStream(packed)
-        pos, seq_scores, scores = device.scan_fused(stream, profile, seq_table, tq, minscore)
-        rec, start0 = stream.locate(pos) if len(pos) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+        pos, seq_scores, scores = device.scan_profile_host(codes, device.HostProfile(packed), seq_table, tq, minscore)
+        rec = np.searchsorted(offsets, pos, side="right") - 1
+        start0 = pos - offsets[rec]
     else:
         rec = start0 = np.zeros(0, np.int64)
         scores = np.zeros(0, np.float64)
