@@ -3,11 +3,12 @@
 
     python bench.py --gpus 1 --steps 10 --warmup 3              # this framework (default)
     python bench.py --impl reference --gpus 1 --steps 3 ...     # the reference's CPU path
-    torchrun ... bench.py --gpus N ...                          # one rank per GPU, weak scaling
+    torchrun ... bench.py --gpus N ...                          # one rank per GPU, the 1 Gnt split N ways
 
 Workload (default "c4", BASELINE.json configs[3] -- the configuration the north-star's
 HBM-fraction target is quoted on): combined sequence-PSSM + averaged 7-channel structure
-profile scan, 125 Mnt per GPU (= 1 Gnt on 8 GPUs), W = 7, m = 6, sequence background
+profile scan of 1 Gnt in total (one GPU holds all of it: 29 GB; N GPUs hold 1/N each -- strong
+scaling; --n-per-gpu fixes the per-GPU share instead), W = 7, m = 6, sequence background
 computed from the data (histogram -> all-reduce of the integer counts -> log-odds on the
 host), structure background = the reference's example 3'UTR table.  A step is ONE pass of
 the whole path over the rank's shard:   histogram -> [all-reduce] -> PSSM -> fused scan ->
@@ -38,6 +39,7 @@ SS_BG = {"B": 0.0163181097311479, "E": 0.272087789050946, "H": 0.153012079123538
          "T": 0.137367490441988}       # example/3p_UTR_background_structural_context.txt
 ALGO_BYTES = {"c4": 29.0, "c2": 1.0, "c3": 5.0, "c5": 29.0}     # SURVEY.md section 8(d), per scored position
 N_MOTIFS_C5 = 256
+OTHERS_N = 125_000_000          # symbols per GPU of the side runs (configs 2, 3, 5) and of weak-scaling shards
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -53,9 +55,10 @@ def recorded_traffic(workload, n_symbols):
     (profiles/traffic.json, written by tools/ncu_summary.py --traffic), for the same shard size; else None."""
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
-            rec = json.load(fh)[workload]
-        if abs(rec["symbols_per_gpu"] - n_symbols) <= 0.001 * n_symbols:
-            return rec["traffic"], rec["source"]
+            db = json.load(fh)
+        for key, rec in db.items():              # keys: "<workload>" or "<workload>@<size tag>"
+            if key.split("@")[0] == workload and abs(rec["symbols_per_gpu"] - n_symbols) <= 0.001 * n_symbols:
+                return rec["traffic"], rec["source"]
     except Exception:
         pass
     return None, None
@@ -211,10 +214,23 @@ def make_device_shard(n_symbols, seed, workload, device):
     return {"codes": full, "prof": prof, "n": n, "lengths": lengths, "offsets": offsets}
 
 
-def make_tables_fn(workload, seed=102):
+def make_tables_fn(workload, seed=102, pure_python=False):
     """PFMs (Dirichlet(0.3) rows, pseudocount 0.01) and the counts -> log-odds tables step,
-    done with the product's own PFM preprocessing (rnascan_b200.motifs)."""
+    done with the product's own PFM preprocessing (rnascan_b200.motifs).  pure_python=True (the reference
+    arm) builds the same tables with motifs.log_odds' Python arithmetic so that the CUDA library is never
+    loaded in that process (the two are bit-identical, tests/test_host_cpu.py)."""
     from rnascan_b200 import motifs, synth
+
+    def log_odds_rows(prob_arr, bgn):
+        if not pure_python:
+            return motifs.log_odds_table(prob_arr, bgn)
+        out = np.empty_like(prob_arr)                   # Python's math.log(p / b, 2), as Biopython's log_odds
+        for i in range(prob_arr.shape[0]):
+            for a in range(prob_arr.shape[1]):
+                pr, b = float(prob_arr[i, a]), float(bgn[a])
+                out[i, a] = math.log(pr / b, 2) if pr > 0 else float("-inf")
+        return out
+
     rng = np.random.default_rng(seed)
     pfm_seq = synth.pfm_rows(W_MOTIF, 4, rng)               # columns A,C,G,U
     pfm_str = synth.pfm_rows(W_MOTIF, 7, np.random.default_rng(seed + 1))   # columns B,E,H,L,M,R,T
@@ -238,14 +254,14 @@ def make_tables_fn(workload, seed=102):
         total = 4 + sum(c[l] for l in rna)
         bg = {l: (float(c[l]) + 1) / total for l in rna}
         norm = sum(bg.values())
-        return motifs.log_odds_table(seq_prob_arr, np.array([bg[l] / norm for l in "ACGU"]))
+        return log_odds_rows(seq_prob_arr, np.array([bg[l] / norm for l in "ACGU"]))
 
     def struct_table_computed(counts8):
         c = {l: int(counts8["BEHLMRT".index(l)]) for l in chan}
         total = 7 + sum(c.values())
         bg = {l: (float(c[l]) + 1) / total for l in chan}
         norm = sum(bg.values())
-        return motifs.log_odds_table(str_prob_arr, np.array([bg[l] / norm for l in "BEHLMRT"]))
+        return log_odds_rows(str_prob_arr, np.array([bg[l] / norm for l in "BEHLMRT"]))
 
     if workload == "c4":
         return lambda counts8: (seq_table(counts8), tq)
@@ -277,7 +293,7 @@ def make_tables_fn(workload, seed=102):
             norm = sum(bg.values())                         # Biopython re-normalises the background
             bgn = np.array([bg[l] / norm for l in "ACGU"])
             ss = np.zeros((N_MOTIFS_C5 * stride, 4), np.float64)
-            ss[row_of] = motifs.log_odds_table(stacked, bgn)   # == motifs.log_odds per motif, bit for bit
+            ss[row_of] = log_odds_rows(stacked, bgn)   # == motifs.log_odds per motif, bit for bit
             return ss.reshape(N_MOTIFS_C5, stride, 4), qs
         batched.widths = np.asarray(widths, np.int32)
         batched.lists = lambda counts8: ([t[:w] for t, w in zip(batched(counts8)[0], widths)], tqs)
@@ -303,7 +319,14 @@ def run_b200(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    out = measure(args, args.workload, args.steps, (rank, world, local, device), full=True)
+    if args.n_per_gpu:
+        n_main, scaling = args.n_per_gpu, "weak"
+    elif args.workload in ("c4", "c5"):
+        n_main, scaling = args.n_total // world, "strong"          # BASELINE config 4/5: 1 Gnt in total
+    else:
+        n_main, scaling = OTHERS_N, "weak"                          # configs 2/3: ~100 Mnt per GPU
+    out = measure(args, args.workload, args.steps, (rank, world, local, device), True, n_main)
+    out["scaling"] = scaling
     if world == 1 and not args.no_others:
         # the other BASELINE.json configurations, briefly, so that one bench line shows them all
         others = {}
@@ -311,12 +334,15 @@ def run_b200(args):
             if wl == args.workload:
                 continue
             torch.cuda.empty_cache()
-            o = measure(args, wl, 3, (rank, world, local, device), full=False)
+            o = measure(args, wl, 5, (rank, world, local, device), False, OTHERS_N)
             others[wl] = {"workload": o["config"]["workload"], "value": o["value"], "unit": o["unit"],
                           "ms_per_step": o["ms_per_step"], "kernel": o["roofline"]["kernel"],
                           "kernel_ms": o["roofline"]["kernel_ms"], "bound": o["roofline"]["bound"],
                           "achieved": o["roofline"]["achieved"], "roofline_unit": o["roofline"]["unit"],
-                          "frac": o["roofline"]["frac"]}
+                          "frac": o["roofline"]["frac"], "symbols": o["config"]["symbols_per_gpu"]}
+            for key in ("frac_executed", "achieved_executed"):
+                if key in o["roofline"]:
+                    others[wl][key] = o["roofline"][key]
             if "e2e" in o:
                 others[wl]["e2e"] = o["e2e"]["value"]
             if "motif_positions_per_s" in o:
@@ -330,15 +356,14 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def measure(args, wl, steps, ctx, full=True):
-    """Time `steps` steps of workload `wl` on this rank's shard; returns the JSON object."""
+def measure(args, wl, steps, ctx, full, n_target):
+    """Time `steps` steps of workload `wl` on this rank's shard of ~n_target symbols; returns the JSON object."""
     import torch
     import torch.distributed as dist
     from rnascan_b200 import device as dev, _lib
     from rnascan_b200.device import lib, check, _ptr
 
     rank, world, local, device = ctx
-    n_target = args.n_per_gpu
     shard = make_device_shard(n_target, 4000 + rank, wl, device)
     n, codes, prof = shard["n"], shard["codes"], shard["prof"]
     positions = scored_positions(shard["lengths"], W_MOTIF)
@@ -379,11 +404,12 @@ def measure(args, wl, steps, ctx, full=True):
         if world > 1:
             dist.all_reduce(t)
 
-    def step():
-        if bgscan is not None:
-            bgscan.launch(codes, prof, _lib.RS_F32, W_MOTIF, tq_fixed, lambda c: tables(c)[0], THRESHOLD, absmax,
-                          all_reduce if world > 1 else None)
-            launches[0] += bgscan.launches
+    def step(thr=THRESHOLD, job=None):
+        job = job or bgscan
+        if job is not None:
+            job.launch(codes, prof, _lib.RS_F32, W_MOTIF, tq_fixed, lambda c: tables(c)[0], thr, absmax,
+                       all_reduce if world > 1 else None)
+            launches[0] += job.launches
             return
         if ohscan is not None:
             ohscan.launch(codes, tables.seq_prob, lambda c: tables(c)[0], THRESHOLD, all_reduce if world > 1 else None)
@@ -472,35 +498,49 @@ def measure(args, wl, steps, ctx, full=True):
     if wl == "c5":
         hits = int(c5_bases[-1].item())
 
+    # ---- sustained: keep stepping for a couple of seconds (power / clock regime of a long job)
+    sustained = None
+    if full and not flush_l2 and args.sustain_seconds > 0:
+        k_s = max(steps, int(math.ceil(args.sustain_seconds * 1e3 / max(ms_total / steps, 1e-3))))
+        e0.record(stream)
+        for _ in range(k_s):
+            step()
+        e1.record(stream)
+        barrier()
+        sustained = {"steps": k_s, "ms": e0.elapsed_time(e1)}
+
+    # ---- threshold sweep (c4): what the scan costs when more windows pass the filter
+    sweep = None
+    if full and wl == "c4" and bgscan is not None and not args.no_sweep:
+        sweep = []
+        job = dev.BackgroundFusedScan(n, device, capacity=max(1 << 16, n // 16))
+        for thr in (6.0, 2.0, 0.0):
+            for _ in range(2):
+                step(thr, job)
+            barrier()
+            e0.record(stream)
+            for _ in range(3):
+                step(thr, job)
+            e1.record(stream)
+            barrier()
+            cand, resc = (int(v) for v in job.hb.cand_counters.cpu().numpy())
+            sweep.append({"minscore": thr, "ms_per_step": e0.elapsed_time(e1) / 3, "hits": int(job.hb.counters[0].item()),
+                          "structure_candidates": cand, "windows_rescored_fp64": resc,
+                          "overflow": cand > job.hb.capacity})
+        del job
+        torch.cuda.empty_cache()
+
     # ---- end to end: host buffers -> device -> results back on the host, every step
     e2e = None
+    e2e_extra = {}
     k2 = max(2, min(steps, 5))
     h_codes = torch.empty(codes.shape, dtype=torch.uint8).pin_memory()
     h_codes.copy_(codes)
     if args.no_e2e:
         pass
     elif wl == "c4":
-        h_prof = torch.empty(prof.shape, dtype=torch.float32).pin_memory()
-        h_prof.copy_(prof)
-        torch.cuda.synchronize()
-        pipe = dev.HostFusedScanner(n, W_MOTIF, device=device)
-        res = None
-        for _ in range(2):
-            res = pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax, all_reduce=all_reduce)
-        barrier()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(k2):
-            res = pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax, all_reduce=all_reduce)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k2
-        e2e = {"ms": ms_e2e, "h2d": pipe.h2d_bytes, "d2h": pipe.d2h_bytes, "hits": int(len(res[0])),
-               "api": "rnascan_b200.device.HostFusedScanner.run (pinned host streams in, host hit arrays out; "
-                      "profile chunks double-buffered against the scan)"}
-        if hits is not None and e2e["hits"] != hits:
-            raise SystemExit("e2e hit count %d != device-resident hit count %d" % (e2e["hits"], hits))
-        del h_prof, pipe
+        e2e, e2e_extra = e2e_c4(args, dev, shard, h_codes, tables, absmax, hits, all_reduce, barrier, (rank, world, device),
+                                full)
     else:
         # plain copy-in / step / copy-out through the same C-ABI calls
         h_prof = None
@@ -557,7 +597,7 @@ def measure(args, wl, steps, ctx, full=True):
     out = {
         "metric": "scored positions/sec", "value": all_positions / (ms_step * 1e-3) / 1e9, "unit": "Gpos/s",
         "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,      # run_b200 sets `scaling`
         "dtype": "f32 filter + f64 exact re-score (sequence: f64 accumulate -> f32)" if wl == "c4" else
                  ("f64 accumulate -> f32" if wl == "c2" else ("f64" if wl == "c3" else
                                                               "f32 filter + f64 exact re-score, per motif")),
@@ -605,9 +645,16 @@ def measure(args, wl, steps, ctx, full=True):
                 src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
             except Exception:
                 tpeak, src = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
-            out["roofline"] = {"bound": "tensor", "kernel": "batched_tc_kernel", "achieved": tf, "peak": tpeak,
-                               "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": src,
-                               "flop_per_position": 2.0 * 96 * 256, "kernel_ms": kernel_ms,
+            # SURVEY.md 8(d)'s ALGORITHMIC figure: 2 * 7 channels * W_m * 256 motifs (no padding of W to 12, no
+            # eighth channel); `achieved`/`frac` below use it -- the padded figure the MMAs execute is given beside it
+            w_mean = float(np.mean(c5_widths))
+            flops_alg = 2.0 * 7 * w_mean * N_MOTIFS_C5 * positions
+            tf_alg = flops_alg / (kernel_ms * 1e-3) / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": "batched_tc_kernel", "achieved": tf_alg, "peak": tpeak,
+                               "unit": "TFLOP/s", "frac": tf_alg / tpeak, "peak_source": src,
+                               "flop_per_position_algorithmic": 2.0 * 7 * w_mean * N_MOTIFS_C5,
+                               "achieved_executed": tf, "frac_executed": tf / tpeak,
+                               "flop_per_position_executed": 2.0 * 96 * 256, "kernel_ms": kernel_ms,
                                "kernel_share_of_step": kernel_ms / ms_step, "traffic": recorded_traffic(wl, n)[0],
                                "traffic_source": recorded_traffic(wl, n)[1],
                                "hbm_GBps_algorithmic": 29.0 * positions / (kernel_ms * 1e-3) / 1e9}
@@ -620,9 +667,185 @@ def measure(args, wl, steps, ctx, full=True):
                       "ms_per_step": ms_e2e,
                       "link_GBps": (e2e["h2d"] + e2e["d2h"]) / (ms_e2e * 1e-3) / 1e9,
                       "api": e2e["api"]}
+        for key in ("candidates", "filter_pass", "launches", "host_prep_s_untimed", "hits"):
+            if key in e2e:
+                out["e2e"][key + "_rank0"] = e2e[key]
+        out.update(e2e_extra)
+    if sustained is not None:
+        st = torch.tensor([sustained["ms"]], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        ms_s = float(st.item()) / sustained["steps"]
+        out["sustained"] = {"steps": sustained["steps"], "seconds": float(st.item()) * 1e-3, "ms_per_step": ms_s,
+                            "value": all_positions / (ms_s * 1e-3) / 1e9, "unit": "Gpos/s"}
+    if sweep is not None:
+        for row in sweep:
+            row["value_rank0"] = positions / (row["ms_per_step"] * 1e-3) / 1e9
+        out["threshold_sweep_rank0"] = sweep
+    out["consistency_timed_region_s"] = ms_total * 1e-3
     if wl == "c5":
         check(lib.rs_set_batched_path(0))
     return out
+
+
+def e2e_c4(args, dev, shard, h_codes, tables, absmax, hits_dev, all_reduce, barrier, ctx, full):
+    """End-to-end legs of config 4: HOST buffers in, host hit arrays out, copies inside the timed region.
+
+    e2e       the rows as a profile pack holds them (rnascan_b200/pack.py): 8-byte quantised filter rows (symbol
+              included) in pinned memory + the exact rows in ordinary host memory; device.HostProfileScanner sends
+              only the filter form over the link (8 B/position), counts the background in the same pass, gathers the
+              exact rows of the candidates on the host and resolves them on the device -- same hits as the
+              device-resident scan (checked).
+    e2e_f32   round 1's pipeline for comparison (float32 rows over the link, 29 B/position), on a prefix.
+    e2e_api   the public scan API: rnascan_b200.rnascan.scan_main(<directory with a pack>) on a prefix."""
+    import torch
+    rank, world, device = ctx
+    n, prof, lengths, offsets = shard["n"], shard["prof"], shard["lengths"], shard["offsets"]
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k2 = max(2, min(args.steps, 3))
+    extra = {}
+
+    # the parsed input on the host: exact rows (float32-representable by construction, SURVEY.md 8d) ...
+    t0 = time.perf_counter()
+    rows_host = np.empty((n, 7), np.float32)
+    bounce = torch.empty((1 << 23, 7), dtype=torch.float32).pin_memory()
+    for a in range(0, n, 1 << 23):
+        b = min(n, a + (1 << 23))
+        bounce[:b - a].copy_(prof[a:b])
+        rows_host[a:b] = bounce[:b - a].numpy()
+    del bounce
+    codes_np = h_codes.numpy()[:n]
+    # ... and their filter form (what `rnascan --pack` leaves on disk), built by the product's host quantiser
+    hp = dev.HostProfile(rows_host)
+    q8 = torch.empty((n, 8), dtype=torch.uint8).pin_memory()
+    if not hp.make_q8(codes_np, out=q8.numpy()):
+        raise SystemExit("synthetic rows do not fit the quantised form")
+    prep_s = time.perf_counter() - t0
+    tq = tables(np.zeros(8, np.int64))[1]
+    seq_fn = lambda c: tables(c)[0]
+    sc = dev.HostProfileScanner(n, W_MOTIF, "q8", device=device)
+    ar = all_reduce if world > 1 else None
+
+    def run():
+        return sc.run(None, q8, rows_host, tq, seq_fn, THRESHOLD, absmax, q8_scale=hp.q8_scale, all_reduce=ar)
+    res = run()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(k2):
+        res = run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k2
+    if hits_dev is not None and len(res[0]) != hits_dev:
+        raise SystemExit("e2e hit count %d != device-resident hit count %d" % (len(res[0]), hits_dev))
+    e2e = {"ms": ms, "h2d": sc.h2d_bytes, "d2h": sc.d2h_bytes, "hits": int(len(res[0])),
+           "api": "rnascan_b200.device.HostProfileScanner.run: pinned 8-byte quantised rows (7 channels + symbol) -> "
+                  "device filter (+ background counts) -> candidate positions -> host gather of the exact rows -> "
+                  "device resolve -> host hit arrays",
+           "candidates": sc.n_candidates, "filter_pass": sc.n_filter_pass, "launches": sc.launches,
+           "host_prep_s_untimed": prep_s}
+    del sc, q8
+    if not full:
+        return e2e, extra
+
+    # ---- round 1's float32 pipeline on a prefix, for comparison
+    n_pre = min(n, OTHERS_N)
+    ends = offsets + lengths
+    k_full = int(np.searchsorted(ends, n_pre, side="right"))
+    pos_pre = int(np.maximum(lengths[:k_full] - W_MOTIF + 1, 0).sum())
+    if k_full < len(lengths):
+        pos_pre += max(0, n_pre - int(offsets[k_full]) - W_MOTIF + 1) if offsets[k_full] < n_pre else 0
+    h_prof = torch.empty((n_pre, 7), dtype=torch.float32).pin_memory()
+    h_prof.copy_(prof[:n_pre])
+    torch.cuda.synchronize()
+    pipe = dev.HostFusedScanner(n_pre, W_MOTIF, device=device)
+    for _ in range(2):
+        pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        pipe.run(h_codes, h_prof, tables, THRESHOLD, absrow_max=absmax)
+    torch.cuda.synchronize()
+    ms32 = (time.perf_counter() - t0) * 1e3 / k2
+    extra["e2e_f32"] = {"value": pos_pre / (ms32 * 1e-3) / 1e9, "unit": "Gpos/s", "symbols": n_pre,
+                        "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms32,
+                        "api": "rnascan_b200.device.HostFusedScanner.run (float32 rows over the link, round 1's e2e)"}
+    del h_prof, pipe
+
+    # ---- the public API on a directory that holds a profile pack
+    if world == 1 and not args.no_api:
+        try:
+            extra["e2e_api"] = e2e_api(dev, rows_host, lengths, offsets, tq, prof, device)
+        except Exception as exc:                       # reported, never fatal for the bench line
+            extra["e2e_api"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return e2e, extra
+
+
+def e2e_api(dev, rows_host, lengths, offsets, tq, prof, device, target_rows=32_000_000):
+    """rnascan_b200.rnascan.scan_main(directory) -- the reference's own entry point (rnascan.py:335-413) -- on a
+    directory whose averaged profiles are present as a pack (what a first `rnascan --pack` run leaves behind):
+    map the pack, send the quantised rows, gather + resolve, build the result frame.  Hits are checked against
+    the device-resident structure-only scan of the same rows."""
+    import argparse as ap
+    import shutil
+    import tempfile
+    import torch
+    from rnascan_b200 import pack, rnascan as ms
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    from rnascan_b200.BioAddons.motifs import matrix
+    k = max(1, int(np.searchsorted(offsets + lengths, target_rows, side="right")))
+    k = min(k, len(lengths))
+    m = int(offsets[k - 1] + lengths[k - 1] + 1)
+    rows64 = rows_host[:m].astype(np.float64)
+    hp = dev.HostProfile(rows64)
+    sep = np.zeros(m, np.uint8)
+    sep[offsets[:k] + lengths[:k]] = 0xFF
+    if not hp.make_q8(sep):
+        raise RuntimeError("rows do not fit the quantised form")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="rnascan_b200_bench_", dir=base)
+    try:
+        t0 = time.perf_counter()
+        pack.write(tmp, None, rows64, lengths[:k], hp.stats(), hp.q8, hp.q8_scale,
+                   names=["structure.rec%d.txt" % i for i in range(k)])
+        write_s = time.perf_counter() - t0
+        del rows64, hp
+        alphabet = ContextualSecondaryStructure()
+        pssm = {"bench_struct": matrix.ExtendedPositionSpecificScoringMatrix(
+            alphabet, {l: tq[:, "BEHLMRT".index(l)].tolist() for l in alphabet.letters})}
+        ns = ap.Namespace(minscore=THRESHOLD, debug=False, pack=False)
+        positions = int(np.maximum(lengths[:k] - W_MOTIF + 1, 0).sum())
+        frame = ms.scan_main(tmp, pssm, alphabet, None, ns)
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            frame = ms.scan_main(tmp, pssm, alphabet, None, ns)
+            times.append(time.perf_counter() - t0)
+        # the same rows, device-resident, structure only
+        st = dev.SymbolStream.__new__(dev.SymbolStream)
+        codes = torch.zeros(dev.padded_count(m), dtype=torch.uint8, device=device)
+        codes[torch.from_numpy(offsets[:k] + lengths[:k]).to(device)] = 0xFF
+        codes[m:] = 0xFF
+        st.codes, st.n, st.kind = codes, m, None
+        st.offsets, st.lengths = offsets[:k], lengths[:k]
+        pf = dev.ProfileStream.from_device(prof, m)
+        pos, _, sc = dev.scan_fused(st, pf, None, tq, THRESHOLD)
+        same = (len(frame) == len(pos) and
+                np.array_equal(np.asarray(frame["LogOdds"], np.float64).view(np.uint64), sc.view(np.uint64)))
+        if not same:
+            raise RuntimeError("scan_main over the pack found %d hits, the device-resident scan %d (or scores differ)"
+                               % (len(frame), len(pos)))
+        sec = float(np.median(times))
+        return {"value": positions / sec / 1e9, "unit": "Gpos/s", "ms_per_call": sec * 1e3, "symbols": m, "records": k,
+                "hits": int(len(frame)), "pack_bytes": os.path.getsize(pack.pack_path(tmp)), "pack_write_s": write_s,
+                "pack_on": "tmpfs" if base else "disk",
+                "api": "rnascan_b200.rnascan.scan_main(<directory holding rnascan_b200.pack>, pssm, alphabet, None, args): "
+                       "map the pack -> quantised rows to the device -> filter -> gather exact float64 rows -> resolve "
+                       "-> result DataFrame; identical hits and scores to the device-resident scan (checked)"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 # ----------------------------------------------------------------------------- CPU legs
@@ -695,7 +918,7 @@ def run_reference(args):
     from oracle import ref_driver
     wl = args.workload
     cores = os.cpu_count() or 1
-    tables = make_tables_fn(wl)
+    tables = make_tables_fn(wl, pure_python=True)       # the CUDA library is never loaded in this process
     target_s = float(os.environ.get("RNASCAN_REF_STEP_SECONDS", "5"))
     # size the per-step sample from a calibration pass through the SAME Pool fan-out (load imbalance
     # between records included), so that one step takes about target_s seconds on this box
@@ -759,12 +982,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
-    ap.add_argument("--n-per-gpu", type=int, default=125_000_000, dest="n_per_gpu")
+    ap.add_argument("--n-total", type=int, default=1_000_000_000, dest="n_total",
+                    help="symbols of the whole job, split evenly over the GPUs (config 4: 1 Gnt)")
+    ap.add_argument("--n-per-gpu", type=int, default=0, dest="n_per_gpu",
+                    help="fix the per-GPU share instead (weak scaling)")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, dest="sustain_seconds",
+                    help="after the K timed steps, keep stepping for this long and report it as `sustained`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e",
                     help="skip the host-buffer end-to-end leg (e.g. for shards too large to pin on the host)")
     ap.add_argument("--serial-bg", action="store_true", dest="serial_bg",
                     help="c4/c2: histogram -> host tables -> scan, strictly in sequence (no overlap)")
+    ap.add_argument("--no-sweep", action="store_true", dest="no_sweep", help="skip the threshold sweep (c4)")
+    ap.add_argument("--no-api", action="store_true", dest="no_api", help="skip the scan_main(pack directory) leg")
     ap.add_argument("--no-others", action="store_true", dest="no_others",
                     help="skip the brief runs of the other configurations (other_workloads)")
     ap.add_argument("--c5-path", default="auto", choices=["auto", "cuda", "tensor"], dest="c5_path")

@@ -133,6 +133,15 @@ extern "C" int rs_host_rows_to_f32(const double *rows, int64_t n_values, float *
     return RS_OK;
 }
 
+extern "C" int rs_host_copy(void *dst, const void *src, int64_t n_bytes, int threads)
+{
+    if ((!dst || !src) && n_bytes > 0) { rs_set_error("rs_host_copy: null buffer"); return RS_ERR_INVALID; }
+    parallel_blocks(n_bytes, threads, (int64_t)1 << 22, [&](int64_t lo, int64_t hi) {
+        memcpy((char *)dst + lo, (const char *)src + lo, (size_t)(hi - lo));
+    });
+    return RS_OK;
+}
+
 extern "C" int rs_host_quantize_q8(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes, double scale,
                                    uint8_t *out_rows8, int threads, int64_t *n_out_of_range)
 {

@@ -841,7 +841,7 @@ class HostProfileScanner(object):
         self.codes = None if form == "q8" else torch.empty(padded_count(self.n) + 1024, dtype=torch.uint8,
                                                            device=self.device)
         self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
-        self.counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.counts_host = torch.zeros(8, dtype=torch.int64, pin_memory=True)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.loaded = [torch.cuda.Event() for _ in range(2)]
         self.freed = [torch.cuda.Event() for _ in range(2)]
@@ -855,7 +855,7 @@ class HostProfileScanner(object):
         k = max(len(self.starts), 1)
         self.cand = torch.empty((k, self.cap), dtype=torch.int64, device=self.device)
         self.cand_counters = torch.zeros((k, 2), dtype=torch.int64, device=self.device)
-        self.cand_counters_host = torch.zeros((k, 2), dtype=torch.int64).pin_memory()
+        self.cand_counters_host = torch.zeros((k, 2), dtype=torch.int64, pin_memory=True)
         self.work_bytes = int(lib.rs_filter_workspace_bytes(self.chunk + self.W + 256, self.cap))
         self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=self.device)
 
@@ -868,7 +868,7 @@ class HostProfileScanner(object):
             piece = src[c0:c0 + rows]
         else:                                       # numpy / memmap: through pinned staging (and, for float64
             if self.stage is None:                  # rows, the conversion to the float32 shadow on the way)
-                self.stage = [torch.empty((self.rows_max, self.cols), dtype=self.tdt).pin_memory()
+                self.stage = [torch.empty((self.rows_max, self.cols), dtype=self.tdt, pin_memory=True)
                               for _ in range(2)]
             if k >= 2:
                 self.loaded[slot].synchronize()     # the previous copy out of this staging buffer is done
@@ -877,6 +877,8 @@ class HostProfileScanner(object):
             if part.dtype == np.float64:
                 part = np.ascontiguousarray(part)
                 check(lib.rs_host_rows_to_f32(part.ctypes.data, rows * self.cols, st.ctypes.data, HOST_THREADS))
+            elif part.flags["C_CONTIGUOUS"] and part.dtype == st.dtype:
+                check(lib.rs_host_copy(st.ctypes.data, part.ctypes.data, part.nbytes, HOST_THREADS))
             else:
                 np.copyto(st[:rows], part)
             piece = self.stage[slot][:rows]
@@ -987,8 +989,8 @@ class HostProfileScanner(object):
         for a in range(0, len(cand), self.RESOLVE_BATCH):
             part = np.ascontiguousarray(cand[a:a + self.RESOLVE_BATCH])
             k = len(part)
-            h_rows = torch.empty((k, W, len(CHANNELS)), dtype=ftype).pin_memory()
-            h_codes = torch.empty((k, W), dtype=torch.uint8).pin_memory()
+            h_rows = torch.empty((k, W, len(CHANNELS)), dtype=ftype, pin_memory=True)
+            h_codes = torch.empty((k, W), dtype=torch.uint8, pin_memory=True)
             check(lib.rs_host_gather_windows(exact_rows.ctypes.data, dtype, exact_rows.shape[0], code_ptr, code_stride,
                                              part.ctypes.data, k, W, h_rows.numpy().ctypes.data,
                                              h_codes.numpy().ctypes.data, HOST_THREADS))
@@ -1019,7 +1021,7 @@ class HostProfileScanner(object):
         return pos, sq, st
 
 
-def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 23, form=None,
+def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 21, form=None,
                       return_scanner=False):
     """Averaged-profile scan of host-resident rows (a HostProfile) through the filter + gather + resolve
     path; same results as scan_fused(SymbolStream(codes), ProfileStream(hp.rows), ...).  `codes`: uint8[n]

@@ -1,0 +1,146 @@
+"""Binary pack of a directory of averaged-structure profiles.
+
+The reference re-parses every ``structure.<id>.txt`` with pandas on each run
+(/root/reference/rnascan/rnascan.py:296-297, :351).  With the scan itself at hundreds of Gpos/s the text
+is the whole cost of a run, so a scan may leave ``<dir>/rnascan_b200.pack`` behind (``rnascan --pack``)
+and later scans map it instead of parsing:
+
+    bytes 0..7    magic  b"RSB200P1"
+    bytes 8..15   little-endian uint64: length H of the JSON header that follows
+    JSON header   {"version", "n_rows", "files": [[basename, size, mtime_ns, rows, row_offset], ...],
+                   "stats": [max_abs_row_sum, n_nonfinite, n_negative, max_abs_value],
+                   "q8_scale": float | null, "off_q8", "off_rows"}
+    off_q8        uint8  [n_rows][8]   quantised filter rows (include/rnascan_b200.h, RS_ROWS_Q8); byte 7 is
+                                       0, or 0xFF on the separator row that follows every profile; absent
+                                       (q8_scale null) when the rows do not fit the form
+    off_rows      float64[n_rows][7]   the exact rows, bit-identical to what pandas parses, B,E,H,L,M,R,T
+
+Both sections start at multiples of 4096 and are read through ``numpy.memmap``: a scan touches all of the
+8-byte rows (they are what travels to the device) and only the candidate windows of the 56-byte ones.
+A pack is used only if it lists exactly the directory's current files (same order, size and mtime).
+"""
+import json
+import os
+import struct
+
+import numpy as np
+
+MAGIC = b"RSB200P1"
+NAME = "rnascan_b200.pack"
+ALIGN = 4096
+VERSION = 1
+
+
+class ProfilePack(object):
+    def __init__(self, path, header, q8, rows):
+        self.path, self.header = path, header
+        self.q8, self.rows = q8, rows
+        files = header["files"]
+        self.names = [f[0] for f in files]
+        self.lengths = np.array([f[3] for f in files], np.int64)
+        self.offsets = np.array([f[4] for f in files], np.int64)
+        self.q8_scale = header.get("q8_scale")
+        self.stats = tuple(header["stats"])
+        self.n_rows = int(header["n_rows"])
+
+
+def pack_path(directory):
+    return os.path.join(directory, NAME)
+
+
+def _roundup(x):
+    return (x + ALIGN - 1) // ALIGN * ALIGN
+
+
+def _file_entries(files, lengths, offsets):
+    out = []
+    for path, rows, off in zip(files, lengths.tolist(), offsets.tolist()):
+        if path is None or not os.path.exists(path):
+            out.append([os.path.basename(path) if path else "", -1, -1, int(rows), int(off)])
+        else:
+            st = os.stat(path)
+            out.append([os.path.basename(path), int(st.st_size), int(st.st_mtime_ns), int(rows), int(off)])
+    return out
+
+
+def write(directory, files, packed_rows, lengths, stats, q8=None, q8_scale=None, names=None):
+    """Write the pack of `files` (paths, in scan order; or `names` alone for a pack that stands for the
+    text files) whose rows are `packed_rows` (sum L + len(files), 7) float64 with a zero separator row
+    after each profile.  Written to a temporary name and renamed, so readers never see a partial pack."""
+    lengths = np.asarray(lengths, np.int64)
+    offsets = np.zeros(len(lengths), np.int64)
+    if len(lengths) > 1:
+        np.cumsum(lengths[:-1] + 1, out=offsets[1:])
+    n_rows = int(packed_rows.shape[0])
+    if names is not None:
+        entries = [[str(nm), -1, -1, int(r), int(o)] for nm, r, o in zip(names, lengths.tolist(), offsets.tolist())]
+    else:
+        entries = _file_entries(files, lengths, offsets)
+    header = {"version": VERSION, "n_rows": n_rows, "files": entries, "stats": [float(v) for v in stats],
+              "q8_scale": None if q8 is None else float(q8_scale), "off_q8": 0, "off_rows": 0}
+    # two passes: the offsets are part of the header whose length they depend on
+    for _ in range(3):
+        blob = json.dumps(header).encode("utf-8")
+        off_q8 = _roundup(16 + len(blob))
+        off_rows = _roundup(off_q8 + (n_rows * 8 if q8 is not None else 0))
+        if header["off_q8"] == off_q8 and header["off_rows"] == off_rows:
+            break
+        header["off_q8"], header["off_rows"] = off_q8, off_rows
+    blob = json.dumps(header).encode("utf-8")
+    path = pack_path(directory)
+    tmp = path + ".tmp.%d" % os.getpid()
+    with open(tmp, "wb") as fh:
+        fh.write(MAGIC)
+        fh.write(struct.pack("<Q", len(blob)))
+        fh.write(blob)
+        if q8 is not None:
+            fh.seek(header["off_q8"])
+            np.ascontiguousarray(q8, np.uint8).tofile(fh)
+        fh.seek(header["off_rows"])
+        np.ascontiguousarray(packed_rows, np.float64).tofile(fh)
+    os.replace(tmp, path)
+    return path
+
+
+def read(directory):
+    """The pack of `directory` (memory-mapped) or None when there is none / it is not readable."""
+    path = pack_path(directory)
+    try:
+        with open(path, "rb") as fh:
+            if fh.read(8) != MAGIC:
+                return None
+            (hlen,) = struct.unpack("<Q", fh.read(8))
+            if hlen > (1 << 31):
+                return None
+            header = json.loads(fh.read(hlen).decode("utf-8"))
+        if header.get("version") != VERSION:
+            return None
+        n_rows = int(header["n_rows"])
+        size = os.path.getsize(path)
+        if header["off_rows"] + n_rows * 56 > size:
+            return None
+        rows = np.memmap(path, dtype=np.float64, mode="r", offset=header["off_rows"], shape=(n_rows, 7)) \
+            if n_rows else np.zeros((0, 7), np.float64)
+        q8 = None
+        if header.get("q8_scale") is not None and n_rows:
+            q8 = np.memmap(path, dtype=np.uint8, mode="r", offset=header["off_q8"], shape=(n_rows, 8))
+        return ProfilePack(path, header, q8, rows)
+    except (OSError, ValueError, KeyError, struct.error):
+        return None
+
+
+def matches(pack, files):
+    """Does the pack describe exactly these files (same order, sizes and modification times)?"""
+    entries = pack.header["files"]
+    if len(entries) != len(files):
+        return False
+    for (name, size, mtime, _, _), path in zip(entries, files):
+        if name != os.path.basename(path):
+            return False
+        try:
+            st = os.stat(path)
+        except OSError:
+            return False
+        if size != st.st_size or mtime != st.st_mtime_ns:
+            return False
+    return True

@@ -36,6 +36,41 @@ from .seq import IUPAC, RNAAlphabet, Seq, SeqRecord  # noqa: F401  (re-exported 
 from .version import __version__
 
 HIT_COLUMNS = ["Motif_ID", "Start", "End", "Sequence", "LogOdds"]
+
+
+class _Stats(object):
+    """--stats: where a run's time goes and what the device achieved (the reference has only the tic/toc of
+    rnascan.py:569-575).  Phases are wall-clock seconds on the host; `kernel_ms` are the durations of the main
+    scan kernels measured with CUDA events inside the library (rs_prof_begin / rs_prof_end)."""
+
+    def __init__(self):
+        self.on = False
+        self.phases = defaultdict(float)
+        self.counts = defaultdict(int)
+        self.notes = {}
+
+    def reset(self, on):
+        self.__init__()
+        self.on = bool(on)
+
+    class _Timer(object):
+        def __init__(self, stats, name):
+            self.stats, self.name = stats, name
+
+        def __enter__(self):
+            self.t0 = time.perf_counter()
+
+        def __exit__(self, *exc):
+            self.stats.phases[self.name] += time.perf_counter() - self.t0
+
+    def phase(self, name):
+        return self._Timer(self, name)
+
+    def add(self, name, value):
+        self.counts[name] += int(value)
+
+
+STATS = _Stats()
 MAX_BATCH_SYMBOLS = 1 << 30          # symbols per device batch when scanning a FASTA file
 
 
@@ -73,6 +108,13 @@ def getoptions(argv=None):
                         help="Load file of pre-computed background probabilities for nucleotide sequences")
     bg_grp.add_argument("-B", "--bg_struct", default=None, dest="bg_struct",
                         help="Load file of pre-computed background probabilities for structure contexts")
+    parser.add_argument("--pack", action="store_true", default=False, dest="pack",
+                        help="(rnascan_b200) After parsing a directory of averaged structure profiles, leave "
+                             "a binary pack (rnascan_b200.pack) in it; later scans of the unchanged directory "
+                             "map the pack instead of parsing the text [%(default)s]")
+    parser.add_argument("--stats", dest="stats", default=None, metavar="FILE",
+                        help="(rnascan_b200) Write one JSON line with the run's phase times, scored positions, "
+                             "Gpos/s and the device kernels' achieved GB/s to FILE ('-' = STDERR)")
     parser.add_argument("-v", "--version", action="version", version="%(prog)s " + __version__)
     parser.add_argument("-x", "--debug", action="store_true", default=False, dest="debug",
                         help="Reference debug mode (no process pool there; here it only changes the "
@@ -577,10 +619,12 @@ def _scan_batch(batch, pm, kind, minscore):
     """(record index, 0-based start, scores) of all hits in a packed batch."""
     from . import device
     table = _table_for(pm, kind)
-    if kind == "rna":
-        pos, scores = device.scan_seq(batch.stream, table, minscore)
-    else:
-        pos, scores = device.scan_struct_onehot(batch.stream, table, minscore)
+    with STATS.phase("scan_s"):
+        if kind == "rna":
+            pos, scores = device.scan_seq(batch.stream, table, minscore)
+        else:
+            pos, scores = device.scan_struct_onehot(batch.stream, table, minscore)
+    STATS.add("scored_positions", int(np.maximum(batch.stream.lengths - table.shape[0] + 1, 0).sum()))
     keep, rec, start0 = batch.locate(pos)
     return pos[keep], rec[keep], start0[keep], scores[keep]
 
@@ -793,6 +837,52 @@ def _scan_fasta_hits(fasta_file, pssm, alphabet, minscore):
     return hits
 
 
+def _scan_fasta_hits_computed_bg(fasta_file, pfm_file, pseudocount, alphabet, minscore):
+    """compute_background -> load_motif -> scan (rnascan.py:507-521) for a FASTA input whose background is
+    computed from the same data, without idling the device between the three: the decision pass starts from
+    a provisional table the device derives from its own counts while the counts travel to the host, the
+    exact log-odds are built there (Python's math.log, as Biopython does) and the finish pass decides every
+    candidate with them (device.BackgroundOneHotScan; results identical to the serial order).
+    Returns (bg, pssm, _Hits), or None when this shape of run takes the serial path."""
+    from . import device
+    kind = _kind_of(alphabet)
+    columns = device.RNA_COLUMNS if kind == "rna" else device.CHANNELS
+    if not np.isfinite(minscore) or any(letter not in columns for letter in alphabet.letters):
+        return None
+    batches = _cached_batches(fasta_file, alphabet)
+    if len(batches) != 1 or batches[0].own is not None or batches[0].stream.n == 0:
+        return None
+    batch = batches[0]
+    try:
+        table = pd.read_csv(pfm_file, sep="\t")
+        counts = table.drop(columns=table.columns[0]).to_dict(orient="list")
+        norm = motifs.normalize_counts(motifs.Motif(alphabet=alphabet, counts=counts).counts, alphabet.letters,
+                                       pseudocount)
+        prob = np.array([norm[c] for c in columns], dtype=np.float64).T.copy()
+    except Exception:
+        return None                       # the serial path reports what is wrong with the PFM
+    if not (1 <= prob.shape[0] <= 16) or not np.isfinite(prob).all():
+        return None
+    state = {}
+
+    def table_fn(counts8):
+        state["bg"] = _background_from_counts(np.asarray(counts8, np.int64), len(batch.ids), alphabet, True)
+        state["pssm"] = load_motif(pfm_file, pseudocount, alphabet, state["bg"])
+        return _table_for(_first_motif(state["pssm"])[1], kind)
+
+    eprint("Calculating background probabilities...")
+    with STATS.phase("scan_s"):
+        pos, scores, _, _ = device.scan_onehot_bg(batch.stream, prob, table_fn, minscore)
+    STATS.add("scored_positions", int(np.maximum(batch.stream.lengths - prob.shape[0] + 1, 0).sum()))
+    motif_id, pm = _first_motif(state["pssm"])
+    eprint("Scanning sequences ")
+    hits = _Hits(motif_id, pm.length, kind)
+    keep, rec, start0 = batch.locate(pos)
+    hits.add(batch, pos[keep], rec[keep], start0[keep], scores[keep])
+    eprint("Processed %d sequences" % hits.n_records)
+    return state["bg"], state["pssm"], hits
+
+
 # one parsed + uploaded input is reused by compute_background and the scan that follows it
 _BATCH_CACHE = {}
 
@@ -806,11 +896,23 @@ def _cache_key(fasta_file, alphabet):
     return (stamp, _kind_of(alphabet), _seq.is_ambiguous_rna_alphabet(alphabet))
 
 
+def _count_input(key, batches):
+    """--stats: every input counts once per run, however often it is looked up."""
+    seen = STATS.notes.setdefault("_inputs", set())
+    if key is None or key not in seen:
+        seen.add(key)
+        STATS.add("symbols", sum(int(b.stream.lengths.sum()) for b in batches))
+        STATS.add("records", sum(len(b.ids) for b in batches))
+
+
 def _cached_batches(fasta_file, alphabet):
     key = _cache_key(fasta_file, alphabet)
     if key is not None and key in _BATCH_CACHE:
+        _count_input(key, _BATCH_CACHE[key])
         return _BATCH_CACHE[key]
-    batches = list(_record_batches(fasta_file, alphabet))
+    with STATS.phase("ingest_fasta_s"):
+        batches = list(_record_batches(fasta_file, alphabet))
+    _count_input(key, batches)
     if key is not None:
         while len(_BATCH_CACHE) >= 2:                      # sequence + structure input of one run
             _BATCH_CACHE.pop(next(iter(_BATCH_CACHE)))
@@ -826,33 +928,77 @@ def _profile_files(directory):
     return structures
 
 
-def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None, want_arrays=False):
-    """All ``structure.<id>.txt`` profiles of a directory in one launch (rnascan.py:348-375).
-    With `seq_batches`/`seq_pm` (combined mode) the sequence PSSM is evaluated in the same
-    kernel and only windows passing BOTH thresholds come back.  Under torchrun every rank
-    takes a contiguous range of files balanced by size; rank 0 assembles the frame."""
+def _load_profile_dir(directory, write_pack=False):
+    """This rank's share of the profiles of a directory as one packed stream:
+    (paths, total number of files, HostProfile, lengths).  A valid ``rnascan_b200.pack`` (pack.py) is
+    mapped instead of parsing the text; `write_pack` leaves one behind after parsing."""
+    from . import device, shard, pack
+    rank, size = shard.world()
+    pk = pack.read(directory)
+    try:
+        files = _profile_files(directory)
+    except IOError:
+        if pk is None:
+            raise
+        files = [os.path.join(directory, nm) for nm in pk.names]        # a pack standing for the text files
+    else:
+        if size > 1:
+            files = shard.broadcast_object(files)      # one canonical order (os.listdir order is per process)
+        if pk is not None and not pack.matches(pk, files):
+            pk = None
+    n_files = len(files)
+    lo, hi = 0, n_files
+    if size > 1:
+        sizes = pk.lengths.tolist() if pk is not None else [os.path.getsize(f) for f in files]
+        mine = [r for (r, a, b, o) in shard.plan_shards(sizes, size, 1)[rank] if a == 0]    # W = 1: whole files
+        lo, hi = (mine[0], mine[-1] + 1) if mine else (0, 0)
+    if pk is not None:
+        lengths = pk.lengths[lo:hi]
+        r0 = int(pk.offsets[lo]) if hi > lo else 0
+        r1 = int(pk.offsets[hi - 1] + pk.lengths[hi - 1] + 1) if hi > lo else 0
+        hp = device.HostProfile(pk.rows[r0:r1], q8=None if pk.q8 is None else pk.q8[r0:r1], q8_scale=pk.q8_scale,
+                                stats=pk.stats)
+        return files[lo:hi], n_files, hp, lengths
+    packed, lengths = _read_profiles_packed(files[lo:hi])
+    hp = device.HostProfile(packed)
+    if write_pack and size == 1 and n_files:
+        sep = np.zeros(packed.shape[0], np.uint8)
+        sep[np.cumsum(lengths + 1) - 1] = device._lib.RS_SEP
+        ok = hp.make_q8(sep)
+        try:
+            pack.write(directory, files, packed, lengths, hp.stats(), hp.q8 if ok else None, hp.q8_scale)
+        except OSError as exc:
+            eprint("Could not write %s: %s" % (pack.pack_path(directory), exc))
+    return files[lo:hi], n_files, hp, lengths
+
+
+def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None, want_arrays=False,
+                      write_pack=False, seq_table_fn=None):
+    """All ``structure.<id>.txt`` profiles of a directory in one pass (rnascan.py:348-375).
+    With `seq_batches`/`seq_pm` (combined mode) the sequence PSSM is evaluated on the same windows and only
+    those passing BOTH thresholds come back (`seq_table_fn(counts)`: the sequence table when its background
+    is computed from the data -- the counts are then taken on the device in the same pass).  The float64
+    rows stay on the host: the device filters a float32 shadow or the pack's 8-byte quantised rows and
+    re-scores the few windows near the threshold from the exact rows (device.scan_profile_host).  Under
+    torchrun every rank takes a contiguous range of files balanced by size; rank 0 assembles the frame."""
     from . import device, shard
     motif_id, pm = _first_motif(pssm)
     tq = _structure_table(pm)
     width = tq.shape[0]
-    files = _profile_files(directory)
-    n_files = len(files)
     rank, size = shard.world()
-    if size > 1:
-        sizes = [os.path.getsize(f) for f in files]
-        plan = shard.plan_shards(sizes, size, 1)[rank]     # W = 1: whole files only
-        files = [files[r] for (r, a, b, o) in plan if a == 0]
-    names = []
-    for path in files:
-        match = re.search(r"^structure\.(.*)\.txt$", os.path.basename(path))
-        names.append(path if debug else match.group(1))
-    packed, lengths = _read_profiles_packed(files)
+    with STATS.phase("ingest_profiles_s"):
+        files, n_files, hp, lengths = _load_profile_dir(directory, write_pack)
+    STATS.add("profile_rows", int(lengths.sum()))
+    STATS.add("profile_files", len(files))
+    STATS.notes["profile_source"] = "pack" if isinstance(hp.rows, np.memmap) else "text"
+    # rnascan.py:299-301: the id is what stands between "structure." and ".txt" (the full path in debug mode)
+    names = list(files) if debug else [os.path.basename(path)[10:-4] for path in files]
     n_prof = len(files)
     offsets = np.zeros(n_prof, np.int64)
     if n_prof > 1:
         np.cumsum(lengths[:-1] + 1, out=offsets[1:])
     codes = np.zeros(int(lengths.sum() + n_prof), np.uint8)
-    seq_table = None
+    seq = None
     if seq_batches is not None:
         # sequence symbols of the record with the same id, aligned row by row; rows beyond the
         # shorter of the two get an invalid symbol (no joint window exists there)
@@ -860,7 +1006,7 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         for batch in seq_batches:
             for rid, text in zip(batch.ids, batch.full_texts):
                 by_id.setdefault(rid, text)
-        seq_table = _table_for(seq_pm, "rna")
+        seq = seq_table_fn if seq_table_fn is not None else _table_for(seq_pm, "rna")
         for k, name in enumerate(names):
             seg = codes[offsets[k]:offsets[k] + lengths[k]]
             seg[:] = device._lib.RS_RNA_OTHER
@@ -872,7 +1018,18 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     if n_prof:
         codes[offsets + lengths] = device._lib.RS_SEP
     if len(codes):
-        pos, seq_scores, scores = device.scan_profile_host(codes, device.HostProfile(packed), seq_table, tq, minscore)
+        if hp.q8 is not None and seq_batches is not None:
+            q8 = np.array(hp.q8)                      # the pack's rows carry no sequence: add the symbols
+            q8[:, 7] = codes
+            hp.q8 = q8
+        with STATS.phase("scan_s"):
+            pos, seq_scores, scores, scanner = device.scan_profile_host(codes, hp, seq, tq, minscore,
+                                                                        return_scanner=True)
+        STATS.add("scored_positions", int(np.maximum(lengths - width + 1, 0).sum()))
+        if scanner is not None:
+            STATS.notes["profile_filter_form"] = scanner.form
+            STATS.add("h2d_bytes", scanner.h2d_bytes)
+            STATS.add("candidates", scanner.n_candidates)
         rec = np.searchsorted(offsets, pos, side="right") - 1
         start0 = pos - offsets[rec]
     else:
@@ -881,7 +1038,7 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         seq_scores = None
     hit_names = [names[r] for r in rec.tolist()]
     arrays = None
-    if want_arrays and size == 1 and seq_table is not None:
+    if want_arrays and size == 1 and seq is not None:
         arrays = (list(hit_names), start0.copy(), np.zeros(0, np.float32) if seq_scores is None else seq_scores,
                   np.asarray(scores, np.float64))
     if size > 1:
@@ -915,7 +1072,8 @@ def scan_main(fasta_file, pssm, alphabet, bg, args):
         final = final[cols[-2:] + cols[:-2]]
     elif os.path.isdir(fasta_file):
         eprint("Scanning averaged secondary structures ")
-        final, count = _scan_profile_dir(fasta_file, pssm, args.minscore, args.debug)
+        final, count = _scan_profile_dir(fasta_file, pssm, args.minscore, args.debug,
+                                         write_pack=getattr(args, "pack", False))
     else:
         eprint("Scanning sequences ")
         final, count = _scan_fasta(fasta_file, pssm, alphabet, args.minscore)
@@ -961,6 +1119,13 @@ def compute_background(fastas, alphabet, verbose=True):
         counts += device.histogram(batch.stream).cpu().numpy() - batch.overlap_counts()
         n_records += len(batch.ids)
     counts = _allreduce_counts(counts)
+    return _background_from_counts(counts, n_records, alphabet, verbose)
+
+
+def _background_from_counts(counts, n_records, alphabet, verbose=True):
+    """(count + 1) / (total + |alphabet|) per letter, messages and checks of rnascan.py:454-465."""
+    from . import device
+    columns = device.RNA_COLUMNS if _kind_of(alphabet) == "rna" else device.CHANNELS
     content = defaultdict(int)
     total = len(alphabet.letters)
     if n_records:
@@ -1065,7 +1230,8 @@ def _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args):
     if os.path.isdir(struct_file):
         eprint("Scanning averaged secondary structures ")
         frame, count, arrays = _scan_profile_dir(struct_file, struct_pssm, args.minscore, args.debug,
-                                                 seq_batches=seq_batches, seq_pm=seq_pm, want_arrays=True)
+                                                 seq_batches=seq_batches, seq_pm=seq_pm, want_arrays=True,
+                                                 write_pack=getattr(args, "pack", False))
         eprint("Processed %d sequences" % count)
         joint.struct_frame = lambda: frame
         if arrays is None or len(seq_batches) != 1 or _world_size() > 1:
@@ -1092,7 +1258,9 @@ def _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args):
     ts, tq = _table_for(seq_pm, "rna"), _table_for(pm, "struct")
     parts, n_records = [], 0
     for sb, qb in zip(seq_batches, struct_batches):
-        pos, seq_sc, scores = device.scan_pair_onehot(sb.stream, qb.stream, ts, tq, args.minscore)
+        with STATS.phase("scan_s"):
+            pos, seq_sc, scores = device.scan_pair_onehot(sb.stream, qb.stream, ts, tq, args.minscore)
+        STATS.add("scored_positions", int(np.maximum(qb.stream.lengths - width + 1, 0).sum()))
         keep, rec, start0 = qb.locate(pos)
         pos = pos[keep]
         parts.append((rec[keep] + n_records, start0[keep], scores[keep], _fragments(qb.raw(), pos, width)
@@ -1135,6 +1303,10 @@ def main(argv=None):
     from . import shard
     rank, _ = shard.init()                # joins the torchrun rendezvous if there is one
     args = getoptions(argv)
+    STATS.reset(args.stats)
+    if STATS.on:
+        from . import _lib
+        _lib.lib.rs_prof_begin(4096)
     seq_type = _guess_seq_type(args)
     bg = None
     seq_file = struct_file = None
@@ -1152,18 +1324,25 @@ def main(argv=None):
             seq_file = SeqRecord(Seq(testseq_stack.pop()))
         else:
             seq_file = args.fastafiles[0]
-            bg = load_background(args.bg_seq, args.uniform_background, seq_file, rna, not args.bgonly)
+            if (arrays_ok and not args.bgonly and not args.bg_seq and not args.uniform_background
+                    and not os.path.isdir(seq_file)):
+                fused = _scan_fasta_hits_computed_bg(seq_file, args.pfm_seq, args.pseudocount, rna, args.minscore)
+                if fused is not None:
+                    bg, seq_pssm, seq_hits = fused
+            if seq_hits is None:
+                bg = load_background(args.bg_seq, args.uniform_background, seq_file, rna, not args.bgonly)
         if args.bgonly:
             if rank == 0:
                 print(dict(bg))
             sys.exit()
-        seq_pssm = load_motif(args.pfm_seq, args.pseudocount, rna, bg)
-        if arrays_ok and not os.path.isdir(seq_file):
-            eprint("Scanning sequences ")
-            seq_hits = _scan_fasta_hits(seq_file, seq_pssm, rna, args.minscore)
-            eprint("Processed %d sequences" % seq_hits.n_records)
-        else:
-            seq_results = scan_main(seq_file, seq_pssm, rna, bg, args)
+        if seq_hits is None:              # else: background, motif and scan were done in one overlapped pass
+            seq_pssm = load_motif(args.pfm_seq, args.pseudocount, rna, bg)
+            if arrays_ok and not os.path.isdir(seq_file):
+                eprint("Scanning sequences ")
+                seq_hits = _scan_fasta_hits(seq_file, seq_pssm, rna, args.minscore)
+                eprint("Processed %d sequences" % seq_hits.n_records)
+            else:
+                seq_results = scan_main(seq_file, seq_pssm, rna, bg, args)
 
     if seq_type in ["SS", "RNASS"]:
         structure = ContextualSecondaryStructure()
@@ -1173,17 +1352,24 @@ def main(argv=None):
             struct_file = args.fastafiles[0]
         else:
             struct_file = args.fastafiles[1]
-        if not args.testseq:
+        if (seq_type == "SS" and arrays_ok and not args.bgonly and not args.bg_struct
+                and not args.uniform_background and not os.path.isdir(struct_file)):
+            fused = _scan_fasta_hits_computed_bg(struct_file, args.pfm_struct, args.pseudocount, structure,
+                                                 args.minscore)
+            if fused is not None:
+                bg, struct_pssm, struct_hits = fused
+        if not args.testseq and struct_hits is None:
             bg = load_background(args.bg_struct, args.uniform_background, struct_file, structure,
                                  not args.bgonly)
         if args.bgonly:
             if rank == 0:
                 print(dict(bg))
             sys.exit()
-        struct_pssm = load_motif(args.pfm_struct, args.pseudocount, structure, bg)
+        if struct_hits is None:
+            struct_pssm = load_motif(args.pfm_struct, args.pseudocount, structure, bg)
         if seq_type == "RNASS" and not args.testseq:
             joint = _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args)
-        if joint is None:
+        if joint is None and struct_hits is None:
             if seq_type == "SS" and arrays_ok and not os.path.isdir(struct_file):
                 eprint("Scanning sequences ")
                 struct_hits = _scan_fasta_hits(struct_file, struct_pssm, structure, args.minscore)
@@ -1191,6 +1377,7 @@ def main(argv=None):
             else:
                 struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
 
+    t_out = time.perf_counter()
     if rank == 0:
         written = False
         if seq_type == "RNASS":
@@ -1221,10 +1408,49 @@ def main(argv=None):
         joint.struct_frame()              # other ranks take part in the gather
 
     runtime = float(time.time() - tic)
+    if STATS.on:
+        STATS.phases["output_s"] = time.perf_counter() - t_out
+        _write_stats(args.stats, seq_type, runtime)
     if runtime > 60:
         eprint("Done in %0.4f minutes!" % (runtime / 60))
     else:
         eprint("Done in %0.4f seconds!" % (runtime))
+
+
+def _write_stats(dest, seq_type, runtime):
+    """One JSON line: phases, sizes, throughput.  `device_GBps` relates the bytes the scan kernels have to read
+    at least (1 B per symbol; + 28 B per float32 profile row or 8 B per quantised row altogether) to the time
+    their main kernels took."""
+    import json
+    from . import _lib
+    kms = np.zeros(4096, np.float32)
+    nrec = np.zeros(1, np.int32)
+    _lib.lib.rs_prof_end(kms.ctypes.data, len(kms), nrec.ctypes.data)
+    kernel_ms = float(kms[:int(nrec[0])].sum())
+    c, ph = STATS.counts, STATS.phases
+    positions = c.get("scored_positions", 0)
+    form = STATS.notes.get("profile_filter_form")
+    per_row = {"q8": 8.0, "f32": 29.0, "shadow": 29.0}.get(form, 0.0)
+    dev_bytes = c.get("symbols", 0) * 1.0 + c.get("profile_rows", 0) * per_row
+    out = {"mode": seq_type, "world_size": _world_size(), "total_s": runtime,
+           "phases_s": {k: round(v, 6) for k, v in sorted(ph.items())},
+           "records": c.get("records", 0), "symbols": c.get("symbols", 0), "profile_rows": c.get("profile_rows", 0),
+           "scored_positions": positions,
+           "gpos_per_s_total": positions / runtime / 1e9 if runtime > 0 else None,
+           "gpos_per_s_scan_phase": positions / ph["scan_s"] / 1e9 if ph.get("scan_s") else None,
+           "main_kernel_launches": int(nrec[0]), "main_kernel_ms": kernel_ms,
+           "gpos_per_s_kernels": positions / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None,
+           "device_GBps": dev_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None,
+           "h2d_bytes": c.get("h2d_bytes", 0), "candidates": c.get("candidates", 0)}
+    out.update({k: v for k, v in STATS.notes.items() if not k.startswith("_")})
+    line = json.dumps(out) + "\n"
+    if _rank() != 0:
+        return
+    if dest == "-":
+        sys.stderr.write(line)
+    else:
+        with open(dest, "a") as fh:
+            fh.write(line)
 
 
 if __name__ == "__main__":

@@ -74,6 +74,19 @@ def gather_objects(obj, dst=0):
     return out if dist.get_rank() == dst else None
 
 
+def broadcast_object(obj, src=0):
+    """Rank `src`'s `obj` on every rank (identity without a group)."""
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return obj
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return obj
+    box = [obj if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def plan_shards(lengths, n_ranks, W):
     """Partition records over ranks by total length.
 

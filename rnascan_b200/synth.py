@@ -7,7 +7,8 @@ variant of `profile_rows` for device-side generation of the large profile stream
 """
 import numpy as np
 
-from . import _lib
+RS_SEP, RS_RNA_OTHER = 0xFF, 0x0C          # include/rnascan_b200.h (kept literal: importing this module must
+                                          # not load the CUDA library -- bench.py's reference arm uses it)
 
 RNA_P = (0.27, 0.22, 0.22, 0.29)                       # p(A, C, G, U)
 # stationary structure-context distribution = example/3p_UTR_background_structural_context.txt
@@ -49,8 +50,8 @@ def rna_codes(lengths, rng, n_frac=0.001):
         starts = rng.integers(0, n, size=n_runs)
         runlen = rng.integers(1, 51, size=n_runs)
         for s, r in zip(starts.tolist(), runlen.tolist()):
-            codes[s:s + r] = _lib.RS_RNA_OTHER
-    codes[offsets + np.asarray(lengths, np.int64)] = _lib.RS_SEP
+            codes[s:s + r] = RS_RNA_OTHER
+    codes[offsets + np.asarray(lengths, np.int64)] = RS_SEP
     return codes, offsets
 
 
@@ -66,7 +67,7 @@ def struct_codes(lengths, rng, stay=0.8):
     np.minimum(draws, 6, out=draws)
     idx = np.cumsum(change) - 1
     codes = draws[idx]
-    codes[offsets + np.asarray(lengths, np.int64)] = _lib.RS_SEP
+    codes[offsets + np.asarray(lengths, np.int64)] = RS_SEP
     return codes, offsets
 
 
@@ -111,11 +112,11 @@ def pssm_table(pfm, background=None, pseudocount=0.01):
 
 _RNA_TEXT = np.full(256, ord("N"), np.uint8)
 _RNA_TEXT[:4] = np.frombuffer(b"ACGU", np.uint8)
-_RNA_TEXT[_lib.RS_SEP] = ord("\n")
+_RNA_TEXT[RS_SEP] = ord("\n")
 _SS_TEXT = np.full(256, ord("X"), np.uint8)
 _SS_TEXT[:7] = np.frombuffer(b"BEHLMRT", np.uint8)
 _SS_TEXT[8:15] = np.frombuffer(b"behlmrt", np.uint8)
-_SS_TEXT[_lib.RS_SEP] = ord("\n")
+_SS_TEXT[RS_SEP] = ord("\n")
 
 
 def to_text(codes, kind):

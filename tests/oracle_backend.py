@@ -124,16 +124,7 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     return out + (0,) if return_stats else out
 
 
-class FakeHostProfile(object):
-    def __init__(self, rows, q8=None, q8_scale=None, stats=None):
-        rows = np.ascontiguousarray(rows)
-        if rows.dtype not in (np.float32, np.float64):
-            rows = rows.astype(np.float64)
-        self.rows, self.n = rows, rows.shape[0]
-        self.q8, self.q8_scale = q8, q8_scale
-
-
-def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 23, form=None,
+def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 21, form=None,
                       return_scanner=False):
     if codes is None:
         codes = np.zeros(hp.n, np.uint8)
@@ -144,13 +135,21 @@ def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, 
     return out + (None,) if return_scanner else out
 
 
+def scan_onehot_bg(stream, prob, table_fn, threshold, all_reduce=None, capacity=None, extra_margin=0.0):
+    counts = histogram(stream).numpy()
+    table = table_fn(counts)
+    fn = scan_seq if (stream.kind or "struct") == "rna" else scan_struct_onehot
+    pos, sc = fn(stream, table, threshold)
+    return pos, sc, counts, 0
+
+
 def install(monkeypatch):
     for name, fn in (("SymbolStream", FakeSymbolStream), ("ProfileStream", FakeProfileStream),
                      ("histogram", histogram), ("dense_seq", dense_seq), ("dense_struct", dense_struct),
                      ("dense_profile", dense_profile), ("scan_seq", scan_seq),
                      ("scan_struct_onehot", scan_struct_onehot), ("scan_pair_onehot", scan_pair_onehot),
-                     ("scan_fused", scan_fused), ("HostProfile", FakeHostProfile),
-                     ("scan_profile_host", scan_profile_host)):
+                     ("scan_fused", scan_fused),
+                     ("scan_profile_host", scan_profile_host), ("scan_onehot_bg", scan_onehot_bg)):
         monkeypatch.setattr(device, name, fn)
     from rnascan_b200 import rnascan as ms
     ms._BATCH_CACHE.clear()

@@ -104,6 +104,74 @@ def test_averaged_combined_native_writer_equals_dataframe_path(in_repo, monkeypa
         assert frames == native and frames.count("\n") > 5
 
 
+def test_profile_pack_gives_identical_output(tmp_path, in_repo):
+    for mode in ("struct", "combined"):
+        _pack_case(tmp_path / mode, mode)
+
+
+def _pack_case(tmp_path, mode):
+    """--pack leaves rnascan_b200.pack in the profile directory; scans of the unchanged directory map it
+    (quantised filter rows + exact float64 rows) and print the same bytes; a changed file invalidates it; a
+    pack can stand for the text files altogether."""
+    import shutil
+    from rnascan_b200 import pack
+    os.makedirs(tmp_path)
+    work = tmp_path / "profiles"
+    shutil.copytree(os.path.join(INP, "profiles_mixed"), work)
+    shutil.copy(os.path.join(INP, "profiles_example", "structure.hg19_dna.txt"), work / "structure.hg19_dna.txt")
+    argv = ["-q", os.path.join(INP, "SLBP_pfm_assembled_normalized_struct.txt"), "-B",
+            os.path.join(INP, "bg_struct_example.txt"), "-m", "2"]
+    if mode == "combined":
+        argv += ["-p", os.path.join(INP, "SLBP_pfm_assembled_normalized_seq.txt"), "-b",
+                 os.path.join(INP, "bg_seq_custom.txt"), os.path.join(INP, "HIST2H3C_3p_end.fa")]
+        argv[argv.index("2")] = " -2"
+    argv += [str(work)]
+    plain, err0, code = run_cli(argv)
+    assert code == 0 and plain.count("\n") > 3
+    assert not os.path.exists(pack.pack_path(str(work)))
+    written, _, _ = run_cli(argv + ["--pack"])
+    pk = pack.read(str(work))
+    assert written == plain and pk is not None and pk.q8 is not None
+    assert sorted(pk.names) == sorted(f for f in os.listdir(work) if f != pack.NAME)
+    mapped, err1, _ = run_cli(argv)
+    assert mapped == plain and err1 == err0
+    # a touched file makes the pack stale: the text is parsed again (same output), --pack refreshes it
+    victim = work / "structure.rec2.txt"
+    os.utime(victim, ns=(1, 1))
+    assert not pack.matches(pack.read(str(work)), [str(work / n) for n in pk.names])
+    assert run_cli(argv + ["--pack"])[0] == plain
+    assert pack.matches(pack.read(str(work)), [str(work / n) for n in pack.read(str(work)).names])
+    # the pack alone
+    for f in os.listdir(work):
+        if f != pack.NAME:
+            os.remove(work / f)
+    alone, _, code = run_cli(argv)
+    assert code == 0 and alone == plain
+
+
+def test_stats_option_writes_one_json_line(tmp_path, in_repo):
+    """--stats FILE: phases, sizes and throughput of the run as one JSON line; stdout is unchanged."""
+    base = CASES["rna_mixed_all"]["argv"]
+    plain = run_cli(base)[0]
+    path = tmp_path / "stats.json"
+    from rnascan_b200 import rnascan as ms
+    ms._BATCH_CACHE.clear()                            # a cached input is not parsed again: no ingest phase
+    out, _, code = run_cli(list(base) + ["--stats", str(path)])
+    assert code == 0 and out == plain
+    lines = path.read_text().splitlines()
+    assert len(lines) == 1
+    st = json.loads(lines[0])
+    assert st["mode"] == "RNA" and st["records"] > 0 and st["symbols"] > 0
+    assert 0 < st["scored_positions"] <= st["symbols"]
+    assert st["total_s"] > 0 and "scan_s" in st["phases_s"] and "ingest_fasta_s" in st["phases_s"]
+    argv = ["-q", os.path.join(INP, "SLBP_pfm_assembled_normalized_struct.txt"), "-B",
+            os.path.join(INP, "bg_struct_example.txt"), "-m", "2", os.path.join(INP, "profiles_mixed"),
+            "--stats", str(path)]
+    assert run_cli(argv)[2] == 0
+    st = json.loads(path.read_text().splitlines()[1])
+    assert st["mode"] == "SS" and st["profile_rows"] > 0 and st["profile_source"] == "text"
+
+
 def test_every_position_structure_scan_through_the_cli(tmp_path, in_repo, oracle):
     """BASELINE config 3 in small: one-hot structure FASTA, -m -inf, every scorable window is a row of
     hits.tab (native writer); rows are rebuilt here from the oracle's dense scores."""
