@@ -645,9 +645,10 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
             }
             S += rowmax;
         }
-        // |sum (bf16(p) - p) * S~| <= 2^-9 * R * S   (p >= 0, S~ >= S entrywise so p*S~ >= p*S);
-        // + fp32 accumulation of 96 products, generous: 2^-16 * R * S
-        const double eps = (ldexp(1.0, -9) + ldexp(1.0, -16)) * R * S * 1.01;
+        // bf16 keeps 8 significant bits, so round-to-nearest (__floats2bfloat162_rn in the converter warps) is off
+        // by up to half an ulp = 2^-8 relative: |sum (bf16(p) - p) * S~| <= 2^-8 * R * S   (p >= 0, S~ >= S
+        // entrywise so p*S~ >= p*S); + fp32 accumulation of 96 products, generous: 2^-16 * R * S
+        const double eps = (ldexp(1.0, -8) + ldexp(1.0, -16)) * R * S * 1.01;
         const double thr_eff = threshold - eps;
         if (!isfinite(thr_eff) || fabs(thr_eff) > 1e30) { rs_set_error("tensor-core path: threshold out of range"); return -1; }
         B[((size_t)0 * TC_N + col) * 8 + 7] = bf16_round_up(-thr_eff);     // bias on the constant-1 channel

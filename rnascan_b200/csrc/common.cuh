@@ -72,6 +72,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
+// Look-back waits (order.cu, kmer_scan.cu) are bounded by WALL time, not by a spin count: a predecessor CTA always
+// runs already (tickets are taken in launch order), so the wait is normally microseconds; under time-slicing, MPS,
+// a debugger or a sanitizer it can legitimately be long, so only a full minute without progress is treated as a
+// lost predecessor (trap: the launch fails instead of hanging the stream for ever).
+__device__ __forceinline__ bool rs_spin_expired(unsigned long long &t_start)
+{
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t_start == 0ull) { t_start = now; return false; }
+    return now - t_start > 60000000000ull;
+}
+
 // --------------------------------------------------------------------------- exact scoring primitives (shared by all kernels)
 // numpy.nan_to_num on a double: NaN -> 0, +-inf -> +-DBL_MAX   (rnascan.py:306)
 __device__ __forceinline__ double rs_nan_to_num(double d)

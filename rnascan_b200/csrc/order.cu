@@ -98,9 +98,10 @@ __global__ void __launch_bounds__(OR_THREADS) order_kernel(HitStage st, int64_t 
     for (unsigned p = threadIdx.x; p < vb; p += OR_THREADS) {
         unsigned long long v;
         unsigned spins = 0;
+        unsigned long long t_start = 0ull;
         while ((v = ((volatile unsigned long long *)tmp->agg)[p]) == 0ull) {
             __nanosleep(20);
-            if (++spins > (1u << 27)) __trap();          // seconds without the predecessor's aggregate: fail, do not hang
+            if ((++spins & 0xFFFFu) == 0u && rs_spin_expired(t_start)) __trap();   // a minute without the predecessor's aggregate
         }
         part += v - 1ull;
     }

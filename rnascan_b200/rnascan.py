@@ -112,6 +112,10 @@ def getoptions(argv=None):
                         help="(rnascan_b200) After parsing a directory of averaged structure profiles, leave "
                              "a binary pack (rnascan_b200.pack) in it; later scans of the unchanged directory "
                              "map the pack instead of parsing the text [%(default)s]")
+    parser.add_argument("--reference-compat", action="store_true", default=False, dest="reference_compat",
+                        help="(rnascan_b200) Averaged structure profiles: pair profile and PSSM columns by "
+                             "position (B,E,H,L,M,R,T against E,H,T,B,L,R,M) as the unmodified reference does on "
+                             "Python >= 3.6, instead of by label [%(default)s]")
     parser.add_argument("--stats", dest="stats", default=None, metavar="FILE",
                         help="(rnascan_b200) Write one JSON line with the run's phase times, scored positions, "
                              "Gpos/s and the device kernels' achieved GB/s to FILE ('-' = STDERR)")
@@ -568,9 +572,21 @@ def _scan_averaged_structure(a_b):
     return scan_averaged_structure(*a_b)
 
 
+REFERENCE_COMPAT = False             # --reference-compat: pair profile columns and PSSM columns by POSITION
+
+
 def _structure_table(pm):
-    """(W, 7) table in device channel order from a PSSM object or a plain {letter: values}."""
+    """(W, 7) table in device channel order from a PSSM object or a plain {letter: values}.
+
+    Channels are matched BY LABEL (profile column "H" meets the PSSM's "H" column).  The unmodified reference
+    on Python >= 3.6 pairs them by position instead (rnascan.py:300-307: ``pd.DataFrame(pm)`` has its columns
+    in ``alphabet.letters`` order E,H,T,B,L,R,M while the profile file has B,E,H,L,M,R,T -- SURVEY.md H6);
+    REFERENCE_COMPAT reproduces that pairing, for diffing against upstream output (profile files in the
+    pfmutil.format_pfm column order)."""
     from . import device
+    if REFERENCE_COMPAT:
+        letters = list(getattr(getattr(pm, "alphabet", None), "letters", None) or pm.keys())
+        return np.array([list(pm[c]) for c in letters], dtype=np.float64).T.copy()
     return np.array([list(pm[c]) for c in device.CHANNELS], dtype=np.float64).T.copy()
 
 
@@ -1303,6 +1319,8 @@ def main(argv=None):
     from . import shard
     rank, _ = shard.init()                # joins the torchrun rendezvous if there is one
     args = getoptions(argv)
+    global REFERENCE_COMPAT
+    REFERENCE_COMPAT = bool(args.reference_compat)
     STATS.reset(args.stats)
     if STATS.on:
         from . import _lib

@@ -90,6 +90,19 @@ def test_averaged_cli_is_label_aligned_not_the_py3_misaligned_variant(in_repo):
     assert [r.split("\t")[i_seq] for r in rows[1:]] == [r.split("\t")[i_seq] for r in mrows[1:]]
 
 
+def test_reference_compat_reproduces_the_py3_reference_byte_for_byte(in_repo):
+    """--reference-compat pairs profile and PSSM columns by position, as the unmodified reference does on
+    Python >= 3.6: stdout equals what the reference's own main() printed (golden file)."""
+    case = CASES["rnass_avg_example_misaligned"]
+    out, err_lines, code = run_cli(list(case["argv"]) + ["--reference-compat"])
+    with open(os.path.join(CLI, "rnass_avg_example_misaligned.stdout")) as fh:
+        want = fh.read()
+    assert code == case["exit"] and out == want
+    assert err_lines == case["stderr_lines"]
+    from rnascan_b200 import rnascan as ms
+    ms.REFERENCE_COMPAT = False
+
+
 def test_averaged_combined_native_writer_equals_dataframe_path(in_repo, monkeypatch):
     """FASTA + profile directory (mode RNASS, averaged): the array/native-writer path and the
     DataFrame + merge path print the same bytes, at -m -inf and at a threshold."""

@@ -433,6 +433,54 @@ def test_bad_arguments(dev):
 
 
 # ----------------------------------------------------------------------------- batched many-PFM scan
+def test_scan_batched_tensor_filter_at_bf16_rounding_midpoints(dev, oracle):
+    """The tensor-core filter rounds profile values to bf16 (8 significant bits: up to 2^-8 relative).  Planted
+    windows put, in every row, three quarters of the mass on three channels that all carry the row's maximum
+    weight, each value just BELOW the midpoint of two bf16 neighbours (0.25 + 2^-10): the filter sees 0.25 and
+    loses 0.75 * 2^-8 * R * S -- more than a 2^-9 guard band.  With the threshold a hair below the planted
+    windows' exact scores they must still be found, bit-identical to the per-motif scan."""
+    from rnascan_b200 import synth
+    rng = np.random.default_rng(2024)
+    M, W = 40, 7
+    lengths = synth.record_lengths(80_000, 20, rng)
+    codes, off = synth.rna_codes(lengths, rng, n_frac=0.0)
+    rows = synth.profile_rows(len(codes), rng, lengths=lengths).astype(np.float32)
+    q = np.nextafter(np.float32(0.25 + 2.0 ** -10), np.float32(0))
+    rest = np.float32(1.0) - np.float32(3) * q
+    tq, planted = [], []
+    for m in range(M):
+        t = rng.integers(1, 9, size=(W, 7)).astype(np.float64) / 8.0          # bf16-representable, <= 1.0
+        p0 = int(off[m % len(off)] + 10 + 20 * (m // len(off)))
+        for j in range(W):
+            ch = rng.permutation(7)
+            t[j, ch[:3]] = 4.875                                               # the row maximum, three times (the bf16
+                                                                               # grid of the threshold bias does not
+                                                                               # hide a 2^-9 guard band at this value)
+            t[j, ch[3]] = 0.0
+            rows[p0 + j] = 0.0
+            rows[p0 + j, ch[:3]] = q
+            rows[p0 + j, ch[3]] = rest
+        tq.append(t)
+        planted.append(p0)
+    rows = np.ascontiguousarray(rows)
+    st, pf = dev.SymbolStream(codes, off, lengths), dev.ProfileStream(rows)
+    exact = []
+    for m in range(M):
+        with np.errstate(all="ignore"):
+            exact.append(oracle.profile_scores(rows, tq[m]))
+        exact[m][window_has_sep(codes, W)] = np.nan
+    scores = np.array([exact[m][planted[m]] for m in range(M)])
+    assert scores.max() - scores.min() < 1e-6                                  # all planted windows tie (nearly)
+    thr = float(np.nextafter(scores.min(), -np.inf))
+    motif, pos, sq, sc, bases = dev.scan_batched(st, pf, None, tq, thr, capacity=1 << 20, path=2)
+    for m in range(M):
+        want = np.nonzero(exact[m] > thr)[0]
+        lo_, hi_ = int(bases[m]), int(bases[m + 1])
+        assert planted[m] in set(want.tolist())
+        assert np.array_equal(pos[lo_:hi_], want), m
+        assert_same_float(sc[lo_:hi_], exact[m][want])
+
+
 @pytest.mark.parametrize("path,M,zero", [(1, 9, False), (2, 9, False), (2, 40, True), (2, 300, False)],
                          ids=["cuda-core", "tensor-core", "tensor-core-inf-tables", "tensor-core-two-groups"])
 @pytest.mark.parametrize("with_seq", [True, False])
