@@ -359,6 +359,18 @@ int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_d
                     uint64_t *d_motif_counters2 /* [2*n_motifs] */, uint64_t *d_bases /* [n_motifs+1] */,
                     void *d_work, int64_t work_bytes, void *stream);
 
+/* The same for float64 rows (what rnascan parses from structure.<id>.txt, rnascan.py:296-297) resident on the
+ * device together with their float32 shadow (rs_host_rows_to_f32): the tensor-core filter reads the shadow
+ * (guard band widened by its rounding), candidates are re-scored from the float64 rows.  Results are
+ * identical to rs_scan_batched(d_exact_f64, RS_F64, ...).                                            */
+int rs_scan_batched_shadow(const uint8_t *d_codes, const float *d_shadow_f32, const double *d_exact_f64,
+                           int64_t n, int n_motifs, const int *widths, const double *seq_tables,
+                           const double *struct_tables, int table_stride_rows, double threshold,
+                           double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
+                           int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                           uint64_t *d_motif_counters2, uint64_t *d_bases, void *d_work, int64_t work_bytes,
+                           void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,8 @@ _SIGS = {
     "rs_last_batched_path": ([], _int),
     "rs_scan_batched": ([_vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _int, _dbl, _dbl, _int, _i64, _vp, _vp,
                          _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "rs_scan_batched_shadow": ([_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _dbl, _dbl, _int, _i64, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
 }
 EXPORTS = sorted(_SIGS)
 for _name, (_args, _res) in _SIGS.items():

@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
 struct RescoreParams {
     const uint8_t *codes;
     const float   *profile;
+    const double  *exact64;             // float64 rows the float32 `profile` is a shadow of (or NULL): exact scores
     const double  *seq_tables;          // [M][stride][4] or NULL
     const double  *struct_tables;       // [M][stride][7]
     const int     *widths;              // [M]
@@ -396,8 +397,9 @@ __device__ __forceinline__ bool tc_exact(const RescoreParams &prm, int m, int64_
     } else if (!rs_no_separator(prm.codes + pos, W)) {
         return false;
     }
-    const double s = rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS,
-                                                    prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS, W);
+    const double *tab = prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS;
+    const double s = prm.exact64 ? rs_exact_profile_window<double>(prm.exact64 + pos * RS_CHANNELS, tab, W)
+                                 : rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS, tab, W);
     str_out = s;
     return s > prm.threshold;
 }
@@ -453,8 +455,9 @@ __global__ void __launch_bounds__(256) batched_rescore_kernel(const RescoreParam
                 sq = qf;
                 hit = ok && (double)qf > prm.threshold;                      // SURVEY.md note N1
                 if (hit) {
-                    st = rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS,
-                                                        prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS, W);
+                    const double *tq = prm.struct_tables + (size_t)m * prm.stride_rows * RS_CHANNELS;
+                    st = prm.exact64 ? rs_exact_profile_window<double>(prm.exact64 + pos * RS_CHANNELS, tq, W)
+                                     : rs_exact_profile_window<float>(prm.profile + pos * RS_CHANNELS, tq, W);
                     hit = st > prm.threshold;
                 }
             }
@@ -601,7 +604,7 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
                        const double *seq_tables, const double *struct_tables, int stride_rows, double threshold,
                        double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
                        int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct, uint64_t *d_motif_counters2,
-                       uint64_t *d_bases, void *d_work, int64_t work_bytes, cudaStream_t st)
+                       uint64_t *d_bases, void *d_work, int64_t work_bytes, cudaStream_t st, const double *d_exact64)
 {
     if (stride_rows > TC_WMAX || !isfinite(threshold) || !(profile_absrow_max >= 0) || !isfinite(profile_absrow_max)) {
         rs_set_error("tensor-core path: needs W <= %d, a finite threshold and a finite non-negative profile", TC_WMAX);
@@ -648,7 +651,8 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
         // bf16 keeps 8 significant bits, so round-to-nearest (__floats2bfloat162_rn in the converter warps) is off
         // by up to half an ulp = 2^-8 relative: |sum (bf16(p) - p) * S~| <= 2^-8 * R * S   (p >= 0, S~ >= S
         // entrywise so p*S~ >= p*S); + fp32 accumulation of 96 products, generous: 2^-16 * R * S
-        const double eps = (ldexp(1.0, -8) + ldexp(1.0, -16)) * R * S * 1.01;
+        // (+ 2^-24 when the float32 rows are themselves a rounded shadow of float64 rows)
+        const double eps = (ldexp(1.0, -8) + ldexp(1.0, -16) + (d_exact64 ? ldexp(1.0, -24) : 0.0)) * R * S * 1.01;
         const double thr_eff = threshold - eps;
         if (!isfinite(thr_eff) || fabs(thr_eff) > 1e30) { rs_set_error("tensor-core path: threshold out of range"); return -1; }
         B[((size_t)0 * TC_N + col) * 8 + 7] = bf16_round_up(-thr_eff);     // bias on the constant-1 channel
@@ -715,7 +719,7 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
 
     // ---- exact re-score, sort, finalize
     RescoreParams rp = {};
-    rp.codes = d_codes; rp.profile = (const float *)d_profile; rp.seq_tables = seq_tables ? d_ts : nullptr;
+    rp.codes = d_codes; rp.profile = (const float *)d_profile; rp.exact64 = d_exact64; rp.seq_tables = seq_tables ? d_ts : nullptr;
     rp.struct_tables = d_tq; rp.widths = d_w; rp.stride_rows = stride_rows; rp.mode = mode; rp.n = n;
     rp.threshold = threshold; rp.cand = cand; rp.cand_count = cand_count; rp.cand_capacity = cand_cap;
     rp.hitkeys = hitkeys; rp.hit_count = hit_count; rp.motif_counters2 = (unsigned long long *)d_motif_counters2;

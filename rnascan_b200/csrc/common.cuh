@@ -234,7 +234,8 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
                        const double *seq_tables, const double *struct_tables, int stride_rows, double threshold,
                        double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
                        int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct, uint64_t *d_motif_counters2,
-                       uint64_t *d_bases, void *d_work, int64_t work_bytes, cudaStream_t st);
+                       uint64_t *d_bases, void *d_work, int64_t work_bytes, cudaStream_t st,
+                       const double *d_exact64 = nullptr);
 int rs_scan_onehot_masks(int A, const uint8_t *d_codes, int64_t n, const double *table, int W, double threshold,
                          int64_t cap, int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_str,
                          uint64_t *d_counters2, void *d_work, cudaStream_t st);

@@ -661,13 +661,13 @@ __global__ void batched_base_kernel(unsigned long long *bases, const unsigned lo
     bases[m + 1] = bases[m] + counters2[2 * m];
 }
 
-extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+static int scan_batched_impl(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
                                int n_motifs, const int *widths, const double *seq_tables,
                                const double *struct_tables, int table_stride_rows, double threshold,
                                double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
                                int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
                                uint64_t *d_motif_counters2, uint64_t *d_bases, void *d_work, int64_t work_bytes,
-                               void *stream)
+                               void *stream, const double *d_exact64)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_motifs < 1 || !widths || !struct_tables || !d_motif_counters2 || !d_bases) {
@@ -687,7 +687,7 @@ extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, in
         int rc = rs_scan_batched_tc(d_codes, d_profile, n, n_motifs, widths, seq_tables, struct_tables,
                                     table_stride_rows, threshold, profile_absrow_max, mode, hit_capacity,
                                     d_hit_motif, d_hit_pos, d_hit_seq, d_hit_struct, d_motif_counters2, d_bases,
-                                    d_work, work_bytes, st);
+                                    d_work, work_bytes, st, d_exact64);
         if (rc >= 0) { g_batched_last = 2; return rc; }
         if (g_batched_path == 2) return RS_ERR_INVALID;      // rs_last_error() says why it does not apply
     }
@@ -697,7 +697,8 @@ extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, in
     for (int m = 0; m < n_motifs; m++) {
         const double *ts = seq_tables ? seq_tables + (size_t)m * table_stride_rows * 4 : nullptr;
         const double *tq = struct_tables + (size_t)m * table_stride_rows * RS_CHANNELS;
-        int rc = scan_fused_impl(d_codes, d_profile, profile_dtype, n, ts, tq, widths[m], threshold,
+        int rc = scan_fused_impl(d_codes, d_exact64 ? (const void *)d_exact64 : d_profile,
+                                 d_exact64 ? RS_F64 : profile_dtype, n, ts, tq, widths[m], threshold,
                                  profile_absrow_max, mode, hit_capacity, d_hit_pos, d_hit_seq, d_hit_struct,
                                  d_motif_counters2 + 2 * m, d_work, work_bytes, stream,
                                  (const unsigned long long *)d_bases + m, d_hit_motif, m);
@@ -707,4 +708,37 @@ extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, in
         RS_CUDA(cudaGetLastError());
     }
     return RS_OK;
+}
+
+extern "C" int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,
+                               int n_motifs, const int *widths, const double *seq_tables,
+                               const double *struct_tables, int table_stride_rows, double threshold,
+                               double profile_absrow_max, int mode, int64_t hit_capacity, int32_t *d_hit_motif,
+                               int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,
+                               uint64_t *d_motif_counters2, uint64_t *d_bases, void *d_work, int64_t work_bytes,
+                               void *stream)
+{
+    return scan_batched_impl(d_codes, d_profile, profile_dtype, n, n_motifs, widths, seq_tables, struct_tables,
+                             table_stride_rows, threshold, profile_absrow_max, mode, hit_capacity, d_hit_motif,
+                             d_hit_pos, d_hit_seq, d_hit_struct, d_motif_counters2, d_bases, d_work, work_bytes, stream,
+                             nullptr);
+}
+
+// float64 rows (what the CLI parses) with their float32 shadow: the tensor-core filter reads the shadow, every
+// candidate is re-scored from the float64 rows -- results identical to rs_scan_batched on the float64 rows.
+extern "C" int rs_scan_batched_shadow(const uint8_t *d_codes, const float *d_shadow_f32, const double *d_exact_f64,
+                                      int64_t n, int n_motifs, const int *widths, const double *seq_tables,
+                                      const double *struct_tables, int table_stride_rows, double threshold,
+                                      double profile_absrow_max, int mode, int64_t hit_capacity,
+                                      int32_t *d_hit_motif, int64_t *d_hit_pos, float *d_hit_seq,
+                                      double *d_hit_struct, uint64_t *d_motif_counters2, uint64_t *d_bases,
+                                      void *d_work, int64_t work_bytes, void *stream)
+{
+    if (!d_shadow_f32 || !d_exact_f64 || ((uintptr_t)d_exact_f64 & 15)) {
+        rs_set_error("rs_scan_batched_shadow: null or misaligned rows"); return RS_ERR_INVALID;
+    }
+    return scan_batched_impl(d_codes, d_shadow_f32, RS_F32, n, n_motifs, widths, seq_tables, struct_tables,
+                             table_stride_rows, threshold, profile_absrow_max, mode, hit_capacity, d_hit_motif,
+                             d_hit_pos, d_hit_seq, d_hit_struct, d_motif_counters2, d_bases, d_work, work_bytes, stream,
+                             d_exact_f64);
 }

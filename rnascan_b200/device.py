@@ -21,6 +21,7 @@ from . import _lib
 from ._lib import lib, check, RnascanCudaError
 
 CHANNELS = "BEHLMRT"        # device channel order == profile file column order
+HOST_THREADS = max(1, min(32, os.cpu_count() or 1))
 RNA_COLUMNS = "ACGU"        # device column order of sequence tables (matrix.py:57 sorts)
 
 
@@ -153,6 +154,20 @@ class ProfileStream(object):
     def absrow_max(self):
         mx, bad, neg = self.stats()
         return float("nan") if (bad or neg) else mx
+
+    def shadow(self):
+        """float32 round-to-nearest copy of float64 rows, resident beside them (the batched scan's tensor-core
+        filter reads it; candidates are re-scored from the float64 rows).  None for float32 streams or when
+        the host copy is gone."""
+        if self.dtype != _lib.RS_F64 or self._host is None:
+            return None
+        if getattr(self, "_shadow", None) is None:
+            h32 = torch.empty(self._host.shape, dtype=torch.float32, pin_memory=True)
+            check(lib.rs_host_rows_to_f32(self._host.numpy().ctypes.data, self._host.numel(), h32.numpy().ctypes.data,
+                                          HOST_THREADS))
+            self._shadow = h32.to(self.rows.device, non_blocking=True)
+            self._shadow_host = h32
+        return self._shadow
 
 
 # --------------------------------------------------------------------------- kernels
@@ -616,16 +631,25 @@ def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity
     counters = torch.zeros(2 * M, dtype=torch.int64, device=dev)
     bases = torch.zeros(M + 1, dtype=torch.int64, device=dev)
     check(lib.rs_set_batched_path(int(path)))
+    # float64 rows (parsed text): the tensor-core filter runs on their float32 shadow
+    shadow = profile.shadow() if (path != 1 and M >= 32 or path == 2) and hasattr(profile, "shadow") else None
     while True:
         hb = HitBuffers(stream.n, cap, dev)
         hb.work_bytes = int(lib.rs_scan_batched_workspace_bytes(stream.n, M, stride, cap))
         hb.work = torch.empty(hb.work_bytes, dtype=torch.uint8, device=dev)
         motif = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
-        check(lib.rs_scan_batched(_ptr(stream.codes), _ptr(profile.rows), profile.dtype, stream.n, M,
-                                  widths.ctypes.data, 0 if ss is None else ss.ctypes.data, qs.ctypes.data,
-                                  stride, threshold, absmax, mode, cap, _ptr(motif), _ptr(hb.pos),
-                                  _ptr(hb.seq), _ptr(hb.struct), _ptr(counters), _ptr(bases), _ptr(hb.work),
-                                  hb.work_bytes, _stream()))
+        if shadow is not None:
+            check(lib.rs_scan_batched_shadow(_ptr(stream.codes), _ptr(shadow), _ptr(profile.rows), stream.n, M,
+                                             widths.ctypes.data, 0 if ss is None else ss.ctypes.data, qs.ctypes.data,
+                                             stride, threshold, absmax, mode, cap, _ptr(motif), _ptr(hb.pos),
+                                             _ptr(hb.seq), _ptr(hb.struct), _ptr(counters), _ptr(bases), _ptr(hb.work),
+                                             hb.work_bytes, _stream()))
+        else:
+            check(lib.rs_scan_batched(_ptr(stream.codes), _ptr(profile.rows), profile.dtype, stream.n, M,
+                                      widths.ctypes.data, 0 if ss is None else ss.ctypes.data, qs.ctypes.data,
+                                      stride, threshold, absmax, mode, cap, _ptr(motif), _ptr(hb.pos),
+                                      _ptr(hb.seq), _ptr(hb.struct), _ptr(counters), _ptr(bases), _ptr(hb.work),
+                                      hb.work_bytes, _stream()))
         b = bases.cpu().numpy()
         total = int(b[-1])
         if total <= cap:
@@ -747,8 +771,6 @@ class HostFusedScanner(object):
 
 
 # --------------------------------------------------------------------------- exact rows on the host: filter + gather + resolve
-HOST_THREADS = max(1, min(32, os.cpu_count() or 1))
-
 
 def _np_ptr(a):
     return 0 if a is None else a.ctypes.data

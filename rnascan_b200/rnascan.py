@@ -131,8 +131,11 @@ def getoptions(argv=None):
     return args
 
 
+_QUIET = 0
+
+
 def eprint(*args, **kwargs):
-    if _rank() == 0:                      # under torchrun only rank 0 talks
+    if _rank() == 0 and not _QUIET:       # under torchrun only rank 0 talks
         print(*args, file=sys.stderr, **kwargs)
 
 
@@ -214,7 +217,10 @@ def load_motif(pfm_file, *args):
     eprint("Loading PFM %s" % pfm_file, end="")
     tic = time.time()
     try:
-        motif_id = os.path.splitext(os.path.basename(pfm_file))[0]
+        if isinstance(pfm_file, _PfmBlock):
+            motif_id = pfm_file.motif_id
+        else:
+            motif_id = os.path.splitext(os.path.basename(pfm_file))[0]
         motifs_set[motif_id] = pfm2pssm(pfm_file, *args)
     except ValueError:
         eprint("\nFailed to load motif %s" % pfm_file)
@@ -237,10 +243,53 @@ def load_motif(pfm_file, *args):
 def pfm2pssm(pfm_file, pseudocount, alphabet, background=None):
     """PFM file -> normalize(pseudocount) -> log_odds(background) -> PSSM
     (rnascan.py:238-252).  The first column is dropped; header letters may come in any order."""
-    table = pd.read_csv(pfm_file, sep="\t")
+    table = pd.read_csv(pfm_file.open() if isinstance(pfm_file, _PfmBlock) else pfm_file, sep="\t")
     counts = table.drop(columns=table.columns[0]).to_dict(orient="list")
     values = motifs.Motif(alphabet=alphabet, counts=counts).pssm(pseudocount, background)
     return matrix.ExtendedPositionSpecificScoringMatrix(alphabet, values)
+
+
+class _PfmBlock(object):
+    """One motif of a multi-PFM file (pfmutil.write_multi_pfm layout, pfmutil.py:89-133 of the reference),
+    standing in for the single-PFM file the reference would be run with: same table text, so the same parse."""
+
+    def __init__(self, motif_id, text, source):
+        self.motif_id, self.text, self.source = motif_id, text, source
+
+    def open(self):
+        import io
+        return io.StringIO(self.text)
+
+    def __str__(self):
+        return "%s#%s" % (self.source, self.motif_id)
+
+
+def pfm_blocks(path):
+    """The motifs of a multi-PFM file as _PfmBlock objects, or None when `path` is an ordinary PFM file
+    (first line does not start with '#').  Layout per block: ``#<id>``, ``#PO<TAB>letters``, one row per
+    position, blank line."""
+    if not isinstance(path, str) or not os.path.isfile(path):
+        return None
+    with open(path) as handle:
+        lines = handle.read().splitlines()
+    if not lines or not lines[0].startswith("#"):
+        return None
+    blocks, k = [], 0
+    while k < len(lines):
+        if not lines[k].startswith("#"):
+            k += 1
+            continue
+        if k + 1 >= len(lines) or not lines[k + 1].startswith("#"):
+            raise ValueError("%s: block '%s' lacks its '#PO<TAB>letters' line" % (path, lines[k]))
+        motif_id, header = lines[k][1:].rstrip(), lines[k + 1][1:].rstrip()
+        k += 2
+        rows = []
+        while k < len(lines) and not lines[k].startswith("#"):
+            if lines[k].strip():
+                rows.append(lines[k].rstrip())
+            k += 1
+        blocks.append(_PfmBlock(motif_id, "\n".join([header] + rows) + "\n", path))
+    return blocks
 
 
 ###############################################################################
@@ -946,7 +995,7 @@ def _profile_files(directory):
 
 def _load_profile_dir(directory, write_pack=False):
     """This rank's share of the profiles of a directory as one packed stream:
-    (paths, total number of files, HostProfile, lengths).  A valid ``rnascan_b200.pack`` (pack.py) is
+    (this rank's paths, all paths, HostProfile, lengths).  A valid ``rnascan_b200.pack`` (pack.py) is
     mapped instead of parsing the text; `write_pack` leaves one behind after parsing."""
     from . import device, shard, pack
     rank, size = shard.world()
@@ -974,7 +1023,7 @@ def _load_profile_dir(directory, write_pack=False):
         r1 = int(pk.offsets[hi - 1] + pk.lengths[hi - 1] + 1) if hi > lo else 0
         hp = device.HostProfile(pk.rows[r0:r1], q8=None if pk.q8 is None else pk.q8[r0:r1], q8_scale=pk.q8_scale,
                                 stats=pk.stats)
-        return files[lo:hi], n_files, hp, lengths
+        return files[lo:hi], files, hp, lengths
     packed, lengths = _read_profiles_packed(files[lo:hi])
     hp = device.HostProfile(packed)
     if write_pack and size == 1 and n_files:
@@ -985,7 +1034,56 @@ def _load_profile_dir(directory, write_pack=False):
             pack.write(directory, files, packed, lengths, hp.stats(), hp.q8 if ok else None, hp.q8_scale)
         except OSError as exc:
             eprint("Could not write %s: %s" % (pack.pack_path(directory), exc))
-    return files[lo:hi], n_files, hp, lengths
+    return files[lo:hi], files, hp, lengths
+
+
+def _profile_dir_streams(directory, debug, seq_batches, write_pack):
+    """The packed streams of a profile directory: (this rank's files, the ids of ALL files, HostProfile, lengths,
+    this rank's ids, offsets, codes).
+    `codes` holds separators only, or -- with `seq_batches` (combined mode) -- the sequence symbols of the
+    record with the same id, aligned row by row; rows beyond the shorter of the two get an invalid symbol (no
+    joint window exists there).  Cached per directory while a motif collection is being scanned."""
+    from . import device
+    key = (os.path.abspath(directory), bool(debug), None if seq_batches is None else id(seq_batches))
+    if key in _PROFILE_DIR_CACHE:
+        return _PROFILE_DIR_CACHE[key]
+    with STATS.phase("ingest_profiles_s"):
+        files, all_files, hp, lengths = _load_profile_dir(directory, write_pack)
+    n_files = len(all_files)
+    STATS.add("profile_rows", int(lengths.sum()))
+    STATS.add("profile_files", len(files))
+    STATS.notes["profile_source"] = "pack" if isinstance(hp.rows, np.memmap) else "text"
+    # rnascan.py:299-301: the id is what stands between "structure." and ".txt" (the full path in debug mode)
+    names = list(files) if debug else [os.path.basename(path)[10:-4] for path in files]
+    n_prof = len(files)
+    offsets = np.zeros(n_prof, np.int64)
+    if n_prof > 1:
+        np.cumsum(lengths[:-1] + 1, out=offsets[1:])
+    codes = np.zeros(int(lengths.sum() + n_prof), np.uint8)
+    if seq_batches is not None:
+        by_id = {}
+        for batch in seq_batches:
+            for rid, text in zip(batch.ids, batch.full_texts):
+                by_id.setdefault(rid, text)
+        for k, name in enumerate(names):
+            seg = codes[offsets[k]:offsets[k] + lengths[k]]
+            seg[:] = device._lib.RS_RNA_OTHER
+            text = by_id.get(name)
+            if text is not None:
+                sym = device.pack_texts([text], "rna")[0][:-1]
+                m = min(len(sym), len(seg))
+                seg[:m] = sym[:m]
+    if n_prof:
+        codes[offsets + lengths] = device._lib.RS_SEP
+    if len(codes) and hp.q8 is not None and seq_batches is not None:
+        q8 = np.array(hp.q8)                          # the pack's rows carry no sequence: add the symbols
+        q8[:, 7] = codes
+        hp.q8 = q8
+    all_names = list(all_files) if debug else [os.path.basename(path)[10:-4] for path in all_files]
+    out = (files, all_names, hp, lengths, names, offsets, codes)
+    if _PROFILE_DIR_CACHE_ON[0]:
+        _PROFILE_DIR_CACHE[key] = out
+    return out
 
 
 def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm=None, want_arrays=False,
@@ -1002,42 +1100,19 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     tq = _structure_table(pm)
     width = tq.shape[0]
     rank, size = shard.world()
-    with STATS.phase("ingest_profiles_s"):
-        files, n_files, hp, lengths = _load_profile_dir(directory, write_pack)
-    STATS.add("profile_rows", int(lengths.sum()))
-    STATS.add("profile_files", len(files))
-    STATS.notes["profile_source"] = "pack" if isinstance(hp.rows, np.memmap) else "text"
-    # rnascan.py:299-301: the id is what stands between "structure." and ".txt" (the full path in debug mode)
-    names = list(files) if debug else [os.path.basename(path)[10:-4] for path in files]
-    n_prof = len(files)
-    offsets = np.zeros(n_prof, np.int64)
-    if n_prof > 1:
-        np.cumsum(lengths[:-1] + 1, out=offsets[1:])
-    codes = np.zeros(int(lengths.sum() + n_prof), np.uint8)
+    files, all_names, hp, lengths, names, offsets, codes = _profile_dir_streams(directory, debug, seq_batches,
+                                                                                write_pack)
+    n_files = len(all_names)
     seq = None
     if seq_batches is not None:
-        # sequence symbols of the record with the same id, aligned row by row; rows beyond the
-        # shorter of the two get an invalid symbol (no joint window exists there)
-        by_id = {}
-        for batch in seq_batches:
-            for rid, text in zip(batch.ids, batch.full_texts):
-                by_id.setdefault(rid, text)
         seq = seq_table_fn if seq_table_fn is not None else _table_for(seq_pm, "rna")
-        for k, name in enumerate(names):
-            seg = codes[offsets[k]:offsets[k] + lengths[k]]
-            seg[:] = device._lib.RS_RNA_OTHER
-            text = by_id.get(name)
-            if text is not None:
-                sym = device.pack_texts([text], "rna")[0][:-1]
-                m = min(len(sym), len(seg))
-                seg[:m] = sym[:m]
-    if n_prof:
-        codes[offsets + lengths] = device._lib.RS_SEP
-    if len(codes):
-        if hp.q8 is not None and seq_batches is not None:
-            q8 = np.array(hp.q8)                      # the pack's rows carry no sequence: add the symbols
-            q8[:, 7] = codes
-            hp.q8 = q8
+    precomputed, _PRECOMPUTED[0] = _PRECOMPUTED[0], None
+    if precomputed is not None:           # this motif pair was scanned in the collection's batched pass
+        pos, seq_scores, scores = precomputed
+        STATS.add("scored_positions", int(np.maximum(lengths - width + 1, 0).sum()))
+        rec = np.searchsorted(offsets, pos, side="right") - 1
+        start0 = pos - offsets[rec]
+    elif len(codes):
         with STATS.phase("scan_s"):
             pos, seq_scores, scores, scanner = device.scan_profile_host(codes, hp, seq, tq, minscore,
                                                                         return_scanner=True)
@@ -1064,16 +1139,55 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         hit_names = [x for g in gathered for x in g[0]]
         start0 = np.concatenate([g[1] for g in gathered])
         scores = np.concatenate([g[2] for g in gathered])
-    n = len(hit_names)
-    frame = pd.DataFrame({
-        "Sequence_ID": np.array(hit_names, dtype=object),
-        "Description": np.array([""] * n, dtype=object),
-        "Motif_ID": np.array([motif_id] * n, dtype=object),
-        "Start": (start0 + 1).astype(object), "End": (start0 + width).astype(object),
-        "Sequence": np.array(["."] * n, dtype=object),
-        "LogOdds": np.asarray(scores, dtype=np.float64).astype(object),
-    })
+    first_has_hits = None
+    if seq is not None and n_files > 1 and rank == 0 and len(lengths):
+        # combined mode: `hit_names` only knows the windows where BOTH scores pass, but the column order of the
+        # reference's structure frame -- and with it that of the merged output -- follows the first file's own
+        # structure hits: one small structure-only scan of that file settles it
+        first = device.HostProfile(np.ascontiguousarray(hp.rows[:int(lengths[0])]))
+        first_has_hits = len(device.scan_profile_host(None, first, None, tq, minscore)[0]) > 0
+    frame = _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits)
+    if want_arrays and arrays is not None and first_has_hits is False:
+        arrays = None                     # unusual column order: the DataFrame path prints it
     return (frame, n_files, arrays) if want_arrays else (frame, n_files)
+
+
+def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits=None):
+    """The frame the reference gets for a directory (rnascan.py:348-375, 408-413): one frame per file built
+    by pd.DataFrame(list of Series) -- or, for a file without hits, pd.DataFrame([]) with only the two id
+    columns -- then pd.concat and the last two columns moved to the front.  What pandas makes of that mix
+    (column order follows the first file's frame; Start/End turn float when any file had no hit; only the id
+    columns remain when no file had one) is learnt from one-row prototypes run through the same calls, then
+    applied to the whole result at once."""
+    n = len(hit_names)
+    with_hits = set(hit_names)
+    any_empty = any(name not in with_hits for name in all_names)
+    hit = pd.DataFrame([pd.Series([motif_id, 1, 2, ".", 0.5], index=HIT_COLUMNS)])
+    empty = pd.DataFrame([])
+    for proto in (hit, empty):
+        _add_sequence_id(proto, "id", "")
+    if first_has_hits is True and all_names and all_names[0] not in with_hits:
+        any_empty = True                  # (combined mode) its structure hits exist, none of them joint
+    if n == 0 and not first_has_hits:
+        protos = [empty]
+    elif not any_empty:
+        protos = [hit]
+    else:
+        if first_has_hits is None:
+            first_has_hits = all_names[0] in with_hits
+        protos = [hit, empty] if first_has_hits else [empty, hit]
+    proto = pd.concat(protos) if all_names else pd.DataFrame()
+    cols = proto.columns.tolist()
+    proto = proto[cols[-2:] + cols[:-2]]
+    data = {"Sequence_ID": np.array(hit_names, dtype=object), "Description": np.array([""] * n, dtype=object),
+            "Motif_ID": np.array([motif_id] * n, dtype=object), "Start": np.asarray(start0, np.int64) + 1,
+            "End": np.asarray(start0, np.int64) + width, "Sequence": np.array(["."] * n, dtype=object),
+            "LogOdds": np.asarray(scores, dtype=np.float64)}
+    frame = pd.DataFrame({c: data[c] for c in proto.columns})
+    for c in ("Start", "End", "LogOdds"):
+        if c in frame.columns and n:
+            frame[c] = frame[c].astype(proto[c].dtype)
+    return frame
 
 
 def scan_main(fasta_file, pssm, alphabet, bg, args):
@@ -1314,6 +1428,144 @@ def _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args):
     return joint
 
 
+_PRECOMPUTED = [None]                # hits of the current motif pair found by the batched scan (_run_multi)
+_PROFILE_DIR_CACHE = {}              # directory -> _profile_dir_streams result while a motif collection is scanned
+_PROFILE_DIR_CACHE_ON = [False]
+
+
+def _multi_pfm_pairs(args):
+    """[(sequence PFM | None, structure PFM | None)] when -p and/or -q name a multi-PFM file, else None.
+    Two multi-PFM files pair up block by block; an ordinary PFM file on the other side serves every pair."""
+    seq_blocks = pfm_blocks(args.pfm_seq) if args.pfm_seq else None
+    struct_blocks = pfm_blocks(args.pfm_struct) if args.pfm_struct else None
+    if seq_blocks is None and struct_blocks is None:
+        return None
+    if seq_blocks is not None and struct_blocks is not None and len(seq_blocks) != len(struct_blocks):
+        eprint("The multi-PFM files hold %d and %d motifs" % (len(seq_blocks), len(struct_blocks)))
+        sys.exit(1)
+    count = len(seq_blocks if seq_blocks is not None else struct_blocks)
+    seq_side = seq_blocks if seq_blocks is not None else [args.pfm_seq] * count
+    struct_side = struct_blocks if struct_blocks is not None else [args.pfm_struct] * count
+    return list(zip(seq_side, struct_side))
+
+
+def _run_multi(args, seq_type, rank, pairs):
+    """A motif collection: the output is the concatenation of what one reference run per motif (pair) prints
+    (rnascan.py:490-567 once per PFM).  Inputs are parsed and uploaded once; with a directory of averaged
+    profiles all pairs are scanned in ONE batched pass (rs_scan_batched: tensor cores from 32 motifs on)."""
+    import copy
+    _PROFILE_DIR_CACHE.clear()
+    _PROFILE_DIR_CACHE_ON[0] = True
+    try:
+        pre = None
+        if not args.bgonly:
+            pre = _batched_profile_hits(args, seq_type, pairs)
+        for k, (seq_pfm, struct_pfm) in enumerate(pairs):
+            one = copy.copy(args)
+            one.pfm_seq, one.pfm_struct = seq_pfm, struct_pfm
+            _run(one, seq_type, rank, None if pre is None else pre[k])
+            if args.bgonly:
+                break
+    finally:
+        _PROFILE_DIR_CACHE_ON[0] = False
+        _PROFILE_DIR_CACHE.clear()
+
+
+def _quiet(fn, *a, **kw):
+    """Run `fn` with this module's stderr messages (and low-content warnings) suppressed."""
+    global _QUIET
+    _QUIET += 1
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return fn(*a, **kw)
+    finally:
+        _QUIET -= 1
+
+
+def _batched_profile_hits(args, seq_type, pairs):
+    """Hits of every motif pair on a directory of averaged profiles from one device.scan_batched call:
+    a list of (pos, seq_scores | None, struct_scores) per pair in packed-stream positions, or None when this
+    run does not have that shape (the per-motif scans then run one after the other)."""
+    from . import device
+    if args.testseq or _world_size() > 1 or len(pairs) < 2 or not np.isfinite(args.minscore):
+        return None
+    struct_file = args.fastafiles[-1] if args.fastafiles else None
+    if seq_type not in ("SS", "RNASS") or not struct_file or not os.path.isdir(struct_file):
+        return None
+    if not (args.bg_struct or args.uniform_background):
+        return None                       # an averaged-profile run cannot compute a structure background
+    structure = ContextualSecondaryStructure()
+    try:
+        bg_struct = _quiet(load_background, args.bg_struct, args.uniform_background)
+        struct_pssms = [_quiet(pfm2pssm, q, args.pseudocount, structure, bg_struct) for _, q in pairs]
+        seq_pssms = seq_batches = None
+        if seq_type == "RNASS":
+            rna = IUPAC.IUPACUnambiguousRNA()
+            seq_file = args.fastafiles[0]
+            bg_seq = _quiet(load_background, args.bg_seq, args.uniform_background, seq_file, rna, False)
+            seq_pssms = [_quiet(pfm2pssm, p_, args.pseudocount, rna, bg_seq) for p_, _ in pairs]
+            if any(a.length != b.length for a, b in zip(seq_pssms, struct_pssms)):
+                return None
+            seq_batches = _cached_batches(seq_file, rna)
+            ids = [i for b in seq_batches for i in b.ids]
+            if len(set(ids)) != len(ids):
+                return None
+    except Exception:
+        return None                       # the per-motif run reports what is wrong
+    tqs = [_structure_table(pm) for pm in struct_pssms]
+    tss = None if seq_pssms is None else [_table_for(pm, "rna") for pm in seq_pssms]
+    if max(t.shape[0] for t in tqs) > 24:
+        return None
+    files, all_names, hp, lengths, names, offsets, codes = _profile_dir_streams(
+        struct_file, args.debug, seq_batches, getattr(args, "pack", False))
+    if not len(codes) or not device.filter_applies(np.concatenate(tqs), args.minscore, hp.absrow_max()):
+        return None
+    with STATS.phase("scan_s"):
+        stream = device.SymbolStream(codes, offsets, lengths)
+        profile = device.ProfileStream(hp.rows)
+        motif, pos, sq, st, bases = device.scan_batched(stream, profile, tss, tqs, args.minscore)
+    STATS.notes["batched_motifs"] = len(pairs)
+    out = []
+    for k in range(len(pairs)):
+        a, b = int(bases[k]), int(bases[k + 1])
+        out.append((pos[a:b], None if sq is None else sq[a:b], st[a:b]))
+    return out
+
+
+def scan_many(struct_dir, struct_pssms, minscore, seq_file=None, seq_pssms=None, debug=False):
+    """Scan a directory of averaged profiles with MANY motifs in one batched pass (BASELINE config 5).
+
+    struct_pssms (and seq_pssms, for the combined mode) are lists of ``{motif_id: PSSM}`` as load_motif
+    returns them.  Returns one DataFrame per motif (pair): what scan_main(struct_dir, ...) returns for that
+    structure motif alone -- restricted, with seq_pssms, to the windows whose sequence score passes too, with
+    an extra ``LogOdds.Seq`` column."""
+    from . import device
+    if seq_pssms is not None and len(seq_pssms) != len(struct_pssms):
+        raise ValueError("sequence and structure motif lists differ in length")
+    seq_batches = None
+    if seq_pssms is not None:
+        seq_batches = _cached_batches(seq_file, IUPAC.IUPACUnambiguousRNA())
+    files, all_names, hp, lengths, names, offsets, codes = _profile_dir_streams(struct_dir, debug, seq_batches, False)
+    pms = [_first_motif(p) for p in struct_pssms]
+    tqs = [_structure_table(pm) for _, pm in pms]
+    tss = None if seq_pssms is None else [_table_for(_first_motif(p)[1], "rna") for p in seq_pssms]
+    stream = device.SymbolStream(codes, offsets, lengths)
+    profile = device.ProfileStream(hp.rows)
+    motif, pos, sq, st, bases = device.scan_batched(stream, profile, tss, tqs, minscore)
+    frames = []
+    for k, (motif_id, pm) in enumerate(pms):
+        a, b = int(bases[k]), int(bases[k + 1])
+        rec = np.searchsorted(offsets, pos[a:b], side="right") - 1
+        start0 = pos[a:b] - offsets[rec]
+        frame = _averaged_dir_frame(all_names, [names[r] for r in rec.tolist()], motif_id, start0, tqs[k].shape[0],
+                                    st[a:b])
+        if sq is not None and len(frame.columns) > 2:
+            frame["LogOdds.Seq"] = _round3_f32(sq[a:b])
+        frames.append(frame)
+    return frames
+
+
 def main(argv=None):
     tic = time.time()
     from . import shard
@@ -1326,7 +1578,25 @@ def main(argv=None):
         from . import _lib
         _lib.lib.rs_prof_begin(4096)
     seq_type = _guess_seq_type(args)
+    pairs = _multi_pfm_pairs(args)
+    if pairs is None:
+        _run(args, seq_type, rank)
+    else:
+        _run_multi(args, seq_type, rank, pairs)
+    runtime = float(time.time() - tic)
+    if STATS.on:
+        _write_stats(args.stats, seq_type, runtime)
+    if runtime > 60:
+        eprint("Done in %0.4f minutes!" % (runtime / 60))
+    else:
+        eprint("Done in %0.4f seconds!" % (runtime))
+
+
+def _run(args, seq_type, rank, precomputed=None):
+    """One reference run (rnascan.py:490-567): backgrounds, motifs, scans, hits.tab on STDOUT.
+    `precomputed`: hits of this motif pair on the profile directory, already found by the batched scan."""
     bg = None
+    _PRECOMPUTED[0] = precomputed
     seq_file = struct_file = None
     seq_pssm = None
     seq_hits = struct_hits = joint = None          # array-level results (single process, FASTA inputs)
@@ -1396,6 +1666,7 @@ def main(argv=None):
                 struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
 
     t_out = time.perf_counter()
+    _PRECOMPUTED[0] = None
     if rank == 0:
         written = False
         if seq_type == "RNASS":
@@ -1424,15 +1695,7 @@ def main(argv=None):
             final.to_csv(sys.stdout, sep="\t", index=False)
     elif joint is not None and joint.struct_frame is not None:
         joint.struct_frame()              # other ranks take part in the gather
-
-    runtime = float(time.time() - tic)
-    if STATS.on:
-        STATS.phases["output_s"] = time.perf_counter() - t_out
-        _write_stats(args.stats, seq_type, runtime)
-    if runtime > 60:
-        eprint("Done in %0.4f minutes!" % (runtime / 60))
-    else:
-        eprint("Done in %0.4f seconds!" % (runtime))
+    STATS.phases["output_s"] += time.perf_counter() - t_out
 
 
 def _write_stats(dest, seq_type, runtime):

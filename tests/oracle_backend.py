@@ -143,13 +143,27 @@ def scan_onehot_bg(stream, prob, table_fn, threshold, all_reduce=None, capacity=
     return pos, sc, counts, 0
 
 
+def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity=None, path=0):
+    motif, pos, sq, st, bases = [], [], [], [], [0]
+    for m, tq in enumerate(struct_tables):
+        p_, a_, b_ = scan_fused(stream, profile, None if seq_tables is None else seq_tables[m], tq, threshold)
+        motif.append(np.full(len(p_), m, np.int32)); pos.append(p_); st.append(b_)
+        if seq_tables is not None:
+            sq.append(a_)
+        bases.append(bases[-1] + len(p_))
+    cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+    return (cat(motif, np.int32), cat(pos, np.int64), cat(sq, np.float32) if seq_tables is not None else None,
+            cat(st, np.float64), np.array(bases, np.int64))
+
+
 def install(monkeypatch):
     for name, fn in (("SymbolStream", FakeSymbolStream), ("ProfileStream", FakeProfileStream),
                      ("histogram", histogram), ("dense_seq", dense_seq), ("dense_struct", dense_struct),
                      ("dense_profile", dense_profile), ("scan_seq", scan_seq),
                      ("scan_struct_onehot", scan_struct_onehot), ("scan_pair_onehot", scan_pair_onehot),
                      ("scan_fused", scan_fused),
-                     ("scan_profile_host", scan_profile_host), ("scan_onehot_bg", scan_onehot_bg)):
+                     ("scan_profile_host", scan_profile_host), ("scan_onehot_bg", scan_onehot_bg),
+                     ("scan_batched", scan_batched)):
         monkeypatch.setattr(device, name, fn)
     from rnascan_b200 import rnascan as ms
     ms._BATCH_CACHE.clear()

@@ -64,6 +64,58 @@ def test_cli_output_is_byte_identical(name, in_repo):
     assert err_lines == case["stderr_lines"]
 
 
+with open(os.path.join(CLI, "multi_cases.json")) as _fh:
+    MULTI_CASES = json.load(_fh)
+
+
+def test_motif_collections_print_what_one_reference_run_per_motif_prints(in_repo):
+    """-p / -q naming multi-PFM files (pfmutil.write_multi_pfm layout): stdout is the concatenation of the
+    reference's stdout for one run per motif pair (golden files made by looping the reference's own main(),
+    tests/golden/make_golden_multi.py).  Directories of averaged profiles go through ONE batched scan."""
+    import warnings
+    from rnascan_b200 import rnascan as ms
+    for name, case in sorted(MULTI_CASES.items()):
+        with open(os.path.join(CLI, name + ".stdout")) as fh:
+            want = fh.read()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, _, code = run_cli(case["argv"])
+        ms.REFERENCE_COMPAT = False
+        assert code == case["exit"], name
+        assert out == want, name
+        assert out.count("Match_ID") == case["runs"], name
+
+
+def test_scan_many_equals_scan_main_per_motif(in_repo):
+    """scan_many(directory, motifs) == [scan_main(directory, motif) for every motif] (frames), and with
+    sequence motifs the windows are restricted to those whose sequence score passes as well."""
+    import argparse
+    from rnascan_b200 import rnascan as ms
+    from rnascan_b200.BioAddons.Alphabet import ContextualSecondaryStructure
+    structure, rna = ContextualSecondaryStructure(), ms.IUPAC.IUPACUnambiguousRNA()
+    directory = os.path.join(INP, "profiles_mixed")
+    bg = {"B": 0.0163, "E": 0.2721, "H": 0.1530, "L": 0.2046, "M": 0.0196, "R": 0.1970, "T": 0.1374}
+    blocks_q = ms.pfm_blocks(os.path.join(INP, "multi", "multi_struct.pfm"))
+    blocks_p = ms.pfm_blocks(os.path.join(INP, "multi", "multi_seq.pfm"))
+    assert len(blocks_q) == len(blocks_p) == 8 and ms.pfm_blocks(os.path.join(INP, "test_seq_pfm.txt")) is None
+    struct_pssms = [ms.load_motif(b, 0.01, structure, bg) for b in blocks_q]
+    frames = ms.scan_many(directory, struct_pssms, 0.5)
+    ns = argparse.Namespace(minscore=0.5, debug=False)
+    for pssm, frame in zip(struct_pssms, frames):
+        want = ms.scan_main(directory, pssm, structure, None, ns)
+        assert list(frame.columns) == list(want.columns) and len(frame) == len(want) > 0
+        for col in want.columns:
+            assert frame[col].tolist() == want[col].tolist()
+    seq_pssms = [ms.load_motif(b, 0.01, rna, None) for b in blocks_p]
+    both = ms.scan_many(directory, struct_pssms, -6.0, seq_file=os.path.join(INP, "mixed.fa"), seq_pssms=seq_pssms)
+    alone = ms.scan_many(directory, struct_pssms, -6.0)
+    assert sum(len(f) for f in both) > 0
+    for a, b in zip(both, alone):
+        assert "LogOdds.Seq" in a.columns and len(a) <= len(b) and (a["LogOdds.Seq"] > -6.0).all()
+        keys = set(zip(b["Sequence_ID"], b["Start"]))
+        assert all(k in keys for k in zip(a["Sequence_ID"], a["Start"]))
+
+
 def test_cores_flag_does_not_change_the_result(in_repo):
     base = CASES["rna_mixed_all"]["argv"]
     a = run_cli(base)[0]

@@ -433,6 +433,52 @@ def test_bad_arguments(dev):
 
 
 # ----------------------------------------------------------------------------- batched many-PFM scan
+@pytest.mark.parametrize("with_seq", [True, False])
+def test_scan_batched_float64_rows_through_the_float32_shadow(dev, oracle, with_seq):
+    """rs_scan_batched_shadow: float64 rows (what the CLI parses; not float32-representable) are filtered on
+    the tensor cores through their float32 shadow and re-scored from the float64 rows -- per motif exactly
+    what the oracle gives on the float64 rows, and the path taken is the tensor-core one."""
+    from rnascan_b200 import synth
+    from rnascan_b200.device import lib
+    rng = np.random.default_rng(77)
+    M = 40
+    lengths = synth.record_lengths(200_000, 50, rng)
+    codes, off = synth.rna_codes(lengths, rng, n_frac=0.005)
+    g = rng.standard_gamma(0.3, size=(len(codes), 7))
+    rows = g / np.maximum(g.sum(axis=1, keepdims=True), 1e-300)
+    rows[off + lengths] = 0.0
+    rows = np.ascontiguousarray(rows, np.float64)
+    assert not np.array_equal(rows, rows.astype(np.float32).astype(np.float64))
+    st, pf = dev.SymbolStream(codes, off, lengths), dev.ProfileStream(rows)
+    bg = [synth.SS_P[c] for c in "BEHLMRT"]
+    widths = rng.integers(7, 13, size=M)
+    tq = [synth.pssm_table(synth.pfm_rows(int(w), 7, rng), background=bg) for w in widths]
+    ts = [synth.pssm_table(synth.pfm_rows(int(w), 4, rng)) for w in widths]
+    text = synth.to_text(codes, "rna")
+    thr = 0.5 if with_seq else 4.0
+    motif, pos, sq, sc, bases = dev.scan_batched(st, pf, ts if with_seq else None, tq, thr, capacity=1 << 20)
+    assert int(lib.rs_last_batched_path()) == 2
+    total = 0
+    for m in range(M):
+        W = int(widths[m])
+        with np.errstate(all="ignore"):
+            b = oracle.profile_scores(rows, tq[m])
+        b[window_has_sep(codes, W)] = np.nan
+        keep = b > thr
+        if with_seq:
+            a = oracle.seq_scores(text, ts[m])
+            with np.errstate(invalid="ignore"):
+                keep &= a.astype(np.float64) > thr
+        want = np.nonzero(keep)[0]
+        lo, hi = int(bases[m]), int(bases[m + 1])
+        assert np.array_equal(pos[lo:hi], want), m
+        assert_same_float(sc[lo:hi], b[want])
+        if with_seq:
+            assert_same_float(sq[lo:hi], a[want])
+        total += len(want)
+    assert total > 0 and bases[-1] == total
+
+
 def test_scan_batched_tensor_filter_at_bf16_rounding_midpoints(dev, oracle):
     """The tensor-core filter rounds profile values to bf16 (8 significant bits: up to 2^-8 relative).  Planted
     windows put, in every row, three quarters of the mass on three channels that all carry the row's maximum
