@@ -373,7 +373,8 @@ def measure(args, wl, steps, ctx, full, n_target):
     counts = torch.zeros(8, dtype=torch.int64, device=device)
     counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
     hb = dev.HitBuffers(n, max(1 << 16, n // 256), device)
-    dense_out = torch.empty(n, dtype=torch.float64, device=device) if wl == "c3" else None
+    # C3: every window's score as rnascan prints it -- round(score, 3) in int32 thousandths, 4 B per position
+    dense_out = torch.empty(n, dtype=torch.int32, device=device) if wl == "c3" else None
     absmax = 1.0
     if wl in ("c4", "c5"):
         absmax = dev.ProfileStream.from_device(prof, n).absrow_max()
@@ -439,7 +440,7 @@ def measure(args, wl, steps, ctx, full, n_target):
                                   _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, sptr))
             launches[0] += 3                                # decision table, scan, finish (segment scan + expansion)
         else:
-            check(lib.rs_scores_dense_struct(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
+            check(lib.rs_scores_dense_struct_milli(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
             launches[0] += 1
 
     def barrier():
@@ -558,7 +559,7 @@ def measure(args, wl, steps, ctx, full, n_target):
                 prof.copy_(h_prof, non_blocking=True); io[0] += prof.numel() * 4
             step()
             if wl == "c3":
-                h_out.copy_(dense_out, non_blocking=True); io[1] = dense_out.numel() * 8
+                h_out.copy_(dense_out, non_blocking=True); io[1] = dense_out.numel() * 4
                 stream.synchronize()
             else:
                 stream.synchronize()
@@ -599,11 +600,11 @@ def measure(args, wl, steps, ctx, full, n_target):
         "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,      # run_b200 sets `scaling`
         "dtype": "f32 filter + f64 exact re-score (sequence: f64 accumulate -> f32)" if wl == "c4" else
-                 ("f64 accumulate -> f32" if wl == "c2" else ("f64" if wl == "c3" else
+                 ("f64 accumulate -> f32" if wl == "c2" else ("f64 (printed form: int32 thousandths)" if wl == "c3" else
                                                               "f32 filter + f64 exact re-score, per motif")),
         "data": "synthetic (SURVEY.md 8d shapes; generated on device, seed 4000+rank)",
         "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile, fused AND scan",
-                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, dense f64 output",
+                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, every position (f64 score -> round(x, 3) as int32 thousandths)",
                                 "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure" % N_MOTIFS_C5}[wl],
                    "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
                    "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
@@ -619,7 +620,7 @@ def measure(args, wl, steps, ctx, full, n_target):
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
         "gpu_launches": n_launch,
         "roofline": {"bound": "hbm", "kernel": {"c4": "fused_filter_kernel<7>", "c2": "kmer_scan_kernel<7>",
-                                               "c3": "dense_w_kernel<7,7>",
+                                               "c3": "dense_w_kernel<7,7,1>",
                                                "c5": "fused_filter_kernel<W> x %d motifs" % N_MOTIFS_C5}[wl],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],

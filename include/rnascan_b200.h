@@ -18,7 +18,13 @@
  *  - every function returns 0 (RS_OK) or an RS_ERR_* code; rs_last_error() gives text;
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work
  *    is enqueued on it, nothing synchronises, nothing allocates: the caller supplies the
- *    workspace (rs_scan_workspace_bytes) and reads counters after syncing the stream;
+ *    workspace (rs_scan_workspace_bytes) and reads counters after syncing the stream
+ *    (ONE exception, stated at its declaration: the tensor-core path of rs_scan_batched waits
+ *    for its candidate and hit counts, which size the exact pass and the ordering);
+ *  - no process-global mutable state: the three knobs (rs_set_reserved_sms, rs_set_batched_path,
+ *    rs_prof_begin/_end) and rs_last_error are per calling THREAD, so concurrent callers do
+ *    not see each other's settings; everything else is re-entrant like the reference's
+ *    _pwm.calculate (_pwm.c has no state);
  *  - there is NO CPU fallback: without a CUDA device every device entry point fails.
  *
  * Symbol stream ("codes"), 1 byte per symbol, records concatenated with ONE separator:
@@ -68,13 +74,13 @@ int         rs_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int64_t     rs_padded_count(int64_t n);                /* elements/rows to allocate     */
 int64_t     rs_scan_workspace_bytes(int64_t n, int64_t hit_capacity);
 
-/* SMs the persistent scan kernels leave unoccupied (default 0).  Set it to 1 while a collective runs
+/* SMs the persistent scan kernels launched BY THE CALLING THREAD leave unoccupied (default 0).  Set it to 1 while a collective runs
  * beside a scan (the all-reduce of the background counts in sharded runs): a persistent kernel that fills
  * every SM's shared memory would otherwise make the collective's kernel wait for the scan to end.      */
 int rs_set_reserved_sms(int n);
 
 /* ---- measurement hook (bench.py; no reference counterpart) --------------------------
- * Between rs_prof_begin and rs_prof_end every scan entry point records a CUDA event pair
+ * Between rs_prof_begin and rs_prof_end every scan entry point called by the same thread records a CUDA event pair
  * tightly around its main kernel on the caller's stream (at most max_records pairs);
  * rs_prof_end waits for them and returns the per-launch durations in milliseconds.     */
 int rs_prof_begin(int max_records);
@@ -131,7 +137,8 @@ int rs_host_annotate_structures(const char *text, const int64_t *offsets, const 
  * Strings come as (blob, offsets[n+1]) pairs indexed by rec[r]; Start = start0[r] + 1,
  * End = start0[r] + width; fragments are text[text_pos[r] .. +width) (NULL prints ".").
  * score kinds: 0 float32 (already rounded) as numpy float32 text; 1 the same widened to a Python
- * float; 2 float64 with Python's round(x, 3) applied here; 3 float64 unrounded (averaged profiles).
+ * float; 2 float64 with Python's round(x, 3) applied here; 3 float64 unrounded (averaged profiles);
+ * 4 int32 thousandths of round(x, 3) as rs_scores_dense_struct_milli delivers them (single-modality only).
  * Returns RS_OK and *written; RS_ERR_WORKSPACE when `capacity` is too small (*written = need);
  * RS_ERR_INVALID when a value is outside the covered text formats (caller falls back).        */
 int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const int64_t *rec, const char *id_blob,
@@ -165,6 +172,17 @@ int rs_scores_dense_seq(const uint8_t *d_codes, int64_t n, const double *table_W
                         float *d_out, void *stream);
 int rs_scores_dense_struct(const uint8_t *d_codes, int64_t n, const double *table_Wx7, int W,
                            double *d_out, void *stream);
+/* Structure scores as rnascan PRINTS them: Python's round(score, 3) (rnascan.py:273) of the float64 score, as an
+ * int32 number of thousandths -- 4 B per position instead of 8 for every-position output (-m -inf), the text
+ * "k/1000" is exactly what repr(round(score, 3)) gives.  Special values: RS_MILLI_NAN (no score: the window
+ * holds an invalid symbol or a separator), RS_MILLI_NINF (score -inf), RS_MILLI_NEG0 (rounds to -0.0),
+ * RS_MILLI_RANGE (|score| >= 2e6 or +inf: use rs_scores_dense_struct).  W <= 16.                          */
+#define RS_MILLI_NAN   (-2147483647 - 1)
+#define RS_MILLI_NINF  (-2147483647)
+#define RS_MILLI_NEG0  (-2147483646)
+#define RS_MILLI_RANGE (-2147483645)
+int rs_scores_dense_struct_milli(const uint8_t *d_codes, int64_t n, const double *table_Wx7, int W,
+                                 int32_t *d_out, void *stream);
 int rs_scores_dense_profile(const void *d_profile, int profile_dtype, int64_t n_rows,
                             const uint8_t *d_codes /* may be NULL: no separators */,
                             const double *table_Wx7, int W, double *d_out, void *stream);
@@ -346,9 +364,10 @@ int rs_host_gather_windows(const void *rows, int rows_dtype, int64_t n_rows, con
  * Semantics per motif are exactly rs_scan_fused's.                                        */
 int64_t rs_scan_batched_workspace_bytes(int64_t n, int n_motifs, int table_stride_rows,
                                         int64_t hit_capacity);
-/* 0 = choose (tensor cores from 32 motifs on, fp32 profiles, W <= 12), 1 = per-motif CUDA-core
- * loop, 2 = tensor cores or RS_ERR_INVALID.  Both paths return identical results.  The tensor-core
- * path synchronises the stream (candidate counts decide the size of the exact pass).          */
+/* Per calling thread: 0 = choose (tensor cores from 32 motifs on, fp32 profiles, W <= 12), 1 = per-motif
+ * CUDA-core loop, 2 = tensor cores or RS_ERR_INVALID.  Both paths return identical results.  The tensor-core
+ * path synchronises the stream twice (the candidate count sizes the exact pass, the hit count the ordering):
+ * the one entry point of this ABI that waits for the device.                                  */
 int rs_set_batched_path(int path);
 int rs_last_batched_path(void);          /* 1 or 2: the path the last rs_scan_batched call took */
 int rs_scan_batched(const uint8_t *d_codes, const void *d_profile, int profile_dtype, int64_t n,

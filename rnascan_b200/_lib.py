@@ -15,6 +15,7 @@ RS_F32, RS_F64 = 0, 1
 RS_MODE_STRUCT, RS_MODE_AND = 0, 1
 RS_ROWS_F32, RS_ROWS_F32_SHADOW, RS_ROWS_Q8 = 0, 1, 2
 RS_SEP, RS_RNA_OTHER, RS_SS_OTHER, RS_MAX_W = 0xFF, 0x0C, 0x0F, 64
+RS_MILLI_NAN, RS_MILLI_NINF, RS_MILLI_NEG0, RS_MILLI_RANGE = -2147483648, -2147483647, -2147483646, -2147483645
 
 
 class RnascanCudaError(RuntimeError):
@@ -60,6 +61,7 @@ _SIGS = {
     "rs_hist_rna": ([_vp, _i64, _vp, _vp], _int),
     "rs_scores_dense_seq": ([_vp, _i64, _vp, _int, _vp, _vp], _int),
     "rs_scores_dense_struct": ([_vp, _i64, _vp, _int, _vp, _vp], _int),
+    "rs_scores_dense_struct_milli": ([_vp, _i64, _vp, _int, _vp, _vp], _int),
     "rs_scores_dense_profile": ([_vp, _int, _i64, _vp, _vp, _int, _vp, _vp], _int),
     "rs_profile_stats": ([_vp, _int, _i64, _vp, _vp], _int),
     "rs_scan_seq": ([_vp, _i64, _vp, _int, _dbl, _i64, _vp, _vp, _vp, _vp, _i64, _vp], _int),

@@ -44,7 +44,7 @@ int rs_sm_count()
 // SMs the persistent scan kernels leave free (rs_set_reserved_sms): a collective that runs BESIDE a scan
 // (the all-reduce of the background counts, device.BackgroundFusedScan) needs somewhere to be scheduled --
 // a persistent kernel that fills every SM's shared memory would make it wait for the scan to end.
-static int g_reserved_sms = 0;
+static thread_local int g_reserved_sms = 0;      // per calling thread: set -> launch -> reset never races another caller
 extern "C" int rs_set_reserved_sms(int n)
 {
     if (n < 0 || n > 64) { rs_set_error("rs_set_reserved_sms: 0..64"); return RS_ERR_INVALID; }
@@ -62,9 +62,9 @@ int rs_grid_sms()
 // point, on the caller's stream, so bench.py can report that kernel's own duration inside
 // a longer timed step without synchronising between steps.
 #include <vector>
-static std::vector<cudaEvent_t> g_prof_ev;     // 2 * max_records
-static int g_prof_n = 0, g_prof_cap = 0;
-static bool g_prof_on = false, g_prof_open = false;
+static thread_local std::vector<cudaEvent_t> g_prof_ev;     // 2 * max_records; per calling thread
+static thread_local int g_prof_n = 0, g_prof_cap = 0;
+static thread_local bool g_prof_on = false, g_prof_open = false;
 
 void rs_prof_start(cudaStream_t s)
 {

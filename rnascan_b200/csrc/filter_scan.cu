@@ -123,21 +123,17 @@ __global__ void __launch_bounds__(FT_THREADS, 4) filter_q8_kernel(const __grid_c
         cnt[0] += packed & 0xffu; cnt[1] += (packed >> 8) & 0xffu;
         cnt[2] += (packed >> 16) & 0xffu; cnt[3] += packed >> 24;
 
-        unsigned hitmask = 0, ncand = 0;
+        unsigned candmask = 0;
 #pragma unroll
-        for (int i = 0; i < FT_P; i++) {
-            if (!(acc[i] <= prm.filt_thr)) {
-                ncand++;
-                if (q8_deferred_window(prm, rows8, tid * FT_P + i, t0 + tid * FT_P + i)) hitmask |= 1u << i;
-            }
-        }
-        if (ncand) atomicAdd(prm.st.counters + 1, (unsigned long long)ncand);
+        for (int i = 0; i < FT_P; i++)
+            if (!(acc[i] <= prm.filt_thr)) candmask |= 1u << i;
 
-        const int any = __syncthreads_or(hitmask != 0);
+        const int any = __syncthreads_or(candmask != 0);
         if (any) {
-            emit_tile_hits<FT_THREADS>(prm.st, tile, hitmask, FT_P, [&](int i, int64_t k) {
-                prm.st.pos[k] = prm.pos_base + t0 + tid * FT_P + i;
-            });
+            resolve_tile_candidates<FT_THREADS, FT_P>(
+                prm.st, tile, candmask,
+                [&](int w) { return q8_deferred_window(prm, rows8, w, t0 + w); },
+                [&](int w, int64_t k) { prm.st.pos[k] = prm.pos_base + t0 + w; });
         } else if (tid == 0) {
             prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
         }

@@ -137,13 +137,33 @@ int run_rows(int64_t n_rows, char *out, int64_t capacity, int64_t *written, F fo
 
 }  // namespace
 
+// round(x, 3) delivered by the device as an int32 number of thousandths (rs_scores_dense_struct_milli): the text
+// of repr(k / 1000.0) is the decimal itself -- integer part, '.', the thousandths without trailing zeros (at least
+// one digit).  RS_MILLI_NEG0 is the -0.0 Python prints for scores in (-0.0005, 0].
+bool put_milli(Out &o, int32_t k)
+{
+    if (k == RS_MILLI_NEG0) { o.put_field("-0.0", 4); return true; }
+    if (k <= RS_MILLI_RANGE) return false;               // NaN / -inf / out of range: not a printable hit
+    int64_t v = k;
+    if (v < 0) { o.put('-'); v = -v; }
+    o.put_int(v / 1000);
+    o.put('.');
+    const int frac = (int)(v % 1000);
+    const char d0 = (char)('0' + frac / 100), d1 = (char)('0' + (frac / 10) % 10), d2 = (char)('0' + frac % 10);
+    o.put(d0);
+    if (d1 != '0' || d2 != '0') o.put(d1);
+    if (d2 != '0') o.put(d2);
+    return true;
+}
+
 // Rows of a single-modality scan (modes RNA and SS):
 //   Sequence_ID  Description  Motif_ID  Start  End  Sequence  LogOdds  Match_ID
 // rec[r] indexes the per-record id/description strings; Start = start0[r] + 1, End = start0[r] + width;
 // the fragment is text[text_pos[r] .. +width).  score_kind: 0 = float32 values already rounded,
 // printed as numpy float32 text; 1 = float32 values already rounded, printed as the Python float they
 // widen to (object column, rnascan.py:408 concat with an empty frame); 2 = float64 values, round(x, 3)
-// applied here, printed as Python floats.  Match_ID = match_id_first + r.
+// applied here, printed as Python floats; 4 = int32 thousandths of round(x, 3) computed on the device.
+// Match_ID = match_id_first + r.
 extern "C" int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const int64_t *rec,
                                    const char *id_blob, const int64_t *id_off, const char *desc_blob,
                                    const int64_t *desc_off, const char *motif_id, const int64_t *start0,
@@ -152,7 +172,7 @@ extern "C" int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const
 {
     if (n_rows < 0 || !written || (n_rows > 0 && (!rec || !id_off || !desc_off || !start0 || !scores || !motif_id)))
         return RS_ERR_INVALID;
-    if (score_kind < 0 || score_kind > 2) return RS_ERR_INVALID;
+    if (score_kind < 0 || (score_kind > 2 && score_kind != 4)) return RS_ERR_INVALID;
     const Strings ids{id_blob, id_off}, descs{desc_blob, desc_off};
     const size_t motif_len = strlen(motif_id);
     return run_rows(n_rows, out, capacity, written, [&](Out &o, int64_t a, int64_t b) {
@@ -168,7 +188,8 @@ extern "C" int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const
             bool fine;
             if (score_kind == 0) fine = put_f32(o, static_cast<const float *>(scores)[r]);
             else if (score_kind == 1) fine = put_f64(o, (double)static_cast<const float *>(scores)[r]);
-            else fine = put_f64(o, round3(static_cast<const double *>(scores)[r]));
+            else if (score_kind == 2) fine = put_f64(o, round3(static_cast<const double *>(scores)[r]));
+            else fine = put_milli(o, static_cast<const int32_t *>(scores)[r]);
             if (!fine) return false;
             o.put('\t');
             o.put_int(match_id_first + r);

@@ -183,15 +183,51 @@ __global__ void __launch_bounds__(OH_THREADS) onehot_kernel(const __grid_constan
 #define DW_STAGES  3
 #define DW_STAGE_BYTES (DW_TILE + 32)
 
-template <int A, int W>
+// Python's round(x, 3) of a float as an integer number of thousandths (rnascan.py:273 rounds every reported
+// structure score): the correctly rounded decimal, ties to even only when x * 1000 is EXACTLY half way.
+// x * 1000 = p + e exactly (e from one FMA); rint(p) is already right unless p sits exactly on a half, where
+// the sign of e decides.  Sentinels: RS_MILLI_NAN (no score: invalid symbol / separator), RS_MILLI_NINF
+// (-inf: a zero-probability letter), RS_MILLI_NEG0 (rounds to -0.0, which prints as "-0.0"),
+// RS_MILLI_RANGE (|x| >= 2e6 or +inf: the caller takes the float64 path).
+__device__ __forceinline__ int32_t rs_round3_milli(double x)
+{
+    if (x != x) return RS_MILLI_NAN;
+    if (x == -INFINITY) return RS_MILLI_NINF;
+    if (!(fabs(x) < 2.0e6)) return RS_MILLI_RANGE;
+    const double p = __dmul_rn(x, 1000.0);
+    const double e = __fma_rn(x, 1000.0, -p);
+    double r = rint(p);
+    const double d = __dsub_rn(p, r);
+    if (d == 0.5 && e > 0.0) r += 1.0;
+    else if (d == -0.5 && e < 0.0) r -= 1.0;
+    if (r == 0.0 && (x < 0.0 || (x == 0.0 && signbit(x)))) return RS_MILLI_NEG0;
+    return (int32_t)r;
+}
+
+// OUT: 0 = the calculate() types (float32 for A = 4, float64 for A = 7), 1 = int32 thousandths (A = 7).
+// PREFIX: the first four symbols' partial sum ((t0 + t1) + t2) + t3 -- the reference's own order, so exact --
+// comes from a 7^4-entry table built per CTA: one LDS.64 instead of four.
+template <int A, int W, int OUT>
 __global__ void __launch_bounds__(DW_THREADS) dense_w_kernel(const __grid_constant__ OneHotParams prm)
 {
     constexpr int NW = (W + 3) / 4;                       // words holding one window's symbols
+    constexpr bool PREFIX = (A == 7 && W >= 5);
+    constexpr int J0 = PREFIX ? 4 : 0;
     __shared__ __align__(128) uint8_t s_stage[DW_STAGES * DW_STAGE_BYTES];
     __shared__ __align__(16) double s_ta[W * OH_TS];
+    __shared__ __align__(16) double s_pre[PREFIX ? 2401 : 1];
     __shared__ uint64_t bars[DW_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < W * OH_TS; k += DW_THREADS) s_ta[k] = prm.ta[k];
+    if (PREFIX) {
+        for (int k = tid; k < 2401; k += DW_THREADS) {
+            const int c3 = k % 7, c2 = (k / 7) % 7, c1 = (k / 49) % 7, c0 = k / 343;
+            double v = __dadd_rn(0.0, prm.ta[0 * OH_TS + c0]);
+            v = __dadd_rn(v, prm.ta[1 * OH_TS + c1]);
+            v = __dadd_rn(v, prm.ta[2 * OH_TS + c2]);
+            s_pre[k] = __dadd_rn(v, prm.ta[3 * OH_TS + c3]);
+        }
+    }
     if (tid == 0) {
         for (int s = 0; s < DW_STAGES; s++) mbar_init(&bars[s], 1);
         fence_mbar_init();
@@ -238,8 +274,14 @@ __global__ void __launch_bounds__(DW_THREADS) dense_w_kernel(const __grid_consta
                 else        bad |= x[i] & (x[i] >> 1) & (x[i] >> 2) & (0x01010101u & m);
             }
             double sum = 0.0;
+            if (PREFIX) {
+                const uint32_t c = x[0] & 0x07070707u;                // four codes, 0..7 each
+                uint32_t idx = (c & 0xFFu) * 343u + ((c >> 8) & 0xFFu) * 49u + ((c >> 16) & 0xFFu) * 7u + (c >> 24);
+                idx = min(idx, 2400u);                                // a code 7 makes the window `bad` anyway
+                sum = s_pre[idx];
+            }
 #pragma unroll
-            for (int j = 0; j < W; j++) {
+            for (int j = J0; j < W; j++) {
                 const int sb = 8 * (j & 3);
                 const uint32_t off = sb >= 3 ? ((x[j >> 2] >> (sb - 3)) & 0x38u) : ((x[j >> 2] << 3) & 0x38u);
                 double t;
@@ -248,32 +290,33 @@ __global__ void __launch_bounds__(DW_THREADS) dense_w_kernel(const __grid_consta
             }
             const int64_t gpos = t0 + w;
             if (gpos + W <= prm.n) {
-                if (A == 4) reinterpret_cast<float *>(prm.dense_out)[gpos] = bad ? nanf("") : (float)sum;
-                else        reinterpret_cast<double *>(prm.dense_out)[gpos] = bad ? nan("") : sum;
+                if (OUT == 1)    reinterpret_cast<int32_t *>(prm.dense_out)[gpos] = bad ? RS_MILLI_NAN : rs_round3_milli(sum);
+                else if (A == 4) reinterpret_cast<float *>(prm.dense_out)[gpos] = bad ? nanf("") : (float)sum;
+                else             reinterpret_cast<double *>(prm.dense_out)[gpos] = bad ? nan("") : sum;
             }
         }
         __syncthreads();
     }
 }
 
-template <int A, int W>
+template <int A, int W, int OUT>
 static int launch_dense_w(OneHotParams &prm, cudaStream_t stream)
 {
     prm.n_tiles = (prm.n + DW_TILE - 1) / DW_TILE;
     int64_t grid = (int64_t)rs_sm_count() * 6;
     if (grid > prm.n_tiles) grid = prm.n_tiles;
     rs_prof_start(stream);
-    dense_w_kernel<A, W><<<(unsigned)grid, DW_THREADS, 0, stream>>>(prm);
+    dense_w_kernel<A, W, OUT><<<(unsigned)grid, DW_THREADS, 0, stream>>>(prm);
     rs_prof_stop(stream);
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }
 
-template <int A>
+template <int A, int OUT>
 static int dispatch_dense_w(int W, OneHotParams &prm, cudaStream_t stream)
 {
     switch (W) {
-#define DW_CASE(w) case w: return launch_dense_w<A, w>(prm, stream);
+#define DW_CASE(w) case w: return launch_dense_w<A, w, OUT>(prm, stream);
         DW_CASE(1) DW_CASE(2) DW_CASE(3) DW_CASE(4) DW_CASE(5) DW_CASE(6) DW_CASE(7) DW_CASE(8)
         DW_CASE(9) DW_CASE(10) DW_CASE(11) DW_CASE(12) DW_CASE(13) DW_CASE(14) DW_CASE(15) DW_CASE(16)
 #undef DW_CASE
@@ -320,8 +363,25 @@ static int dense_impl(const uint8_t *d_codes, int64_t n, const double *table, in
     prm.codes_a = d_codes; prm.dense_out = d_out; prm.n = n; prm.padded = rs_padded_count(n);
     prm.n_tiles = (n + OH_TILE - 1) / OH_TILE; prm.W = W;
     fill_table(prm.ta, table, W, A);
-    if (W <= 16) return dispatch_dense_w<A>(W, prm, (cudaStream_t)stream);
+    if (W <= 16) return dispatch_dense_w<A, 0>(W, prm, (cudaStream_t)stream);
     return launch<A, false, true>(prm, (cudaStream_t)stream);
+}
+
+// Every window's structure score as Python's round(score, 3) in thousandths (what rnascan prints, rnascan.py:273):
+// 4 bytes per position instead of 8.  W <= 16.
+extern "C" int rs_scores_dense_struct_milli(const uint8_t *d_codes, int64_t n, const double *table, int W,
+                                            int32_t *d_out, void *stream)
+{
+    int rc = check_args(d_codes, n, table, W);
+    if (rc) return rc;
+    if (W > 16) { rs_set_error("rs_scores_dense_struct_milli: W <= 16 (use rs_scores_dense_struct)"); return RS_ERR_INVALID; }
+    if (n < W) return RS_OK;
+    if (!d_out) { rs_set_error("null output"); return RS_ERR_INVALID; }
+    OneHotParams prm = {};
+    prm.codes_a = d_codes; prm.dense_out = d_out; prm.n = n; prm.padded = rs_padded_count(n);
+    prm.W = W;
+    fill_table(prm.ta, table, W, 7);
+    return dispatch_dense_w<7, 1>(W, prm, (cudaStream_t)stream);
 }
 
 extern "C" int rs_scores_dense_seq(const uint8_t *d_codes, int64_t n, const double *table, int W, float *d_out,

@@ -128,33 +128,30 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __gri
             }
         }
 
-        // ---- guard band: anything not provably below the threshold is re-scored exactly
-        unsigned hitmask = 0;
-        unsigned nexact = 0;
+        // ---- guard band: anything not provably below the threshold is re-scored exactly, the whole CTA sharing
+        //      the tile's candidates (resolve_tile_candidates)
+        unsigned candmask = 0;
 #pragma unroll
-        for (int i = 0; i < FT_P; i++) {
-            if (!(acc[i] <= prm.filt_thr)) {
-                float sq; double st;
-                nexact++;
-                if (prm.defer ? deferred_window(prm, codes, tid * FT_P + i, t0 + tid * FT_P + i)
-                              : exact_window<float>(prm, prof, codes, tid * FT_P + i, t0 + tid * FT_P + i, sq, st))
-                    hitmask |= 1u << i;
-            }
-        }
-        if (nexact) atomicAdd(prm.st.counters + 1, (unsigned long long)nexact);
+        for (int i = 0; i < FT_P; i++)
+            if (!(acc[i] <= prm.filt_thr)) candmask |= 1u << i;
 
-        const int any = __syncthreads_or(hitmask != 0);
+        const int any = __syncthreads_or(candmask != 0);
         if (any) {
-            emit_tile_hits<FT_THREADS>(prm.st, tile, hitmask, FT_P, [&](int i, int64_t k) {
-                float sq; double st;
-                const int w = tid * FT_P + i;
-                prm.st.pos[k] = prm.pos_base + t0 + w;
-                if (prm.defer) return;
-                exact_window<float>(prm, prof, codes, w, t0 + w, sq, st);
-                prm.st.str[k] = st;
-                if (prm.st.seq) prm.st.seq[k] = sq;
-            });
-            __syncthreads();          // staged tile still in use until every hit is written
+            resolve_tile_candidates<FT_THREADS, FT_P>(
+                prm.st, tile, candmask,
+                [&](int w) {
+                    float sq; double st;
+                    return prm.defer ? deferred_window(prm, codes, w, t0 + w)
+                                     : exact_window<float>(prm, prof, codes, w, t0 + w, sq, st);
+                },
+                [&](int w, int64_t k) {
+                    prm.st.pos[k] = prm.pos_base + t0 + w;
+                    if (prm.defer) return;
+                    float sq; double st;
+                    exact_window<float>(prm, prof, codes, w, t0 + w, sq, st);
+                    prm.st.str[k] = st;
+                    if (prm.st.seq) prm.st.seq[k] = sq;
+                });
         } else if (tid == 0) {
             prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
         }
@@ -639,8 +636,8 @@ extern "C" int rs_filter_profile(const uint8_t *d_codes, const void *d_rows, int
 // ------------------------------------------------------------------------------------------------
 // Batched many-PFM scan, CUDA-core path: one fused scan per motif over the same resident
 // streams; every motif's ordered hits are appended behind the previous motif's.
-static int g_batched_path = 0;       // 0 auto, 1 CUDA-core loop, 2 tensor cores (error if not applicable)
-static int g_batched_last = 0;       // path the last rs_scan_batched call actually took (1 or 2)
+static thread_local int g_batched_path = 0;       // 0 auto, 1 CUDA-core loop, 2 tensor cores (error if not applicable)
+static thread_local int g_batched_last = 0;       // path this thread's last rs_scan_batched call took (1 or 2)
 extern "C" int rs_last_batched_path(void) { return g_batched_last; }
 extern "C" int rs_set_batched_path(int path)
 {

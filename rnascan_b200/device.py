@@ -209,6 +209,35 @@ def dense_struct(stream, table):
     return out[:nout]
 
 
+def dense_struct_milli(stream, table):
+    """int32 thousandths of Python's round(score, 3) for every window (rs_scores_dense_struct_milli), W <= 16."""
+    t = _table(table, 7)
+    W = t.shape[0]
+    nout = max(0, stream.n - W + 1)
+    out = torch.empty(max(nout, 1), dtype=torch.int32, device=stream.codes.device)
+    check(lib.rs_scores_dense_struct_milli(_ptr(stream.codes), stream.n, t.ctypes.data, W, _ptr(out), _stream()))
+    return out[:nout]
+
+
+def scan_struct_every_position(stream, table):
+    """The -m -inf scan of a structure stream as it is PRINTED: (pos, round(score, 3) in thousandths, int32) for
+    every window with a finite score (NaN and -inf windows are never reported); 4 bytes per
+    position come back from the device instead of 8.  None when the form does not apply (W > 16, a score
+    outside its range): the caller uses scan_struct_onehot."""
+    t = _table(table, 7)
+    if t.shape[0] > 16:
+        return None
+    host = torch.empty(max(stream.n - t.shape[0] + 1, 0), dtype=torch.int32, pin_memory=True)
+    if host.numel() == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int32)
+    host.copy_(dense_struct_milli(stream, t))
+    m = host.numpy()
+    if (m == _lib.RS_MILLI_RANGE).any():
+        return None
+    pos = np.nonzero((m > _lib.RS_MILLI_RANGE) | (m == _lib.RS_MILLI_NEG0))[0].astype(np.int64)
+    return pos, m[pos]
+
+
 def dense_profile(profile, table, stream=None):
     t = _table(table, 7)
     W = t.shape[0]
@@ -661,6 +690,12 @@ def scan_batched(stream, profile, seq_tables, struct_tables, threshold, capacity
 
 
 # --------------------------------------------------------------------------- host-buffer pipeline
+class _HitOverflow(Exception):
+    def __init__(self, found):
+        Exception.__init__(self, "hit buffer overflow")
+        self.found = int(found)
+
+
 class HostFusedScanner(object):
     """Combined sequence + averaged-profile scan of HOST-resident streams.
 
@@ -699,7 +734,18 @@ class HostFusedScanner(object):
             all_reduce=None):
         """h_codes: pinned uint8[>= n]; h_prof: pinned float32[>= n, 7];
         make_tables(counts int64[8]) -> (seq_table | None, struct_table).
-        Returns (pos, seq_scores, struct_scores) as numpy arrays, positions ascending."""
+        Returns (pos, seq_scores, struct_scores) as numpy arrays, positions ascending.  A chunk whose hits do
+        not fit its buffer makes the buffers grow and the pass run again."""
+        while True:
+            try:
+                return self._run_once(h_codes, h_prof, make_tables, threshold, mode, absrow_max, all_reduce)
+            except _HitOverflow as over:
+                cap = int(over.found * 1.25) + 1024
+                self.hb = [HitBuffers(self.chunk + self.W, cap, self.device) for _ in self.starts]
+                for hb in self.hb[1:]:
+                    hb.work = self.hb[0].work
+
+    def _run_once(self, h_codes, h_prof, make_tables, threshold, mode, absrow_max, all_reduce):
         n, W = self.n, self.W
         comp = torch.cuda.current_stream(self.device)
         self.h2d_bytes = self.d2h_bytes = 0
@@ -756,8 +802,7 @@ class HostFusedScanner(object):
             found = int(hb.counters[0].item())
             self.d2h_bytes += 16
             if found > hb.capacity:
-                raise MemoryError("hit buffer of chunk %d overflowed (%d > %d): raise hits_per_row"
-                                  % (k, found, hb.capacity))
+                raise _HitOverflow(found)
             if found:
                 pos_l.append(hb.pos[:found].cpu().numpy() + c0)
                 str_l.append(hb.struct[:found].cpu().numpy())

@@ -503,8 +503,13 @@ def _round3_f32(scores):
 
 
 def _round3_f64(scores):
-    """round(float, 3) elementwise with Python's exact decimal rounding."""
-    return [round(v, 3) for v in np.asarray(scores, dtype=np.float64).tolist()]
+    """round(float, 3) elementwise with Python's exact decimal rounding.  int32 input = the same values already
+    rounded on the device, in thousandths (device.scan_struct_every_position)."""
+    scores = np.asarray(scores)
+    if scores.dtype == np.int32:
+        from . import _lib
+        return [-0.0 if k == _lib.RS_MILLI_NEG0 else k / 1000.0 for k in scores.tolist()]
+    return [round(v, 3) for v in scores.astype(np.float64).tolist()]
 
 
 ###############################################################################
@@ -688,7 +693,10 @@ def _scan_batch(batch, pm, kind, minscore):
         if kind == "rna":
             pos, scores = device.scan_seq(batch.stream, table, minscore)
         else:
-            pos, scores = device.scan_struct_onehot(batch.stream, table, minscore)
+            every = None
+            if minscore == float("-inf"):               # every position: the device rounds, 4 B per window come back
+                every = device.scan_struct_every_position(batch.stream, table)
+            pos, scores = every if every is not None else device.scan_struct_onehot(batch.stream, table, minscore)
     STATS.add("scored_positions", int(np.maximum(batch.stream.lengths - table.shape[0] + 1, 0).sum()))
     keep, rec, start0 = batch.locate(pos)
     return pos[keep], rec[keep], start0[keep], scores[keep]
@@ -798,13 +806,21 @@ class _Hits(object):
         blobs = _StringBlobs(self.ids, self.descs)
         if self.kind == "rna":                     # float32 text unless a record has no hit (H8, a17)
             kind = 1 if self.any_record_without_hits() else 0
+        elif all(np.asarray(p[4]).dtype == np.int32 for p in self.parts):
+            kind = 4                               # thousandths rounded on the device
         else:
             kind = 2
         header = "\t".join(["Sequence_ID", "Description", "Motif_ID", "Start", "End", "Sequence", "LogOdds",
                             "Match_ID"]) + "\n"
         first, started = 1, False
         for batch, pos, rec, start0, scores in self.parts:
-            sc = _round3_f32(scores) if self.kind == "rna" else np.ascontiguousarray(scores, np.float64)
+            if self.kind == "rna":
+                sc = _round3_f32(scores)
+            elif kind == 4:
+                sc = np.ascontiguousarray(scores, np.int32)
+            else:
+                sc = np.ascontiguousarray(_round3_f64(scores) if np.asarray(scores).dtype == np.int32 else scores,
+                                          np.float64)
             for a in range(0, len(pos), NATIVE_CHUNK_ROWS):
                 b = min(len(pos), a + NATIVE_CHUNK_ROWS)
                 text = _native_rows(b - a, first, rec[a:b], blobs, None, self.motif_id, None, start0[a:b],

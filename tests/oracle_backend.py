@@ -105,6 +105,20 @@ def scan_struct_onehot(stream, table, threshold, capacity=None):
     return pos, sc[pos]
 
 
+def scan_struct_every_position(stream, table):
+    import math
+    t = device._table(table, 7)
+    if t.shape[0] > 16:
+        return None
+    sc = dense_struct(stream, t).numpy()
+    pos = np.nonzero(np.isfinite(sc))[0].astype(np.int64)
+    milli = np.empty(len(pos), np.int32)
+    for k, x in enumerate(sc[pos].tolist()):
+        r = round(x, 3)
+        milli[k] = _lib.RS_MILLI_NEG0 if (r == 0 and math.copysign(1.0, r) < 0) else int(round(r * 1000))
+    return pos, milli
+
+
 def scan_pair_onehot(seq_stream, struct_stream, seq_table, struct_table, threshold, capacity=None):
     a = dense_seq(seq_stream, seq_table).numpy()
     b = dense_struct(struct_stream, struct_table).numpy()
@@ -161,6 +175,7 @@ def install(monkeypatch):
                      ("histogram", histogram), ("dense_seq", dense_seq), ("dense_struct", dense_struct),
                      ("dense_profile", dense_profile), ("scan_seq", scan_seq),
                      ("scan_struct_onehot", scan_struct_onehot), ("scan_pair_onehot", scan_pair_onehot),
+                     ("scan_struct_every_position", scan_struct_every_position),
                      ("scan_fused", scan_fused),
                      ("scan_profile_host", scan_profile_host), ("scan_onehot_bg", scan_onehot_bg),
                      ("scan_batched", scan_batched)):

@@ -256,3 +256,29 @@ def test_filter_entry_point_validates_arguments(dev):
     assert args(_lib.RS_ROWS_F32, 7, float("-inf")) == _lib.RS_ERR_INVALID
     assert args(_lib.RS_ROWS_Q8, 7, 0.0, scale=0.0) == _lib.RS_ERR_INVALID
     assert args(_lib.RS_ROWS_Q8, 7, 0.0) == _lib.RS_OK
+
+
+def test_host_fused_scanner_matches_oracle_and_regrows(dev, oracle):
+    """Round 1's float32 host pipeline (device.HostFusedScanner, kept as bench.py's e2e_f32 leg): chunks with
+    a W-1 overlap, background from the device counts, and hit buffers that grow when a chunk overflows."""
+    from rnascan_b200 import synth
+    W, thr = 7, -1.0
+    codes, off, lengths, rows, _, tq = make_case(300_000, 60, 808, W, np.float32)
+    prob = synth.pfm_rows(W, 4, np.random.default_rng(11))
+
+    def tables(counts8):
+        bg = (np.asarray(counts8[:4], np.float64) + 1) / (float(np.sum(counts8[:4])) + 4)
+        return synth.pssm_table(prob, background=list(bg / bg.sum())), tq
+
+    n = len(codes)
+    h_codes = torch.from_numpy(codes).pin_memory()
+    h_prof = torch.from_numpy(rows).pin_memory()
+    pipe = dev.HostFusedScanner(n, W, chunk_rows=65536, hits_per_row=1e-5)
+    cap0 = pipe.hb[0].capacity
+    pos, sq, sc = pipe.run(h_codes, h_prof, tables, thr, absrow_max=float(np.abs(rows).sum(axis=1).max()))
+    counts = np.array([(codes == k).sum() for k in range(4)] + [0] * 4, np.int64)
+    wpos, wsq, wsc = oracle_hits(oracle, codes, rows, tables(counts)[0], tq, thr, W)
+    assert len(wpos) > cap0 and pipe.hb[0].capacity > cap0
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sq, wsq)
+    assert_same_float(sc, wsc)

@@ -432,6 +432,49 @@ def test_bad_arguments(dev):
         dev.scan_seq(st, np.zeros((7, 4)), float("nan"))
 
 
+# ----------------------------------------------------------------------------- structure scores as printed (thousandths)
+@pytest.mark.parametrize("W", [1, 4, 5, 7, 12, 16])
+@pytest.mark.parametrize("kind", ["logodds", "dyadic", "tiny"])
+def test_dense_struct_milli_is_python_round3(dev, oracle, W, kind):
+    """rs_scores_dense_struct_milli == int(round(score, 3) * 1000) with Python's round (correctly rounded
+    decimal, ties to even only on exact ties) of the oracle's float64 score; dyadic tables make exact ties
+    (x * 1000 = k + 0.5) common, tiny ones exercise -0.0; NaN / -inf windows get their sentinels."""
+    import math
+    from rnascan_b200 import synth, _lib
+    st, codes, lengths = make_stream(dev, 150_000, 40, 900 + W, kind="struct")
+    rng = np.random.default_rng(W)
+    if kind == "logodds":
+        table = synth.pssm_table(synth.pfm_rows(W, 7, rng), background=[synth.SS_P[c] for c in "BEHLMRT"])
+        table[0, 3] = -np.inf
+    elif kind == "dyadic":
+        table = rng.integers(-40, 41, size=(W, 7)).astype(np.float64) / 16.0 + 0.0625 * (rng.random((W, 7)) < 0.5) / 2
+    else:
+        table = (rng.random((W, 7)) - 0.5) * 4e-4
+    got = dev.dense_struct_milli(st, table).cpu().numpy()
+    want_sc = oracle.alpha_scores(synth.to_text(codes, "struct"), table, "BEHLMRT")
+    want_sc[window_has_sep(codes, W)] = np.nan
+    want = np.empty(len(want_sc), np.int64)
+    for k, x in enumerate(want_sc.tolist()):
+        if x != x:
+            want[k] = _lib.RS_MILLI_NAN
+        elif x == -math.inf:
+            want[k] = _lib.RS_MILLI_NINF
+        else:
+            r = round(x, 3)
+            want[k] = _lib.RS_MILLI_NEG0 if (r == 0 and math.copysign(1.0, r) < 0) else int(round(r * 1000))
+    assert np.array_equal(got.astype(np.int64), want)
+    if kind == "dyadic":
+        frac = np.abs(want_sc[np.isfinite(want_sc)] * 1000) % 1
+        assert (frac == 0.5).sum() > 100                       # exact ties really occurred
+    if kind == "tiny":
+        assert (want == _lib.RS_MILLI_NEG0).sum() > 100
+    # the every-position scan built on it: finite windows only, same positions as the float64 scan
+    pos, milli = dev.scan_struct_every_position(st, table)
+    p64, s64 = dev.scan_struct_onehot(st, table, float("-inf"))
+    assert np.array_equal(pos, p64)
+    assert np.array_equal(milli.astype(np.int64), want[pos])
+
+
 # ----------------------------------------------------------------------------- batched many-PFM scan
 @pytest.mark.parametrize("with_seq", [True, False])
 def test_scan_batched_float64_rows_through_the_float32_shadow(dev, oracle, with_seq):
