@@ -373,8 +373,10 @@ def measure(args, wl, steps, ctx, full, n_target):
     counts = torch.zeros(8, dtype=torch.int64, device=device)
     counts_host = torch.zeros(8, dtype=torch.int64).pin_memory()
     hb = dev.HitBuffers(n, max(1 << 16, n // 256), device)
-    # C3: every window's score as rnascan prints it -- round(score, 3) in int32 thousandths, 4 B per position
-    dense_out = torch.empty(n, dtype=torch.int32, device=device) if wl == "c3" else None
+    # C3: every window's float64 score (the calculate() result) for the device-resident figure; the end-to-end leg
+    # brings back what rnascan prints -- round(score, 3) as int32 thousandths, 4 B per position
+    dense_out = torch.empty(n, dtype=torch.float64, device=device) if wl == "c3" else None
+    milli_out = torch.empty(n, dtype=torch.int32, device=device) if wl == "c3" else None
     absmax = 1.0
     if wl in ("c4", "c5"):
         absmax = dev.ProfileStream.from_device(prof, n).absrow_max()
@@ -387,6 +389,7 @@ def measure(args, wl, steps, ctx, full, n_target):
         hb.work = torch.empty(hb.work_bytes, dtype=torch.uint8, device=device)
         check(lib.rs_set_batched_path({"auto": 0, "cuda": 1, "tensor": 2}[args.c5_path]))
     launches = [0]
+    c3_milli = [False]
     bgscan = None
     if wl == "c4" and not args.serial_bg:
         # the structure-only candidate scan overlaps histogram -> all-reduce -> host log-odds (side stream);
@@ -440,7 +443,10 @@ def measure(args, wl, steps, ctx, full, n_target):
                                   _ptr(hb.seq), _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, sptr))
             launches[0] += 3                                # decision table, scan, finish (segment scan + expansion)
         else:
-            check(lib.rs_scores_dense_struct_milli(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
+            if c3_milli[0]:
+                check(lib.rs_scores_dense_struct_milli(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(milli_out), sptr))
+            else:
+                check(lib.rs_scores_dense_struct(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
             launches[0] += 1
 
     def barrier():
@@ -548,7 +554,8 @@ def measure(args, wl, steps, ctx, full, n_target):
         if wl == "c5":
             h_prof = torch.empty(prof.shape, dtype=torch.float32).pin_memory()
             h_prof.copy_(prof)
-        h_out = torch.empty(dense_out.shape, dtype=dense_out.dtype).pin_memory() if wl == "c3" else None
+        h_out = torch.empty(milli_out.shape, dtype=milli_out.dtype).pin_memory() if wl == "c3" else None
+        c3_milli[0] = wl == "c3"
         h_pos = torch.empty(hb.capacity, dtype=torch.int64).pin_memory()
         h_sc = torch.empty(hb.capacity, dtype=torch.float64).pin_memory()
         io = [0, 0]
@@ -559,7 +566,7 @@ def measure(args, wl, steps, ctx, full, n_target):
                 prof.copy_(h_prof, non_blocking=True); io[0] += prof.numel() * 4
             step()
             if wl == "c3":
-                h_out.copy_(dense_out, non_blocking=True); io[1] = dense_out.numel() * 4
+                h_out.copy_(milli_out, non_blocking=True); io[1] = milli_out.numel() * 4
                 stream.synchronize()
             else:
                 stream.synchronize()
@@ -600,11 +607,11 @@ def measure(args, wl, steps, ctx, full, n_target):
         "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,      # run_b200 sets `scaling`
         "dtype": "f32 filter + f64 exact re-score (sequence: f64 accumulate -> f32)" if wl == "c4" else
-                 ("f64 accumulate -> f32" if wl == "c2" else ("f64 (printed form: int32 thousandths)" if wl == "c3" else
+                 ("f64 accumulate -> f32" if wl == "c2" else ("f64" if wl == "c3" else
                                                               "f32 filter + f64 exact re-score, per motif")),
         "data": "synthetic (SURVEY.md 8d shapes; generated on device, seed 4000+rank)",
         "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile, fused AND scan",
-                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, every position (f64 score -> round(x, 3) as int32 thousandths)",
+                                "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan, every position: dense f64 scores on the device; e2e returns round(x, 3) as int32 thousandths",
                                 "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure" % N_MOTIFS_C5}[wl],
                    "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
                    "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
@@ -620,7 +627,7 @@ def measure(args, wl, steps, ctx, full, n_target):
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world},
         "gpu_launches": n_launch,
         "roofline": {"bound": "hbm", "kernel": {"c4": "fused_filter_kernel<7>", "c2": "kmer_scan_kernel<7>",
-                                               "c3": "dense_w_kernel<7,7,1>",
+                                               "c3": "dense_w_kernel<7,7,0>",
                                                "c5": "fused_filter_kernel<W> x %d motifs" % N_MOTIFS_C5}[wl],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],

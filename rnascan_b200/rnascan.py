@@ -315,6 +315,37 @@ class _Batch(object):
         self.stream = device.SymbolStream.from_texts(texts, kind)
         self._raw = None
 
+    @classmethod
+    def from_pieces(cls, ids, descriptions, text, codes, offsets, lengths, kind, pieces):
+        """This rank's pieces (shard.plan_shards: (record, start, stop, own_stop)) cut out of the natively parsed
+        arrays of the whole input -- slices of `codes` / `text`, no Python strings."""
+        from . import device, _lib
+        n = len(pieces)
+        rec = np.array([p[0] for p in pieces], np.int64)
+        a = np.array([p[1] for p in pieces], np.int64)
+        b = np.array([p[2] for p in pieces], np.int64)
+        o = np.array([p[3] for p in pieces], np.int64)
+        ln = b - a
+        poff = np.zeros(n, np.int64)
+        if n > 1:
+            np.cumsum(ln[:-1] + 1, out=poff[1:])
+        total = int(ln.sum() + n)
+        pcodes = np.full(total, _lib.RS_SEP, np.uint8)
+        ptext = np.full(total, ord("\n"), np.uint8)
+        for k in range(n):
+            src = int(offsets[rec[k]] + a[k])
+            pcodes[poff[k]:poff[k] + ln[k]] = codes[src:src + ln[k]]
+            ptext[poff[k]:poff[k] + ln[k]] = text[src:src + ln[k]]
+        self = cls.__new__(cls)
+        self.ids, self.descriptions, self.kind = ids, descriptions, kind
+        self.texts = _LazyTexts(ptext, poff, ln)
+        self.full_texts = _LazyTexts(text, np.asarray(offsets, np.int64), np.asarray(lengths, np.int64))
+        self.record, self.piece_start = rec, a
+        self.own = np.where(o >= b, b, o) - a
+        self.stream = device.SymbolStream(pcodes, poff, ln, kind=kind)
+        self._raw = ptext
+        return self
+
     def overlap_counts(self):
         """Counts (int64[8]) of the symbols this rank holds but does not own (the overlap
         tails of split records); the device histogram minus these is the owned count."""
@@ -386,7 +417,29 @@ def _read_fasta_bytes(fasta_file):
 def _native_batch(fasta_file, alphabet):
     """Parse + pre-process + encode a FASTA input in one native pass (rs_host_fasta_*); None when
     the input is not plain ASCII or too large for one batch (the Python parser handles those)."""
-    from . import device, _lib
+    from . import device
+    native = _native_parse(fasta_file, alphabet, MAX_BATCH_SYMBOLS)
+    if native is None:
+        return None
+    text, codes, off, ln, ids, descs, kind = native
+    n_rec = len(ids)
+    batch = _Batch.__new__(_Batch)
+    batch.ids, batch.descriptions, batch.kind = ids, descs, kind
+    batch.texts = batch.full_texts = _LazyTexts(text, off, ln)
+    batch.record = np.arange(n_rec, dtype=np.int64)
+    batch.piece_start = np.zeros(n_rec, np.int64)
+    batch.own = None
+    batch.stream = device.SymbolStream(codes, off if n_rec else None, ln if n_rec else None, kind=kind) \
+        if n_rec else device.SymbolStream(np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int64), kind=kind)
+    batch._raw = text
+    return batch
+
+
+def _native_parse(fasta_file, alphabet, max_symbols=None):
+    """(text uint8[], codes uint8[], offsets, lengths, ids, descriptions, kind) of a FASTA input from the native
+    two-pass parser, records laid out one after the other with one separator each; None when it does not
+    apply (non-ASCII input, DNA target alphabet, unreadable file, more than `max_symbols`)."""
+    from . import _lib
     rna_target = _seq.is_ambiguous_rna_alphabet(alphabet)
     kind = _kind_of(alphabet)
     if kind == "rna" and not rna_target:
@@ -402,7 +455,7 @@ def _native_batch(fasta_file, alphabet):
     _lib.check(_lib.lib.rs_host_fasta_index(buf.ctypes.data if len(buf) else 0, len(buf), sizes[0:].ctypes.data,
                                             sizes[1:].ctypes.data, sizes[2:].ctypes.data))
     n_rec, n_sym, n_title = (int(v) for v in sizes)
-    if n_sym + n_rec > MAX_BATCH_SYMBOLS:
+    if max_symbols is not None and n_sym + n_rec > max_symbols:
         return None
     text = np.empty(max(n_sym + n_rec, 1), np.uint8)
     codes = np.empty(max(n_sym + n_rec, 1), np.uint8)
@@ -417,16 +470,7 @@ def _native_batch(fasta_file, alphabet):
     blob = titles[:n_title].tobytes().decode("ascii")
     descs = [blob[a:b] for a, b in zip(toff[:-1].tolist(), toff[1:].tolist())]
     ids = [(d.split(None, 1) or [""])[0] for d in descs]
-    batch = _Batch.__new__(_Batch)
-    batch.ids, batch.descriptions, batch.kind = ids, descs, kind
-    batch.texts = batch.full_texts = _LazyTexts(text, off, ln)
-    batch.record = np.arange(n_rec, dtype=np.int64)
-    batch.piece_start = np.zeros(n_rec, np.int64)
-    batch.own = None
-    batch.stream = device.SymbolStream(codes, off if n_rec else None, ln if n_rec else None, kind=kind) \
-        if n_rec else device.SymbolStream(np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int64), kind=kind)
-    batch._raw = text
-    return batch
+    return text, codes, off, ln, ids, descs, kind
 
 
 NATIVE_INGEST = True                 # tests switch it off to exercise the Python parser
@@ -438,8 +482,17 @@ def _kind_of(alphabet):
 
 def _sharded_batch(fasta_file, alphabet, rank, size):
     """This rank's share of the input: contiguous pieces balanced by total length, split
-    records overlapping by RS_MAX_W - 1 symbols (enough for any motif width)."""
+    records overlapping by RS_MAX_W - 1 symbols (enough for any motif width).  The file is parsed and encoded
+    natively on host threads (rs_host_fasta_*: no Python object per record); only this rank's pieces are
+    packed and uploaded.  Inputs outside the native parser's scope go through the Python parser."""
     from . import shard, _lib
+    if NATIVE_INGEST:
+        native = _native_parse(fasta_file, alphabet)
+        if native is not None:
+            text, codes, off, ln, ids, descs, kind = native
+            plan = shard.plan_shards(ln.tolist(), size, _lib.RS_MAX_W)
+            mine = plan[rank]
+            return _Batch.from_pieces(ids, descs, text, codes, off, ln, kind, mine)
     ids, descs, texts = [], [], []
     for rec in parse_sequences(fasta_file):
         ids.append(rec.id)
@@ -712,10 +765,19 @@ def _gather_parts(parts, n_records, ids, descs):
     start0 = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
     scores = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0)
     frags = [f for p in parts for f in p[3]]
-    gathered = shard.gather_objects((rec, start0, scores, frags))
+    width = len(frags[0]) if frags else 1
+    # the fragments travel as one (hits, width) byte matrix, the rest as plain arrays: no pickled Python objects
+    frag_bytes = np.frombuffer("".join(frags).encode("latin-1"), np.uint8).reshape(len(frags), width) if frags \
+        else np.zeros((0, width), np.uint8)
+    gathered = shard.gather_arrays([rec, start0, scores, frag_bytes])
     if gathered is None:
         return None
-    return [(g[0], g[1], g[2], g[3], ids, descs) for g in gathered]
+    out = []
+    for g_rec, g_start, g_scores, g_frag in gathered:
+        texts = [] if not len(g_frag) else \
+            np.ascontiguousarray(g_frag).view("S%d" % g_frag.shape[1]).ravel().astype("U%d" % g_frag.shape[1]).tolist()
+        out.append((g_rec, g_start, g_scores, texts, ids, descs))
+    return out
 
 
 def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
@@ -1149,10 +1211,11 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         arrays = (list(hit_names), start0.copy(), np.zeros(0, np.float32) if seq_scores is None else seq_scores,
                   np.asarray(scores, np.float64))
     if size > 1:
-        gathered = shard.gather_objects((hit_names, start0, scores))
+        first = all_names.index(names[0]) if names else 0          # this rank's files are a contiguous range
+        gathered = shard.gather_arrays([rec + first, start0, np.asarray(scores, np.float64)])
         if gathered is None:
             return (pd.DataFrame(), n_files, None) if want_arrays else (pd.DataFrame(), n_files)
-        hit_names = [x for g in gathered for x in g[0]]
+        hit_names = [all_names[r] for g in gathered for r in g[0].tolist()]
         start0 = np.concatenate([g[1] for g in gathered])
         scores = np.concatenate([g[2] for g in gathered])
     first_has_hits = None

@@ -74,6 +74,49 @@ def gather_objects(obj, dst=0):
     return out if dist.get_rank() == dst else None
 
 
+def gather_arrays(arrays, dst=0):
+    """Every rank's list of numpy arrays on rank `dst` as [[rank 0's arrays], [rank 1's], ...] (None elsewhere).
+    The payload travels as ONE byte tensor per rank through all_gather (padded to the longest rank): no
+    pickling of the data, only the shapes/dtypes go through the object channel."""
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:
+        return [arrays]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [arrays]
+    size, rank = dist.get_world_size(), dist.get_rank()
+    meta = [(a.shape, a.dtype.str) for a in arrays]
+    nbytes = int(sum(a.nbytes for a in arrays))
+    metas = [None] * size
+    dist.all_gather_object(metas, (meta, nbytes))
+    longest = max(1, max(m[1] for m in metas))
+    on_gpu = dist.get_backend() == "nccl"
+    buf = np.zeros(longest, np.uint8)
+    off = 0
+    for a in arrays:
+        buf[off:off + a.nbytes] = a.view(np.uint8).reshape(-1)
+        off += a.nbytes
+    mine = torch.from_numpy(buf)
+    if on_gpu:
+        mine = mine.cuda()
+    parts = [torch.empty_like(mine) for _ in range(size)]
+    dist.all_gather(parts, mine)
+    if rank != dst:
+        return None
+    out = []
+    for (meta_r, _), part in zip(metas, parts):
+        raw = part.cpu().numpy()
+        off, items = 0, []
+        for shape, dt in meta_r:
+            n = int(np.prod(shape)) * np.dtype(dt).itemsize
+            items.append(raw[off:off + n].view(np.dtype(dt)).reshape(shape).copy())
+            off += n
+        out.append(items)
+    return out
+
+
 def broadcast_object(obj, src=0):
     """Rank `src`'s `obj` on every rank (identity without a group)."""
     try:

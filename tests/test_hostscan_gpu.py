@@ -262,7 +262,8 @@ def test_host_fused_scanner_matches_oracle_and_regrows(dev, oracle):
     """Round 1's float32 host pipeline (device.HostFusedScanner, kept as bench.py's e2e_f32 leg): chunks with
     a W-1 overlap, background from the device counts, and hit buffers that grow when a chunk overflows."""
     from rnascan_b200 import synth
-    W, thr = 7, -1.0
+    from rnascan_b200 import _lib
+    W, thr = 7, -3.0
     codes, off, lengths, rows, _, tq = make_case(300_000, 60, 808, W, np.float32)
     prob = synth.pfm_rows(W, 4, np.random.default_rng(11))
 
@@ -275,10 +276,16 @@ def test_host_fused_scanner_matches_oracle_and_regrows(dev, oracle):
     h_prof = torch.from_numpy(rows).pin_memory()
     pipe = dev.HostFusedScanner(n, W, chunk_rows=65536, hits_per_row=1e-5)
     cap0 = pipe.hb[0].capacity
-    pos, sq, sc = pipe.run(h_codes, h_prof, tables, thr, absrow_max=float(np.abs(rows).sum(axis=1).max()))
+    amax = float(np.abs(rows).sum(axis=1).max())
+    pos, sq, sc = pipe.run(h_codes, h_prof, tables, thr, absrow_max=amax)
     counts = np.array([(codes == k).sum() for k in range(4)] + [0] * 4, np.int64)
     wpos, wsq, wsc = oracle_hits(oracle, codes, rows, tables(counts)[0], tq, thr, W)
-    assert len(wpos) > cap0 and pipe.hb[0].capacity > cap0
     assert np.array_equal(pos, wpos)
     assert_same_float(sq, wsq)
+    assert_same_float(sc, wsc)
+    # structure only: far more hits than a chunk's first buffer holds
+    pos, sq, sc = pipe.run(h_codes, h_prof, lambda c: (None, tq), thr, mode=_lib.RS_MODE_STRUCT, absrow_max=amax)
+    wpos, _, wsc = oracle_hits(oracle, codes, rows, None, tq, thr, W)
+    assert len(wpos) > 4 * cap0 and pipe.hb[0].capacity > cap0
+    assert np.array_equal(pos, wpos) and sq is None
     assert_same_float(sc, wsc)
