@@ -42,6 +42,9 @@
 #define TC_B_BYTES    (TC_WMAX * TC_N * 16)          // 49152
 #define TC_THREADS  512
 #define TC_CBUF     1024                // staged candidate keys per epilogue warp (>= 32 lanes x 32 motifs)
+#define TC_MASK_STAGES 8                // sequence masks of 8 tiles in flight: the converters run at most 4 tiles ahead
+                                        // of the MMAs, the MMAs 2 ahead of the epilogue, so a stage is long read when
+                                        // it is written again
 
 struct TcParams {
     const float   *profile;             // fp32 [padded][7]
@@ -51,6 +54,11 @@ struct TcParams {
     unsigned long long *cand;           // candidate keys: motif << 40 | position
     unsigned long long *cand_count;
     int64_t        cand_capacity;
+    // RS_MODE_AND: the sequence condition as a bit per (8-mer, motif), applied before a candidate is staged
+    const uint8_t  *codes;              // symbol stream (NULL: structure-only scan, no mask)
+    const uint32_t *seqmask;            // [65536][mask_words]: bit (31 - k) of word c = motif 32 c + k may pass
+    int            mask_words;          // words per 8-mer over ALL motif groups
+    uint32_t       wmask[TC_WMAX + 1][TC_N / 32];   // [f]: motifs of this group whose width is <= f
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -164,9 +172,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_raw + TC_STAGES * TC_RAW_BYTES);
     uint64_t *raw_full = bars, *raw_empty = bars + TC_STAGES, *a_full = bars + 2 * TC_STAGES,
              *a_empty = bars + 3 * TC_STAGES, *acc_full = bars + 4 * TC_STAGES, *acc_empty = acc_full + 2,
-             *b_full = acc_empty + 2;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(b_full + 1);
+             *b_full = acc_empty + 2, *mask_full = b_full + 1;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(mask_full + TC_MASK_STAGES);
     unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(smem + 96 * 1024);   // 4 x TC_CBUF keys
+    uint4 *s_mask = reinterpret_cast<uint4 *>(smem + 160 * 1024);   // [TC_MASK_STAGES][128 positions][2 x uint4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -178,6 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
         }
         for (int t = 0; t < 2; t++) { mbar_init(&acc_full[t], 1); mbar_init(&acc_empty[t], 8); }
         mbar_init(b_full, 1);
+        for (int k = 0; k < TC_MASK_STAGES; k++) mbar_init(&mask_full[k], 4);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -257,8 +267,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             __syncwarp();
             cnt = 0;
         };
+        // RS_MODE_AND: the converter warps leave every position's sequence mask (8 words = 256 motifs) in shared memory
+        const bool use_mask = prm.codes != nullptr;
         for (int64_t it = 0; it < my_tiles; it++) {
             const int t = (int)(it & 1);
+            uint4 mk = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (use_mask) {
+                const int ms = (int)(it % TC_MASK_STAGES);
+                mbar_wait(&mask_full[ms], (uint32_t)((it / TC_MASK_STAGES) & 1));
+                mk = s_mask[(ms * TC_M + q * 32 + lane) * 2 + half];
+            }
+            const uint32_t smask[TC_N / 64] = {mk.x, mk.y, mk.z, mk.w};
             mbar_wait(&acc_full[t], (uint32_t)((it >> 1) & 1));
             if (warp == 4 && lane == 0) TC_STAMP(it, 3);
             tc_fence_after();
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             constexpr int NCH = TC_N / 64;
             const int c_first = half * NCH;
             uint32_t va[32], vb[32];
-            auto process = [&](uint32_t (&v)[32], int c) {
+            auto process = [&](uint32_t (&v)[32], int c, uint32_t seq_ok) {
                 // sign bits of the 32 accumulators, one funnel shift each: candidate <=> sign clear
                 // (accumulator >= +0; unused motif columns carry a -1 bias so they never qualify)
                 uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;           // four independent chains of 8
@@ -282,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
                     n3 = __funnelshift_l(v[24 + k], n3, 1);
                 }
                 const uint32_t neg = (n0 << 24) | (n1 << 16) | (n2 << 8) | n3;        // bit (31-k) = sign of v[k]
-                uint32_t cand = in_range ? ~neg : 0u;
+                uint32_t cand = in_range ? (~neg & seq_ok) : 0u;
                 if (__any_sync(0xffffffffu, cand != 0)) {                  // warp-uniform, ~40 % of chunks at m = 6
                     const unsigned mine = __popc(cand);
                     unsigned incl = mine;
@@ -310,11 +329,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
                 if ((i & 1) == 0) {
                     tc_ld_wait(va);
                     if (i + 1 < NCH) tc_ld32_issue(taddr + 32u * (c_first + i + 1), vb);
-                    process(va, c_first + i);
+                    process(va, c_first + i, smask[i]);
                 } else {
                     tc_ld_wait(vb);
                     if (i + 1 < NCH) tc_ld32_issue(taddr + 32u * (c_first + i + 1), va);
-                    process(vb, c_first + i);
+                    process(vb, c_first + i, smask[i]);
                 }
             }
             tc_fence_before();
@@ -326,8 +345,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
     } else if (warp >= 8 && warp < 12) {
         // ================= converters: fp32 x 7 -> bf16 x 8 (channel 7 := 1.0, the bias input)
         const int ct = tid - 256;                 // 0..127
+        // RS_MODE_AND: sequence mask of position (tile, ct) = seqmask[8-mer its window starts with], restricted to
+        // the motifs no wider than the distance to the first invalid symbol (prm.wmask).  The symbols are fetched one
+        // tile ahead, the mask row is requested before the conversion work and stored after it.
+        const bool use_mask = prm.codes != nullptr;
+        auto load_codes = [&](int64_t it) {
+            const int64_t pos = (first + it * stride) * TC_M + ct;
+            uint4 w = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);       // beyond the end: separators
+            if (pos < prm.n) {
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(prm.codes + (pos & ~(int64_t)3));
+                w = make_uint4(__ldg(cw), __ldg(cw + 1), __ldg(cw + 2), __ldg(cw + 3));
+            }
+            return w;
+        };
+        uint4 cw_next = make_uint4(0u, 0u, 0u, 0u);
+        if (use_mask && my_tiles > 0) cw_next = load_codes(0);
         for (int64_t it = 0; it < my_tiles; it++) {
             const int s = (int)(it % TC_STAGES);
+            uint4 m_lo = make_uint4(0u, 0u, 0u, 0u), m_hi = m_lo;
+            int f = 0;
+            if (use_mask) {
+                const uint4 cw = cw_next;
+                const unsigned sh = (unsigned)(((first + it * stride) * TC_M + ct) & 3) * 8u;
+                const uint32_t w0 = __funnelshift_r(cw.x, cw.y, sh), w1 = __funnelshift_r(cw.y, cw.z, sh),
+                               w2 = __funnelshift_r(cw.z, cw.w, sh);
+                // 8-mer index: symbol k in bits 2k, 2k+1 (the multiply gathers four 2-bit fields into the top byte)
+                const uint32_t kmer = (((w0 & 0x03030303u) * 0x01041040u) >> 24) |
+                                      ((((w1 & 0x03030303u) * 0x01041040u) >> 24) << 8);
+                // first symbol that is not A,C,G,U (bits 2,3 set: other, separator): a motif wider than that is out
+                const uint32_t i0 = w0 & 0x0C0C0C0Cu, i1 = w1 & 0x0C0C0C0Cu, i2 = w2 & 0x0C0C0C0Cu;
+                f = i0 ? (__ffs(i0) - 1) >> 3 : (i1 ? 4 + ((__ffs(i1) - 1) >> 3) : (i2 ? 8 + ((__ffs(i2) - 1) >> 3) : 12));
+                const uint4 *row = reinterpret_cast<const uint4 *>(prm.seqmask + (size_t)kmer * prm.mask_words +
+                                                                   (prm.motif_base >> 5));
+                m_lo = __ldg(row); m_hi = __ldg(row + 1);
+                if (it + 1 < my_tiles) cw_next = load_codes(it + 1);
+            }
             mbar_wait(&raw_full[s], (uint32_t)((it / TC_STAGES) & 1));
             if (it >= TC_STAGES) mbar_wait(&a_empty[s], (uint32_t)(((it / TC_STAGES) - 1) & 1));
             if (warp == 8 && lane == 0) TC_STAMP(it, 5);
@@ -346,10 +398,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
                 o.w = *reinterpret_cast<uint32_t *>(&h3);
                 arow[r] = o;
             }
+            if (use_mask) {
+                const int ms = (int)(it % TC_MASK_STAGES);
+                const uint32_t *wm = prm.wmask[f];
+                s_mask[(ms * TC_M + ct) * 2] = make_uint4(m_lo.x & wm[0], m_lo.y & wm[1], m_lo.z & wm[2], m_lo.w & wm[3]);
+                s_mask[(ms * TC_M + ct) * 2 + 1] = make_uint4(m_hi.x & wm[4], m_hi.y & wm[5], m_hi.z & wm[6], m_hi.w & wm[7]);
+            }
             fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (warp == 8 && lane == 0) TC_STAMP(it, 6);
-            if (lane == 0) { tc_mbar_arrive(&a_full[s]); tc_mbar_arrive(&raw_empty[s]); }
+            if (lane == 0) {
+                if (use_mask) tc_mbar_arrive(&mask_full[it % TC_MASK_STAGES]);
+                tc_mbar_arrive(&a_full[s]); tc_mbar_arrive(&raw_empty[s]);
+            }
         }
     }
 
@@ -359,6 +420,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------------ sequence mask
+// seqmask[kmer][word]: for the 8 symbols a window starts with, which motifs' SEQUENCE score can exceed the threshold.
+// W <= 8: the decision itself -- the reference's arithmetic (_pwm.c:36-65: float64 adds in j order, one cast to
+// float32; compared widened) over the first W symbols.  W > 8: the exact prefix sum plus the largest
+// the remaining rows can add (a superset; the exact pass decides).  Bit (31 - k) of word c stands for motif 32 c + k,
+// the order in which the epilogue's sign masks come out.
+__global__ void __launch_bounds__(256) seqmask_build_kernel(uint32_t *mask, int mask_words, const double *seq_tables,
+                                                            const int *widths, int n_motifs, int stride_rows,
+                                                            double threshold)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)65536 * mask_words) return;
+    const uint32_t kmer = (uint32_t)(t / mask_words);
+    const int word = (int)(t % mask_words);
+    uint32_t bits = 0;
+    for (int k = 0; k < 32; k++) {
+        const int m = word * 32 + k;
+        if (m >= n_motifs) break;
+        const int W = widths[m];
+        const double *tab = seq_tables + (size_t)m * stride_rows * 4;
+        double sum = 0.0;
+        const int wp = W < 8 ? W : 8;
+        for (int j = 0; j < wp; j++) sum = __dadd_rn(sum, tab[j * 4 + ((kmer >> (2 * j)) & 3u)]);
+        bool pass;
+        if (W <= 8) {
+            pass = (double)(float)sum > threshold;
+        } else {
+            bool inf = false;
+            for (int j = 8; j < W; j++) {
+                const double mx = fmax(fmax(tab[j * 4], tab[j * 4 + 1]), fmax(tab[j * 4 + 2], tab[j * 4 + 3]));
+                if (mx != mx || mx == INFINITY) inf = true;      // NaN / +inf entries: no bound, let the exact pass decide
+                sum += mx;
+            }
+            // the sequential float64 adds of the real score differ from this sum by a few ulps at most
+            const double bound = sum + fabs(sum) * 1e-12 + 1e-300;
+            pass = inf || sum != sum || (double)(float)bound > threshold;
+        }
+        if (pass) bits |= 1u << (31 - k);
+    }
+    mask[t] = bits;
 }
 
 // ------------------------------------------------------------------------------------------------ exact re-score
@@ -596,8 +699,12 @@ int64_t rs_batched_tc_work_bytes(int64_t n, int n_motifs, int stride_rows, int64
     while (np2 < hit_capacity) np2 <<= 1;
     const int groups = (n_motifs + TC_N - 1) / TC_N;
     return 256 + (int64_t)groups * TC_B_BYTES + cand_cap * 8 + np2 * 8 + 1024 +
-           rs_roundup((int64_t)n_motifs * stride_rows * 11 * 8, 256) + rs_roundup((int64_t)n_motifs * 4, 256);
+           rs_roundup((int64_t)n_motifs * stride_rows * 11 * 8, 256) + rs_roundup((int64_t)n_motifs * 4, 256) +
+           (int64_t)65536 * groups * (TC_N / 32) * 4;           // sequence mask: 2 MB per group of 256 motifs
 }
+
+static int g_tc_seqmask = 1;          // experiment switch (tools/c5_perf.py): sequence mask in the epilogue on / off
+extern "C" int rs_debug_set_tc_seqmask(int on) { g_tc_seqmask = on; return RS_OK; }
 
 // Returns RS_OK, or -1 when this path does not apply (caller falls back to the CUDA-core loop).
 int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n, int n_motifs, const int *widths,
@@ -672,7 +779,9 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     double *d_tq = (double *)(wk + off);                             off += (int64_t)n_motifs * stride_rows * 7 * 8;
     double *d_ts = (double *)(wk + off);                             off += (int64_t)n_motifs * stride_rows * 4 * 8;
     off = rs_roundup(off, 256);
-    int *d_w = (int *)(wk + off);
+    int *d_w = (int *)(wk + off);                                    off += rs_roundup((int64_t)n_motifs * 4, 256);
+    uint32_t *d_seqmask = (uint32_t *)(wk + off);
+    const int mask_words = groups * (TC_N / 32);
 
     RS_CUDA(cudaMemsetAsync(cand_count, 0, 16, st));
     RS_CUDA(cudaMemsetAsync(d_motif_counters2, 0, sizeof(uint64_t) * 2 * (size_t)n_motifs, st));
@@ -686,8 +795,8 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     // ---- tensor-core filter, one launch per group of 256 motifs
     // 160 KB of dynamic shared memory: more than half an SM's, so exactly one CTA (which owns all
     // 512 TMEM columns) is resident per SM
-    const size_t smem = 160 * 1024;
-    static_assert(TC_B_BYTES + TC_STAGES * (TC_A_BYTES + TC_RAW_BYTES) + 256 <= 96 * 1024, "smem layout");
+    const size_t smem = 160 * 1024 + TC_MASK_STAGES * TC_M * 32;      // + the sequence masks of 8 tiles
+    static_assert(TC_B_BYTES + TC_STAGES * (TC_A_BYTES + TC_RAW_BYTES) + (21 + TC_MASK_STAGES) * 8 + 16 <= 96 * 1024, "smem layout");
     static_assert(96 * 1024 + 8 * TC_CBUF * 8 <= 160 * 1024, "smem layout");
     static bool configured[RS_MAX_DEVICES] = {};          // the attribute is per device
     const int dev = rs_current_device();
@@ -695,7 +804,15 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
         RS_CUDA(cudaFuncSetAttribute(batched_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
+    const bool use_mask = mode == RS_MODE_AND && seq_tables != nullptr && g_tc_seqmask;
+    if (use_mask) {
+        const int64_t threads = (int64_t)65536 * mask_words;
+        seqmask_build_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_seqmask, mask_words, d_ts, d_w, n_motifs,
+                                                                              stride_rows, threshold);
+        RS_CUDA(cudaGetLastError());
+    }
     TcParams tp = {};
+    tp.codes = use_mask ? d_codes : nullptr; tp.seqmask = d_seqmask; tp.mask_words = mask_words;
     tp.profile = (const float *)d_profile; tp.n = n; tp.padded = rs_padded_count(n);
     tp.n_tiles = (n + TC_M - 1) / TC_M;
     tp.cand = cand; tp.cand_count = cand_count; tp.cand_capacity = cand_cap;
@@ -704,6 +821,9 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     for (int g = 0; g < groups; g++) {
         tp.bmat = d_bmat + (size_t)g * TC_WMAX * TC_N * 8;
         tp.motif_base = g * TC_N;
+        memset(tp.wmask, 0, sizeof(tp.wmask));
+        for (int k = 0; k < TC_N && g * TC_N + k < n_motifs; k++)
+            for (int f = widths[g * TC_N + k]; f <= TC_WMAX; f++) tp.wmask[f][k >> 5] |= 1u << (31 - (k & 31));
         rs_prof_start(st);
         batched_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(tp);
         rs_prof_stop(st);

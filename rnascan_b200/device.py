@@ -941,7 +941,9 @@ class HostProfileScanner(object):
                 self.loaded[slot].synchronize()     # the previous copy out of this staging buffer is done
             st = self.stage[slot].numpy()
             part = src[c0:c0 + rows]
-            if part.dtype == np.float64:
+            if hasattr(part, "readinto"):           # a file range (profile pack): page cache -> pinned staging
+                part.readinto(st, 0, rows)
+            elif part.dtype == np.float64:
                 part = np.ascontiguousarray(part)
                 check(lib.rs_host_rows_to_f32(part.ctypes.data, rows * self.cols, st.ctypes.data, HOST_THREADS))
             elif part.flags["C_CONTIGUOUS"] and part.dtype == st.dtype:
@@ -1044,7 +1046,7 @@ class HostProfileScanner(object):
         dtype = _lib.RS_F32 if exact_rows.dtype == np.float32 else _lib.RS_F64
         ftype = torch.float32 if dtype == _lib.RS_F32 else torch.float64
         if codes is None and self.form == "q8":     # the symbols ride in byte 7 of the quantised rows
-            q = filt_src.numpy() if isinstance(filt_src, torch.Tensor) else filt_src
+            q = filt_src.numpy() if isinstance(filt_src, torch.Tensor) else np.asarray(filt_src)
             code_ptr, code_stride = q.ctypes.data + 7, 8
         elif codes is None:
             code_ptr, code_stride = 0, 1

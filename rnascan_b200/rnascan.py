@@ -1083,7 +1083,7 @@ def _load_profile_dir(directory, write_pack=False):
     except IOError:
         if pk is None:
             raise
-        files = [os.path.join(directory, nm) for nm in pk.names]        # a pack standing for the text files
+        files = [directory + os.sep + nm for nm in pk.names]            # a pack standing for the text files
     else:
         if size > 1:
             files = shard.broadcast_object(files)      # one canonical order (os.listdir order is per process)
@@ -1132,7 +1132,8 @@ def _profile_dir_streams(directory, debug, seq_batches, write_pack):
     STATS.add("profile_files", len(files))
     STATS.notes["profile_source"] = "pack" if isinstance(hp.rows, np.memmap) else "text"
     # rnascan.py:299-301: the id is what stands between "structure." and ".txt" (the full path in debug mode)
-    names = list(files) if debug else [os.path.basename(path)[10:-4] for path in files]
+    cut = len(os.path.dirname(files[0])) + 1 + 10 if files else 0     # "<directory>/structure."
+    names = list(files) if debug else [path[cut:-4] for path in files]
     n_prof = len(files)
     offsets = np.zeros(n_prof, np.int64)
     if n_prof > 1:
@@ -1157,7 +1158,7 @@ def _profile_dir_streams(directory, debug, seq_batches, write_pack):
         q8 = np.array(hp.q8)                          # the pack's rows carry no sequence: add the symbols
         q8[:, 7] = codes
         hp.q8 = q8
-    all_names = list(all_files) if debug else [os.path.basename(path)[10:-4] for path in all_files]
+    all_names = list(all_files) if debug else [path[cut:-4] for path in all_files]
     out = (files, all_names, hp, lengths, names, offsets, codes)
     if _PROFILE_DIR_CACHE_ON[0]:
         _PROFILE_DIR_CACHE[key] = out

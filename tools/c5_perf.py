@@ -22,8 +22,11 @@ motif = torch.empty(cap, dtype=torch.int32, device=device)
 c2 = torch.zeros(2 * M, dtype=torch.int64, device=device); bases = torch.zeros(M + 1, dtype=torch.int64, device=device)
 absmax = dev.ProfileStream.from_device(prof, n).absrow_max()
 check(lib.rs_set_batched_path(2))
-for thr in (50.0, 9.0, 7.0, 6.0, 5.0):
-    for rep in range(2):
+import ctypes
+lib.rs_debug_set_tc_seqmask.argtypes = [ctypes.c_int]
+for mask_on, thr in ((0, 6.0), (1, 6.0), (1, 4.0), (1, 2.0), (1, 50.0)):
+    lib.rs_debug_set_tc_seqmask(mask_on)
+    for rep in range(3):
         check(lib.rs_prof_begin(4))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -34,5 +37,5 @@ for thr in (50.0, 9.0, 7.0, 6.0, 5.0):
         kms = np.zeros(4, np.float32); nrec = np.zeros(1, np.int32)
         check(lib.rs_prof_end(kms.ctypes.data, 4, nrec.ctypes.data))
     resc = int(c2[1::2].sum().item()); hits = int(bases[-1].item())
-    print("thr %5.1f  total %.2f ms  tc kernel %.2f ms  (%.1f Gpos/s kernel)  candidates %d  hits %d" %
-          (thr, e0.elapsed_time(e1), kms[0], n / kms[0] / 1e6, resc, hits), flush=True)
+    print("mask %d  thr %5.1f  total %.2f ms  tc kernel %.2f ms  (%.1f Gpos/s kernel)  candidates %d  hits %d" %
+          (mask_on, thr, e0.elapsed_time(e1), kms[0], n / kms[0] / 1e6, resc, hits), flush=True)
