@@ -318,7 +318,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     if args.n_per_gpu:
         n_main, scaling = args.n_per_gpu, "weak"
     elif args.workload in ("c4", "c5"):
@@ -508,7 +509,11 @@ def measure(args, wl, steps, ctx, full, n_target):
     # ---- sustained: keep stepping for a couple of seconds (power / clock regime of a long job)
     sustained = None
     if full and not flush_l2 and args.sustain_seconds > 0:
-        k_s = max(steps, int(math.ceil(args.sustain_seconds * 1e3 / max(ms_total / steps, 1e-3))))
+        # every rank must run the SAME number of steps (each step holds one all-reduce): agree on the slowest rank's time
+        agreed = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(agreed, op=dist.ReduceOp.MAX)
+        k_s = max(steps, int(math.ceil(args.sustain_seconds * 1e3 / max(float(agreed.item()) / steps, 1e-3))))
         e0.record(stream)
         for _ in range(k_s):
             step()

@@ -1012,9 +1012,7 @@ class HostProfileScanner(object):
                 self.freed[slot].record(comp)
                 if k + 2 < len(self.starts):
                     pending[k + 2] = self._load(k + 2, filt_src)
-            if deferred_seq:
-                if all_reduce is not None:
-                    all_reduce(self.counts)         # the path's only collective
+            if deferred_seq and all_reduce is None:
                 self.counts_host.copy_(self.counts, non_blocking=True)
                 self.d2h_bytes += 64
             self.cand_counters_host.copy_(self.cand_counters, non_blocking=True)
@@ -1027,6 +1025,12 @@ class HostProfileScanner(object):
                 self._alloc_cand()
                 continue
             break
+        if deferred_seq and all_reduce is not None:
+            # the path's only collective -- outside the regrow loop: every rank calls it exactly once per run
+            all_reduce(self.counts)
+            self.counts_host.copy_(self.counts, non_blocking=True)
+            comp.synchronize()
+            self.d2h_bytes += 64
         self.n_filter_pass = int(cc[:, 1].sum()) if len(self.starts) else 0
         parts = [self.cand[k, :int(f)].cpu().numpy() for k, f in enumerate(found.tolist()) if f]
         cand = np.concatenate(parts) if parts else np.zeros(0, np.int64)

@@ -10,6 +10,10 @@ rank, size = shard.init()
 cases = json.load(open("tests/golden/cli/cases.json"))
 names = ["rna_mixed_all", "rna_mixed_pc", "rna_bgonly", "rna_test_default", "ss_mixed_all", "ss_mixed_thr",
          "ss_bgonly", "rnass_fasta_all", "rnass_fasta_thr", "rna_empty_fasta", "rna_nohits", "rna_example_bg_all"]
+multi = json.load(open("tests/golden/cli/multi_cases.json"))
+cases.update(multi)
+names += sorted(multi) + ["rnass_avg_example_misaligned+compat"]
+cases["rnass_avg_example_misaligned+compat"] = {"argv": cases["rnass_avg_example_misaligned"]["argv"] + ["--reference-compat"]}
 bad = []
 for name in names:
     ms._BATCH_CACHE.clear()
@@ -21,7 +25,8 @@ for name in names:
         except SystemExit:
             pass
     if rank == 0:
-        want = open("tests/golden/cli/%s.stdout" % name).read()
+        want = open("tests/golden/cli/%s.stdout" % name.split("+")[0]).read()
+        ms.REFERENCE_COMPAT = False
         if out.getvalue() != want:
             bad.append(name)
 import torch.distributed as dist
