@@ -958,7 +958,9 @@ def run_reference(args):
               "%s; Pool(%d); %d hits" % (len(codes), len(lengths), positions, ref_driver.describe(wl), cores, nh))
     out = {"impl": "reference", "metric": "scored positions/sec", "value": value, "unit": "Gpos/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "higher_is_better": True,
+           "scaling": "strong" if (not args.n_per_gpu and wl in ("c4", "c5")) else "weak",     # as the b200 arm reports it
+           "vs_baseline": None,
            "dtype": "f64 accumulate -> f32 (sequence), f64 (structure)", "data": "synthetic (bounded sample)",
            "config": {"workload": {"c4": "C4 seq PSSM + averaged 7-channel structure profile",
                                    "c2": "C2 sequence-only scan", "c3": "C3 one-hot structure scan",
