@@ -340,13 +340,10 @@ int rs_resolve_candidates(const int64_t *d_cand_pos, int64_t n_cand,
  *                         not be used);
  * rs_host_gather_windows  rows [pos[k], pos[k] + W) and their symbols (codes[(pos + j) * code_stride], so
  *                         byte 7 of quantised rows serves with stride 8; NULL = none) for every candidate;
- * rs_host_copy            memcpy on several threads (page-cache / pageable rows -> pinned staging);
- * rs_host_pread           file bytes [offset, offset + n_bytes) of descriptor `fd` -> dst on several threads
- *                         (profile packs: the quantised rows go from the page cache to pinned staging).      */
+ * rs_host_copy            memcpy on several threads (memory-mapped pack / pageable rows -> pinned staging).  */
 int rs_host_rows_stats(const void *rows, int rows_dtype, int64_t n_rows, int threads, double *out4);
 int rs_host_rows_to_f32(const double *rows, int64_t n_values, float *out, int threads);
 int rs_host_copy(void *dst, const void *src, int64_t n_bytes, int threads);
-int rs_host_pread(int fd, void *dst, int64_t n_bytes, int64_t offset, int threads);
 int rs_host_quantize_q8(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes, double scale,
                         uint8_t *out_rows8, int threads, int64_t *n_out_of_range);
 int rs_host_gather_windows(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes,

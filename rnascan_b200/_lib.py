@@ -85,7 +85,6 @@ _SIGS = {
     "rs_host_rows_stats": ([_vp, _int, _i64, _int, _vp], _int),
     "rs_host_rows_to_f32": ([_vp, _i64, _vp, _int], _int),
     "rs_host_copy": ([_vp, _vp, _i64, _int], _int),
-    "rs_host_pread": ([_int, _vp, _i64, _i64, _int], _int),
     "rs_host_quantize_q8": ([_vp, _int, _i64, _vp, _dbl, _vp, _int, _vp], _int),
     "rs_host_gather_windows": ([_vp, _int, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp, _int], _int),
     "rs_scan_batched_workspace_bytes": ([_i64, _int, _int, _i64], _i64),

@@ -5,8 +5,6 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
-#include <errno.h>
-#include <unistd.h>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -141,25 +139,6 @@ extern "C" int rs_host_copy(void *dst, const void *src, int64_t n_bytes, int thr
     parallel_blocks(n_bytes, threads, (int64_t)1 << 22, [&](int64_t lo, int64_t hi) {
         memcpy((char *)dst + lo, (const char *)src + lo, (size_t)(hi - lo));
     });
-    return RS_OK;
-}
-
-// File bytes [offset, offset + n_bytes) -> dst on several threads (pread: straight out of the page cache, without
-// the page faults a memory map of the same bytes costs on first touch).
-extern "C" int rs_host_pread(int fd, void *dst, int64_t n_bytes, int64_t offset, int threads)
-{
-    if (fd < 0 || (!dst && n_bytes > 0) || n_bytes < 0 || offset < 0) { rs_set_error("rs_host_pread: bad argument"); return RS_ERR_INVALID; }
-    std::atomic<int> failed(0);
-    parallel_blocks(n_bytes, threads, (int64_t)1 << 23, [&](int64_t lo, int64_t hi) {
-        int64_t done = lo;
-        while (done < hi) {
-            const ssize_t got = pread(fd, (char *)dst + done, (size_t)(hi - done), (off_t)(offset + done));
-            if (got < 0 && errno == EINTR) continue;
-            if (got <= 0) { failed.store(1); return; }
-            done += got;
-        }
-    });
-    if (failed.load()) { rs_set_error("rs_host_pread: short read or I/O error"); return RS_ERR_INVALID; }
     return RS_OK;
 }
 

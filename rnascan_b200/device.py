@@ -941,9 +941,7 @@ class HostProfileScanner(object):
                 self.loaded[slot].synchronize()     # the previous copy out of this staging buffer is done
             st = self.stage[slot].numpy()
             part = src[c0:c0 + rows]
-            if hasattr(part, "readinto"):           # a file range (profile pack): page cache -> pinned staging
-                part.readinto(st, 0, rows)
-            elif part.dtype == np.float64:
+            if part.dtype == np.float64:
                 part = np.ascontiguousarray(part)
                 check(lib.rs_host_rows_to_f32(part.ctypes.data, rows * self.cols, st.ctypes.data, HOST_THREADS))
             elif part.flags["C_CONTIGUOUS"] and part.dtype == st.dtype:

@@ -31,50 +31,6 @@ ALIGN = 4096
 VERSION = 1
 
 
-class FileRows(object):
-    """The quantised rows of a pack as a FILE range: chunks are read (pread, several threads) straight into the
-    scanner's pinned staging buffers; indexing gives ordinary arrays for everything else."""
-
-    def __init__(self, path, offset, n_rows, row0=0, fd=None):
-        self.path, self.offset, self.n_rows = path, int(offset), int(n_rows)
-        self.shape, self.dtype = (self.n_rows, 8), np.dtype(np.uint8)
-        self._fd = os.open(path, os.O_RDONLY) if fd is None else fd
-        self._owner = fd is None
-        self.row0 = int(row0)
-
-    def __len__(self):
-        return self.n_rows
-
-    def readinto(self, dst, r0, r1):
-        """Rows [r0, r1) -> dst (a C-contiguous uint8 array with room for them)."""
-        from . import _lib
-        from .device import HOST_THREADS
-        _lib.check(_lib.lib.rs_host_pread(self._fd, dst.ctypes.data, (int(r1) - int(r0)) * 8,
-                                          self.offset + (self.row0 + int(r0)) * 8, HOST_THREADS))
-
-    def __getitem__(self, key):
-        if isinstance(key, slice):
-            r0, r1, step = key.indices(self.n_rows)
-            if step == 1:
-                sub = FileRows(self.path, self.offset, max(r1 - r0, 0), self.row0 + r0, fd=self._fd)
-                sub._parent = self                    # keeps the descriptor open
-                return sub
-        return np.asarray(self)[key]
-
-    def __array__(self, dtype=None, copy=None):
-        out = np.empty((self.n_rows, 8), np.uint8)
-        if self.n_rows:
-            self.readinto(out, 0, self.n_rows)
-        return out if dtype is None else out.astype(dtype)
-
-    def __del__(self):
-        if getattr(self, "_owner", False):
-            try:
-                os.close(self._fd)
-            except OSError:
-                pass
-
-
 class ProfilePack(object):
     def __init__(self, path, header, q8, rows):
         self.path, self.header = path, header
@@ -167,7 +123,7 @@ def read(directory):
             if n_rows else np.zeros((0, 7), np.float64)
         q8 = None
         if header.get("q8_scale") is not None and n_rows:
-            q8 = FileRows(path, header["off_q8"], n_rows)
+            q8 = np.memmap(path, dtype=np.uint8, mode="r", offset=header["off_q8"], shape=(n_rows, 8))
         return ProfilePack(path, header, q8, rows)
     except (OSError, ValueError, KeyError, struct.error):
         return None

@@ -9,6 +9,9 @@ implementations of the same quantity or two decompositions of the same input.
   (the multi-GPU decomposition, shard.plan_shards);
 * background counts: sum over shards == whole, and == a torch.bincount of the same bytes;
 * the tensor-core batched path == the per-motif CUDA-core loop;
+* host-resident rows: the quantised and the float32 filter + gather + resolve pipelines == the device-resident
+  fused scan (three forms of the same input, different kernels, different precision of the filter);
+* every-position structure scores: int32 thousandths == Python round() of the float64 kernel's output on a sample;
 * idempotence: a second run returns bit-identical arrays;
 * a bounded random sample of positions is re-scored by the CPU oracle (bit-exact).
 """
@@ -143,6 +146,70 @@ def test_sampled_positions_against_the_cpu_oracle(env, oracle):
         nan = np.isnan(want)
         assert np.array_equal(nan, np.isnan(got))
         assert np.array_equal(want[~nan].view(np.uint32), got[~nan].view(np.uint32))
+
+
+@pytest.mark.parametrize("thr", [6.0, 2.5])
+def test_host_resident_pipelines_equal_the_device_resident_scan_full_size(env, thr):
+    """100 M rows in HOST memory through device.HostProfileScanner -- 8-byte quantised rows (background counted in the
+    filter pass) and float32 rows -- against rs_scan_fused on the resident streams: identical positions and scores,
+    identical counts."""
+    dev, st, pf, tq, bench = env["dev"], env["st"], env["pf"], env["tq"], env["bench"]
+    n = st.n
+    tables = bench.make_tables_fn("c4")
+    want = dev.scan_fused(st, pf, env["ts"], tq, thr)
+    rows = np.empty((n, 7), np.float32)
+    bounce = torch.empty((1 << 23, 7), dtype=torch.float32).pin_memory()
+    for a in range(0, n, 1 << 23):
+        b = min(n, a + (1 << 23))
+        bounce[:b - a].copy_(pf.rows[a:b])
+        rows[a:b] = bounce[:b - a].numpy()
+    codes = st.codes[:n].cpu().numpy()
+    hp = dev.HostProfile(rows)
+    assert hp.make_q8(codes)
+    seen = []
+
+    def seq_fn(counts8):
+        seen.append(np.array(counts8, np.int64))
+        return tables(counts8)[0]
+
+    for form, src, cd in (("q8", hp.q8, None), ("f32", rows, codes)):
+        sc = dev.HostProfileScanner(n, tq.shape[0], form)
+        got = sc.run(cd, src, rows, tq, seq_fn, thr, hp.absrow_max(), q8_scale=hp.q8_scale if form == "q8" else 1.0)
+        assert np.array_equal(seen[-1], env["counts"]), form
+        assert np.array_equal(got[0], want[0]), form
+        assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), form
+        assert np.array_equal(got[2].view(np.uint64), want[2].view(np.uint64)), form
+        assert sc.n_candidates >= len(want[0])
+        assert np.all(np.diff(got[0]) > 0)
+    assert len(want[0]) > 0
+
+
+def test_thousandths_equal_python_round_of_the_float64_kernel_full_size(env):
+    """C3 shape: 100 M one-hot structure windows; int32 thousandths vs the float64 kernel + CPython round() on a
+    random sample of 200 k positions, sentinels where the float64 score is NaN."""
+    import math
+    from rnascan_b200 import _lib
+    dev, bench = env["dev"], env["bench"]
+    shard = bench.make_device_shard(N_FULL, 777, "c3", torch.device("cuda", 0))
+
+    class Stream(object):
+        pass
+    st = Stream()
+    st.codes, st.n, st.kind = shard["codes"], shard["n"], "struct"
+    counts = dev.histogram(st).cpu().numpy()
+    tq = bench.make_tables_fn("c3")(counts)[1]
+    milli = dev.dense_struct_milli(st, tq)
+    dense = dev.dense_struct(st, tq)
+    idx = torch.randint(0, milli.numel(), (200_000,), device=milli.device)
+    m, d = milli[idx].cpu().numpy(), dense[idx].cpu().numpy()
+    for k, x in zip(m.tolist(), d.tolist()):
+        if x != x:
+            assert k == _lib.RS_MILLI_NAN
+        else:
+            r = round(x, 3)
+            assert k == (_lib.RS_MILLI_NEG0 if (r == 0 and math.copysign(1.0, r) < 0) else int(round(r * 1000)))
+    # and the NaN pattern agrees everywhere
+    assert torch.equal(milli == _lib.RS_MILLI_NAN, dense != dense)
 
 
 def test_batched_paths_agree_full_size(env):

@@ -4,6 +4,8 @@ assembly, messages and TSV text are compared with the reference's golden outputs
 cases run through the real kernels in tests/test_cli_gpu.py (-m gpu)."""
 import warnings
 
+import numpy as np
+
 import pytest
 
 import test_cli_gpu as gpu_cases
@@ -63,8 +65,11 @@ class Patch(object):
 oracle_backend.install(Patch())
 rank, size = shard.init("gloo")
 cases = json.load(open("tests/golden/cli/cases.json"))
+extra = %(extra)r                     # name -> {"argv": [...], "want_file": path}: stdout only
+for name, case in extra.items():
+    cases[name] = {"argv": case["argv"], "stderr_lines": None, "want_file": case["want_file"]}
 bad = []
-for name in %(names)r:
+for name in list(%(names)r) + sorted(extra):
     ms._BATCH_CACHE.clear()
     out, err = io.StringIO(), io.StringIO()
     with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), warnings.catch_warnings():
@@ -73,10 +78,11 @@ for name in %(names)r:
             ms.main(list(cases[name]["argv"]))
         except SystemExit:
             pass
+    ms.REFERENCE_COMPAT = False
     if rank == 0:
-        want = open("tests/golden/cli/%%s.stdout" %% name).read()
+        want = open(cases[name].get("want_file") or "tests/golden/cli/%%s.stdout" %% name).read()
         lines = [l for l in err.getvalue().splitlines() if "seconds" not in l and "minutes" not in l]
-        if out.getvalue() != want or lines != cases[name]["stderr_lines"]:
+        if out.getvalue() != want or (cases[name]["stderr_lines"] is not None and lines != cases[name]["stderr_lines"]):
             bad.append(name)
     elif out.getvalue() or err.getvalue():
         bad.append(name + ":rank%%d-wrote-output" %% rank)
@@ -101,8 +107,33 @@ def test_cli_sharded_over_ranks_matches_golden(tmp_path, nproc):
     names = ["rna_mixed_all", "rna_mixed_pc", "rna_bgonly", "rna_test_default", "ss_mixed_all", "ss_mixed_thr",
              "ss_bgonly", "rnass_fasta_all", "rnass_fasta_thr", "rna_empty_fasta", "rna_nohits",
              "rna_example_bg_all"]
+    # profile directories (files split over ranks), motif collections, the reference's column pairing, and a
+    # directory that holds a pack (every rank maps only its rows)
+    import shutil
+    golden = os.path.join(repo, "tests", "golden")
+    extra = {}
+    with open(os.path.join(golden, "cli", "multi_cases.json")) as fh:
+        for name, case in json.load(fh).items():
+            extra[name] = {"argv": case["argv"], "want_file": os.path.join(golden, "cli", name + ".stdout")}
+    with open(os.path.join(golden, "cli", "cases.json")) as fh:
+        mis = json.load(fh)["rnass_avg_example_misaligned"]
+    extra["avg_compat"] = {"argv": mis["argv"] + ["--reference-compat"],
+                           "want_file": os.path.join(golden, "cli", "rnass_avg_example_misaligned.stdout")}
+    packed = tmp_path / "packed"
+    shutil.copytree(os.path.join(golden, "inputs", "profiles_mixed"), packed)
+    argv = list(extra["multi_ss_avg"]["argv"])
+    argv[argv.index(os.path.join("tests", "golden", "inputs", "profiles_mixed"))] = str(packed)
+    from rnascan_b200 import device, pack, rnascan as ms
+    files = ms._profile_files(str(packed))
+    rows, lengths = ms._read_profiles_packed(files)
+    hp = device.HostProfile(rows)
+    sep = np.zeros(rows.shape[0], np.uint8)
+    sep[np.cumsum(lengths + 1) - 1] = 0xFF
+    assert hp.make_q8(sep)
+    pack.write(str(packed), files, rows, lengths, hp.stats(), hp.q8, hp.q8_scale)
+    extra["multi_ss_avg_from_pack"] = {"argv": argv, "want_file": extra["multi_ss_avg"]["want_file"]}
     script = tmp_path / "rank_worker.py"
-    script.write_text(_RANK_WORKER % {"repo": repo, "names": names})
+    script.write_text(_RANK_WORKER % {"repo": repo, "names": names, "extra": extra})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1", "--master-port",
