@@ -1646,16 +1646,67 @@ def scan_many(struct_dir, struct_pssms, minscore, seq_file=None, seq_pssms=None,
     return frames
 
 
+class _CleanStdout(object):
+    """Under torchrun native libraries write to file descriptor 1 (NCCL prints its version banner there), which
+    would end up in hits.tab: for the duration of a multi-rank run fd 1 is pointed at stderr and sys.stdout at
+    a private duplicate of the real stdout, so that only what this module prints reaches it."""
+
+    def __enter__(self):
+        # (a caller that has replaced sys.stdout -- a test harness capturing it -- keeps its object)
+        self.active = int(os.environ.get("WORLD_SIZE", "1")) > 1 and sys.stdout is sys.__stdout__
+        if not self.active:
+            return self
+        try:
+            sys.stdout.flush()
+            self.saved_fd = os.dup(1)
+            os.dup2(2, 1)
+            self.saved_stdout = sys.stdout
+            sys.stdout = os.fdopen(os.dup(self.saved_fd), "w")
+        except (OSError, ValueError, AttributeError):      # stdout is not a real file (captured by a test harness)
+            self.active = False
+        return self
+
+    def __exit__(self, *exc):
+        if not self.active:
+            return False
+        try:
+            sys.stdout.flush()
+            sys.stdout.close()
+        finally:
+            sys.stdout = self.saved_stdout
+            os.dup2(self.saved_fd, 1)
+            os.close(self.saved_fd)
+        return False
+
+
 def main(argv=None):
+    from . import shard
+    brought_its_own_group = shard.initialized()          # a caller's process group is left alone
+    with _CleanStdout():
+        try:
+            return _main(argv)
+        finally:
+            if not brought_its_own_group:
+                shard.finalize()
+
+
+def _main(argv=None):
     tic = time.time()
     from . import shard
     rank, _ = shard.init()                # joins the torchrun rendezvous if there is one
+    t_init = time.time() - tic            # importing torch + the rendezvous: reported by --stats
     args = getoptions(argv)
     global REFERENCE_COMPAT
     REFERENCE_COMPAT = bool(args.reference_compat)
     STATS.reset(args.stats)
     if STATS.on:
         from . import _lib
+        STATS.phases["import_and_rendezvous_s"] = t_init
+        with STATS.phase("cuda_context_s"):
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.init()
+                torch.zeros(1, device="cuda")
         _lib.lib.rs_prof_begin(4096)
     seq_type = _guess_seq_type(args)
     pairs = _multi_pfm_pairs(args)

@@ -40,7 +40,35 @@ def init(backend=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         dist.init_process_group(backend)
+    global _JOINED_HERE
+    _JOINED_HERE = True
     return world()
+
+
+_JOINED_HERE = False
+
+
+def initialized():
+    try:
+        import torch.distributed as dist
+        return bool(dist.is_available() and dist.is_initialized())
+    except ImportError:
+        return False
+
+
+def finalize():
+    """Leave the process group that init() created."""
+    global _JOINED_HERE
+    if not _JOINED_HERE:
+        return
+    _JOINED_HERE = False
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def allreduce_counts(counts):

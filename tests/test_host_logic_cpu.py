@@ -141,3 +141,55 @@ def test_cli_sharded_over_ranks_matches_golden(tmp_path, nproc):
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res == {"bad": [], "size": nproc}
+
+
+_NOISY_WORKER = r"""
+import json, os, sys, warnings
+sys.path.insert(0, %(repo)r)
+sys.path.insert(0, os.path.join(%(repo)r, "tests"))
+os.chdir(%(repo)r)
+import oracle_backend
+from rnascan_b200 import rnascan as ms, shard
+
+
+class Patch(object):
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+oracle_backend.install(Patch())
+real_init = shard.init
+
+
+def noisy_init(*a, **k):
+    os.write(1, b"NCCL version 0.0.0 (a native library writing to file descriptor 1)\n")
+    return real_init("gloo")
+
+
+shard.init = noisy_init
+warnings.simplefilter("ignore")
+ms.main(%(argv)r)
+"""
+
+
+def test_native_library_output_stays_out_of_hits_tab_under_torchrun(tmp_path):
+    """NCCL prints its version banner on file descriptor 1 while the process group comes up; under torchrun
+    the CLI points fd 1 at stderr for the run and writes hits.tab to a private duplicate of the real stdout
+    (found by timing the sharded CLI on 8 GPUs: the first line of hits.tab was the banner)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(repo, "tests", "golden", "cli", "cases.json")) as fh:
+        case = json.load(fh)["rna_mixed_all"]
+    script = tmp_path / "noisy_worker.py"
+    script.write_text(_NOISY_WORKER % {"repo": repo, "argv": case["argv"]})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29561", str(script)],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    with open(os.path.join(repo, "tests", "golden", "cli", "rna_mixed_all.stdout")) as fh:
+        assert out.stdout == fh.read()
+    assert out.stderr.count("a native library writing to file descriptor 1") == 2
