@@ -26,7 +26,12 @@
 //   warps 4-7, 12-15  epilogue: two warps per TMEM lane quadrant, 128 motif columns each:
 //               tcgen05.ld, sign-bit mask of the 32 accumulators per load (one funnel shift each),
 //               candidates staged per warp in shared memory, flushed with one atomic per ~1000
-//   warps 8-11  converters: fp32 rows -> bf16 x 8 rows (the A operand), fence.proxy.async
+//   warps 8-11  converters: fp32 rows -> bf16 x 8 rows (the A operand), fence.proxy.async; in RS_MODE_AND also
+//               the SEQUENCE MASK of every position of the tile (one thread per position): the 8-mer the window
+//               starts with indexes a 65536 x 256-bit table (seqmask_build_kernel: which motifs' sequence score can
+//               pass), restricted to the motifs no wider than the distance to the first invalid symbol; 32 B per
+//               position into an 8-stage shared-memory ring that the epilogue ANDs into its sign masks, so only
+//               (position, motif) pairs that can be combined hits are ever staged
 #include <cuda_bf16.h>
 #include <string.h>
 #include <vector>

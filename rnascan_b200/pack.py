@@ -15,8 +15,9 @@ and later scans map it instead of parsing:
                                        (q8_scale null) when the rows do not fit the form
     off_rows      float64[n_rows][7]   the exact rows, bit-identical to what pandas parses, B,E,H,L,M,R,T
 
-Both sections start at multiples of 4096 and are read through ``numpy.memmap``: a scan touches all of the
-8-byte rows (they are what travels to the device) and only the candidate windows of the 56-byte ones.
+Both sections start at multiples of 4096 and are read through ``numpy.memmap``: a scan copies all of the
+8-byte rows into pinned staging buffers on host threads (they are what travels to the device) and touches
+only the candidate windows of the 56-byte ones.
 A pack is used only if it lists exactly the directory's current files (same order, size and mtime).
 """
 import json
