@@ -680,7 +680,10 @@ def measure(args, wl, steps, ctx, full, n_target):
                       "ms_per_step": ms_e2e,
                       "link_GBps": (e2e["h2d"] + e2e["d2h"]) / (ms_e2e * 1e-3) / 1e9,
                       "api": e2e["api"]}
-        for key in ("candidates", "filter_pass", "launches", "host_prep_s_untimed", "hits"):
+        for key in ("form", "bytes_per_position", "guard_band_score_units"):
+            if key in e2e:
+                out["e2e"][key] = e2e[key]
+        for key in ("candidates", "structure_candidates", "filter_pass", "launches", "host_prep_s_untimed", "hits"):
             if key in e2e:
                 out["e2e"][key + "_rank0"] = e2e[key]
         out.update(e2e_extra)
@@ -731,13 +734,19 @@ def e2e_c4(args, dev, shard, h_codes, tables, absmax, hits_dev, all_reduce, barr
     codes_np = h_codes.numpy()[:n]
     # ... and their filter form (what `rnascan --pack` leaves on disk), built by the product's host quantiser
     hp = dev.HostProfile(rows_host)
-    q8 = torch.empty((n, 8), dtype=torch.uint8).pin_memory()
-    if not hp.make_q8(codes_np, out=q8.numpy()):
+    tq = tables(np.zeros(8, np.int64))[1]
+    # which quantised form: 4 bytes per position when its guard band (here ~2 score units) leaves the threshold
+    # selective, else 8 bytes (guard ~0.2); `--e2e-form` forces one
+    guard4 = dev.q4_guard(tq, max(hp.stats()[3], 1e-300))
+    form = args.e2e_form if args.e2e_form != "auto" else ("q4" if guard4 <= 0.4 * THRESHOLD else "q8")
+    width = 4 if form == "q4" else 8
+    q8 = torch.empty((n, width), dtype=torch.uint8).pin_memory()
+    ok = hp.make_q4(codes_np, out=q8.numpy()) if form == "q4" else hp.make_q8(codes_np, out=q8.numpy())
+    if not ok:
         raise SystemExit("synthetic rows do not fit the quantised form")
     prep_s = time.perf_counter() - t0
-    tq = tables(np.zeros(8, np.int64))[1]
     seq_fn = lambda c: tables(c)[0]
-    sc = dev.HostProfileScanner(n, W_MOTIF, "q8", device=device)
+    sc = dev.HostProfileScanner(n, W_MOTIF, form, device=device)
     ar = all_reduce if world > 1 else None
 
     def run():
@@ -754,11 +763,13 @@ def e2e_c4(args, dev, shard, h_codes, tables, absmax, hits_dev, all_reduce, barr
     if hits_dev is not None and len(res[0]) != hits_dev:
         raise SystemExit("e2e hit count %d != device-resident hit count %d" % (len(res[0]), hits_dev))
     e2e = {"ms": ms, "h2d": sc.h2d_bytes, "d2h": sc.d2h_bytes, "hits": int(len(res[0])),
-           "api": "rnascan_b200.device.HostProfileScanner.run: pinned 8-byte quantised rows (7 channels + symbol) -> "
-                  "device filter (+ background counts) -> candidate positions -> host gather of the exact rows -> "
-                  "device resolve -> host hit arrays",
-           "candidates": sc.n_candidates, "filter_pass": sc.n_filter_pass, "launches": sc.launches,
-           "host_prep_s_untimed": prep_s}
+           "api": "rnascan_b200.device.HostProfileScanner.run: pinned %d-byte quantised rows (7 channels + symbol) -> "
+                  "device filter (+ background counts)%s -> candidate positions -> host gather of the exact rows -> "
+                  "device resolve -> host hit arrays"
+                  % (width, " -> sequence table applied to the candidates' packed symbols on the device" if form == "q4" else ""),
+           "form": form, "bytes_per_position": width, "guard_band_score_units": guard4 if form == "q4" else None,
+           "candidates": sc.n_candidates, "structure_candidates": sc.n_struct_candidates or sc.n_candidates,
+           "filter_pass": sc.n_filter_pass, "launches": sc.launches, "host_prep_s_untimed": prep_s}
     del sc, q8
     if not full:
         return e2e, extra
@@ -1008,6 +1019,8 @@ def main():
                     help="skip the host-buffer end-to-end leg (e.g. for shards too large to pin on the host)")
     ap.add_argument("--serial-bg", action="store_true", dest="serial_bg",
                     help="c4/c2: histogram -> host tables -> scan, strictly in sequence (no overlap)")
+    ap.add_argument("--e2e-form", default="auto", choices=["auto", "q4", "q8"], dest="e2e_form",
+                    help="quantised row form of the end-to-end leg (auto: 4 bytes when its guard band allows)")
     ap.add_argument("--no-sweep", action="store_true", dest="no_sweep", help="skip the threshold sweep (c4)")
     ap.add_argument("--no-api", action="store_true", dest="no_api", help="skip the scan_main(pack directory) leg")
     ap.add_argument("--no-others", action="store_true", dest="no_others",

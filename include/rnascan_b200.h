@@ -304,10 +304,18 @@ int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_t
  *     RS_ROWS_F32_SHADOW  float32[n][7]  -- round-to-nearest shadow of float64 rows (guard band widened)
  *     RS_ROWS_Q8          uint8[n][8]    -- {q_B..q_T, symbol code}; p ~ q * q8_scale / 255, 0 <= p <= q8_scale
  *                                           (rs_host_quantize_q8); d_codes is ignored (may be NULL)
+ *     RS_ROWS_Q4          uint32[n]      -- nibble c = floor(p_c * 15 / q8_scale) for the seven channels, top nibble
+ *                                           = symbol code & 15 (rs_host_quantize_q4); 4 B per position; the
+ *                                           guard band is wider (q8_scale / 15 * sum of the POSITIVE table
+ *                                           entries), so it suits high thresholds on a slow link; d_codes ignored
  * rs_filter_profile returns, in position order, every window whose exact score COULD exceed the
  * threshold (and, when seq_table is given, whose sequence score does: _pwm.c:34-68 arithmetic) as
  * d_cand_pos[k] = pos_base + window start; d_counters2[0] = candidates found (above cand_capacity the
- * excess is dropped: re-run larger), [1] = windows that passed the fp32 filter.  With RS_ROWS_Q8 and
+ * excess is dropped: re-run larger), [1] = windows that passed the fp32 filter.  d_cand_sym (RS_ROWS_Q4 only, may be
+ * NULL) receives each candidate's W symbols, 2 bits each (symbol j in bits 2j, 2j+1; bit 63: one of them is not
+ * A,C,G,U; W <= 24): rs_refine_candidates_packed then applies a sequence table that only became known later
+ * (computed background) ON THE DEVICE -- survivors in order, d_counters2[0] = their number -- before anything is
+ * gathered.  With RS_ROWS_Q8 / RS_ROWS_Q4 and
  * d_counts8 != NULL the letters A,C,G,U (codes 0..3) of rows [0, count_rows) are ADDED to
  * d_counts8[0..3] in the same pass (the background counts of rnascan.py:450-453; not zeroed here).
  * The host then gathers each candidate's W rows and W symbols (rs_host_gather_windows) and
@@ -318,13 +326,18 @@ int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_t
 #define RS_ROWS_F32        0
 #define RS_ROWS_F32_SHADOW 1
 #define RS_ROWS_Q8         2
+#define RS_ROWS_Q4         3
 int64_t rs_filter_workspace_bytes(int64_t n, int64_t cand_capacity);
 int rs_filter_profile(const uint8_t *d_codes, const void *d_rows, int row_format, double q8_scale, int64_t n,
                       const double *seq_table_Wx4 /* NULL: no sequence check in this pass */,
                       const double *struct_table_Wx7, int W, double threshold, double absrow_max,
                       int64_t pos_base, int64_t count_rows, uint64_t *d_counts8 /* may be NULL */,
-                      int64_t cand_capacity, int64_t *d_cand_pos, uint64_t *d_counters2, void *d_work,
-                      int64_t work_bytes, void *stream);
+                      int64_t cand_capacity, int64_t *d_cand_pos, uint64_t *d_cand_sym /* may be NULL */,
+                      uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
+int64_t rs_refine_packed_workspace_bytes(int64_t n_cand);
+int rs_refine_candidates_packed(const int64_t *d_cand_pos, const uint64_t *d_cand_sym, int64_t n_cand,
+                                const double *seq_table_Wx4, int W, double threshold, int64_t *d_out_pos,
+                                uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream);
 int64_t rs_resolve_workspace_bytes(int64_t n_cand);
 int rs_resolve_candidates(const int64_t *d_cand_pos, int64_t n_cand,
                           const void *d_win_rows /* [n_cand][W][7] */, int rows_dtype /* RS_F32 | RS_F64 */,
@@ -338,14 +351,19 @@ int rs_resolve_candidates(const int64_t *d_cand_pos, int64_t n_cand,
  * rs_host_quantize_q8     the RS_ROWS_Q8 form: q = rint(p * 255 / scale), byte 7 = codes[r] (0 if NULL);
  *                         *n_out_of_range = entries outside [0, scale] or non-finite (then the form must
  *                         not be used);
+ * rs_host_quantize_q4     the RS_ROWS_Q4 form: nibble c = floor(p_c * 15 / scale) (never above p), top nibble =
+ *                         codes[r] & 15; *n_out_of_range as above;
  * rs_host_gather_windows  rows [pos[k], pos[k] + W) and their symbols (codes[(pos + j) * code_stride], so
- *                         byte 7 of quantised rows serves with stride 8; NULL = none) for every candidate;
+ *                         byte 7 of 8-byte quantised rows serves with stride 8; code_stride = -4: `codes` points at
+ *                         4-byte quantised rows, the symbols are their top nibbles; NULL = none) for every candidate;
  * rs_host_copy            memcpy on several threads (memory-mapped pack / pageable rows -> pinned staging).  */
 int rs_host_rows_stats(const void *rows, int rows_dtype, int64_t n_rows, int threads, double *out4);
 int rs_host_rows_to_f32(const double *rows, int64_t n_values, float *out, int threads);
 int rs_host_copy(void *dst, const void *src, int64_t n_bytes, int threads);
 int rs_host_quantize_q8(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes, double scale,
                         uint8_t *out_rows8, int threads, int64_t *n_out_of_range);
+int rs_host_quantize_q4(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes, double scale,
+                        uint32_t *out_rows4, int threads, int64_t *n_out_of_range);
 int rs_host_gather_windows(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes,
                            int64_t code_stride, const int64_t *pos, int64_t n_cand, int W, void *out_rows,
                            uint8_t *out_codes, int threads);

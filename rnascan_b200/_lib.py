@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "librnascan_b200.so")
 RS_OK, RS_ERR_INVALID, RS_ERR_CUDA, RS_ERR_WORKSPACE = 0, 1, 2, 3
 RS_F32, RS_F64 = 0, 1
 RS_MODE_STRUCT, RS_MODE_AND = 0, 1
-RS_ROWS_F32, RS_ROWS_F32_SHADOW, RS_ROWS_Q8 = 0, 1, 2
+RS_ROWS_F32, RS_ROWS_F32_SHADOW, RS_ROWS_Q8, RS_ROWS_Q4 = 0, 1, 2, 3
 RS_SEP, RS_RNA_OTHER, RS_SS_OTHER, RS_MAX_W = 0xFF, 0x0C, 0x0F, 64
 RS_MILLI_NAN, RS_MILLI_NINF, RS_MILLI_NEG0, RS_MILLI_RANGE = -2147483648, -2147483647, -2147483646, -2147483645
 
@@ -77,8 +77,10 @@ _SIGS = {
     "rs_scan_fused_candidates": ([_vp, _vp, _int, _i64, _vp, _int, _dbl, _dbl, _i64, _vp, _vp, _i64, _vp, _vp], _int),
     "rs_scan_fused_resolve": ([_vp, _i64, _vp, _int, _dbl, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_filter_workspace_bytes": ([_i64, _i64], _i64),
-    "rs_filter_profile": ([_vp, _vp, _int, _dbl, _i64, _vp, _vp, _int, _dbl, _dbl, _i64, _i64, _vp, _i64, _vp, _vp,
+    "rs_filter_profile": ([_vp, _vp, _int, _dbl, _i64, _vp, _vp, _int, _dbl, _dbl, _i64, _i64, _vp, _i64, _vp, _vp, _vp,
                            _vp, _i64, _vp], _int),
+    "rs_refine_packed_workspace_bytes": ([_i64], _i64),
+    "rs_refine_candidates_packed": ([_vp, _vp, _i64, _vp, _int, _dbl, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_resolve_workspace_bytes": ([_i64], _i64),
     "rs_resolve_candidates": ([_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _i64,
                                _vp], _int),
@@ -86,6 +88,7 @@ _SIGS = {
     "rs_host_rows_to_f32": ([_vp, _i64, _vp, _int], _int),
     "rs_host_copy": ([_vp, _vp, _i64, _int], _int),
     "rs_host_quantize_q8": ([_vp, _int, _i64, _vp, _dbl, _vp, _int, _vp], _int),
+    "rs_host_quantize_q4": ([_vp, _int, _i64, _vp, _dbl, _vp, _int, _vp], _int),
     "rs_host_gather_windows": ([_vp, _int, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp, _int], _int),
     "rs_scan_batched_workspace_bytes": ([_i64, _int, _int, _i64], _i64),
     "rs_set_batched_path": ([_int], _int),

@@ -124,16 +124,18 @@ __device__ __forceinline__ void resolve_tile_candidates(const HitStage &st, int6
 }
 
 // Workspace of the candidate-only scans (rs_filter_profile): staged positions, per-tile segments, ordering scratch.
-struct FilterWork { int64_t off_pos, off_seg, off_scan, total; };
+struct FilterWork { int64_t off_pos, off_sym, off_seg, off_scan, total; };
 static inline FilterWork rs_filter_layout(int64_t n, int64_t cap)
 {
     FilterWork w;
     const int64_t tiles = (n > 0 ? n : 0) / RS_MIN_TILE + 16;
     int64_t off = 0;
     w.off_pos = off;  off += rs_roundup((cap > 0 ? cap : 0) * 8, 256);
+    w.off_sym = off;  off += rs_roundup((cap > 0 ? cap : 0) * 8, 256);      // candidates' packed symbols (4-bit rows)
     w.off_seg = off;  off += rs_roundup(tiles * 16, 256);
     w.off_scan = off; off += rs_roundup(rs_order_tmp_bytes(tiles), 256);
     w.total = off;
     return w;
 }
 int rs_filter_q8_launch(const ProfileParams &prm, int W, cudaStream_t stream);   // filter_scan.cu
+int rs_filter_q4_launch(const ProfileParams &prm, int W, cudaStream_t stream);   // filter_scan.cu

@@ -321,11 +321,12 @@ __global__ void stats_finish_kernel(double *stats)
 //   quantised rows) -- folded into the table; quant_step: largest |p - stored * value_scale| per entry
 //   (0 for float rows; the float32 shadow of float64 rows is covered by `shadow`).
 static bool build_filter(ProfileParams &prm, const double *struct_table, int W, double threshold,
-                         double profile_absrow_max, double value_scale, double quant_step, bool shadow)
+                         double profile_absrow_max, double value_scale, double quant_step, bool shadow,
+                         bool one_sided = false)
 {
     if (!(isfinite(threshold) && isfinite(profile_absrow_max) && profile_absrow_max >= 0 && profile_absrow_max < 1e30))
         return false;
-    double S = 0.0, Sf = 0.0, A = 0.0;
+    double S = 0.0, Sf = 0.0, A = 0.0, Apos = 0.0;
     for (int j = 0; j < W; j++) {
         bool row_nonfinite = false;
         double rowmax = 0.0, rowmax_f = 0.0;
@@ -343,6 +344,7 @@ static bool build_filter(ProfileParams &prm, const double *struct_table, int W, 
             rowmax = fmax(rowmax, fabs(f));
             rowmax_f = fmax(rowmax_f, fabs((double)sf));
             A += fabs(f);
+            if (f > 0) Apos += f;
         }
         S += rowmax;
         Sf += rowmax_f;
@@ -352,7 +354,10 @@ static bool build_filter(ProfileParams &prm, const double *struct_table, int W, 
     // entry wise for stored values >= 0; negative p are covered by the generous constant.
     const double R = fmax(profile_absrow_max, 1.0);
     double tol = ldexp(1.0, -23) * (double)(RS_CHANNELS * W + 8) * Sf * (R / value_scale + (quant_step > 0 ? 4.0 : 0.0));
-    if (quant_step > 0) tol += quant_step * A * (1.0 + 1e-9);          // |p - p~| <= quant_step per entry
+    if (quant_step > 0 && !one_sided) tol += quant_step * A * (1.0 + 1e-9);      // |p - p~| <= quant_step per entry
+    // floored values: 0 <= p - p~ < quant_step, so only positive table entries can be under-counted (the tiny
+    // two-sided term covers the floating-point evaluation of the floor itself)
+    if (quant_step > 0 && one_sided) tol += quant_step * Apos * (1.0 + 1e-9) + quant_step * A * 1e-9;
     if (shadow) tol += ldexp(1.0, -24) * R * S * 1.001 + ldexp(1.0, -149) * A;   // float32 rounding of float64 rows
     prm.filt_thr = f32_round_down(threshold - tol);
     return isfinite((double)prm.filt_thr);
@@ -589,13 +594,17 @@ extern "C" int rs_filter_profile(const uint8_t *d_codes, const void *d_rows, int
                                  int64_t n, const double *seq_table, const double *struct_table, int W,
                                  double threshold, double absrow_max, int64_t pos_base, int64_t count_rows,
                                  uint64_t *d_counts8, int64_t cand_capacity, int64_t *d_cand_pos,
-                                 uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+                                 uint64_t *d_cand_sym, uint64_t *d_counters2, void *d_work, int64_t work_bytes,
+                                 void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (row_format != RS_ROWS_F32 && row_format != RS_ROWS_F32_SHADOW && row_format != RS_ROWS_Q8) {
-        rs_set_error("row_format must be RS_ROWS_F32, RS_ROWS_F32_SHADOW or RS_ROWS_Q8"); return RS_ERR_INVALID;
+    if (row_format != RS_ROWS_F32 && row_format != RS_ROWS_F32_SHADOW && row_format != RS_ROWS_Q8 &&
+        row_format != RS_ROWS_Q4) {
+        rs_set_error("row_format must be RS_ROWS_F32, RS_ROWS_F32_SHADOW, RS_ROWS_Q8 or RS_ROWS_Q4"); return RS_ERR_INVALID;
     }
-    const bool q8 = row_format == RS_ROWS_Q8;
+    const bool q4 = row_format == RS_ROWS_Q4;
+    const bool q8 = row_format == RS_ROWS_Q8 || q4;          // "quantised": the rows carry the symbols
+    if (d_cand_sym && !q4) { rs_set_error("candidate symbols come with RS_ROWS_Q4 only"); return RS_ERR_INVALID; }
     if (!d_rows || ((uintptr_t)d_rows & 15) || !struct_table) { rs_set_error("rows pointer null or not 16-byte aligned, or null table"); return RS_ERR_INVALID; }
     if (!q8 && (!d_codes || ((uintptr_t)d_codes & 15))) { rs_set_error("codes pointer null or not 16-byte aligned"); return RS_ERR_INVALID; }
     if (W < 1 || W > RS_FAST_W) { rs_set_error("filter scans need 1 <= W <= %d", RS_FAST_W); return RS_ERR_INVALID; }
@@ -616,20 +625,22 @@ extern "C" int rs_filter_profile(const uint8_t *d_codes, const void *d_rows, int
     prm.count_rows = d_counts8 ? (count_rows < n ? count_rows : n) : 0;
     uint8_t *wk = (uint8_t *)d_work;
     prm.st.pos = (int64_t *)(wk + wl.off_pos);
+    prm.st.str = d_cand_sym ? (double *)(wk + wl.off_sym) : nullptr;
     prm.st.tile_seg = (ulonglong2 *)(wk + wl.off_seg);
     prm.st.counters = (unsigned long long *)d_counters2;
     prm.st.capacity = cand_capacity;
-    const double vs = q8 ? q8_scale / 255.0 : 1.0;
-    if (!build_filter(prm, struct_table, W, threshold, absrow_max, vs, q8 ? 0.5 * vs : 0.0,
-                      row_format == RS_ROWS_F32_SHADOW)) {
+    const double vs = q4 ? q8_scale / 15.0 : (q8 ? q8_scale / 255.0 : 1.0);
+    if (!build_filter(prm, struct_table, W, threshold, absrow_max, vs, q4 ? vs : (q8 ? 0.5 * vs : 0.0),
+                      row_format == RS_ROWS_F32_SHADOW, q4)) {
         rs_set_error("the fp32 filter does not apply (non-finite threshold, table or row bound): use the exact scan");
         return RS_ERR_INVALID;
     }
     if (seq_table) for (int k = 0; k < W * 4; k++) prm.qd[k] = seq_table[k];
     prm.n_tiles = (n + FT_TILE - 1) / FT_TILE;
-    int rc = q8 ? rs_filter_q8_launch(prm, W, st) : FilterDispatch<RS_FAST_W>::run(W, prm, st);
+    int rc = q4 ? rs_filter_q4_launch(prm, W, st)
+                : (q8 ? rs_filter_q8_launch(prm, W, st) : FilterDispatch<RS_FAST_W>::run(W, prm, st));
     if (rc) return rc;
-    OrderDest od = {d_cand_pos, nullptr, nullptr, nullptr, nullptr, 0};
+    OrderDest od = {d_cand_pos, nullptr, (double *)d_cand_sym, nullptr, nullptr, 0};
     return rs_order_hits(prm.st, prm.n_tiles, od, wk + wl.off_scan, st);
 }
 

@@ -104,3 +104,79 @@ extern "C" int rs_refine_hits_seq(const uint8_t *d_codes, int64_t n, const doubl
     OrderDest od = {d_hit_pos, d_hit_seq, d_hit_struct, nullptr, nullptr, 0};
     return rs_order_hits(prm.st, n_tiles, od, wk + wl.off_scan, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// The same decision for candidates that carry their window's symbols with them (rs_filter_profile on 4-bit rows:
+// symbol j in bits 2j, 2j+1 of the 64-bit payload, bit 63 = a symbol that is not A,C,G,U): the symbol stream is
+// not on the device at all in that pipeline.  Survivors stay in order; their positions come back.
+struct RefinePackedParams {
+    const int64_t *in_pos;
+    const unsigned long long *in_sym;
+    int64_t        n_cand;
+    double         threshold;
+    int            W;
+    HitStage       st;
+    double         qd[RS_MAX_W * 4];
+};
+
+__global__ void __launch_bounds__(RF_THREADS) refine_packed_kernel(const __grid_constant__ RefinePackedParams prm)
+{
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t k0 = tile * RF_TILE + (int64_t)tid * RF_PER;
+    unsigned mask = 0;
+#pragma unroll
+    for (int i = 0; i < RF_PER; i++) {
+        if (k0 + i < prm.n_cand) {
+            const unsigned long long sym = prm.in_sym[k0 + i];
+            if (!(sym >> 63)) {
+                double q = 0.0;
+                for (int j = 0; j < prm.W; j++) q = __dadd_rn(q, prm.qd[j * 4 + (int)((sym >> (2 * j)) & 3ull)]);
+                if ((double)(float)q > prm.threshold) mask |= 1u << i;      // _pwm.c:65 + SURVEY.md note N1
+            }
+        }
+    }
+    const int any = __syncthreads_or(mask != 0);
+    if (any) {
+        emit_tile_hits<RF_THREADS>(prm.st, tile, mask, RF_PER, [&](int i, int64_t k) { prm.st.pos[k] = prm.in_pos[k0 + i]; });
+    } else if (tid == 0) {
+        prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
+    }
+}
+
+extern "C" int64_t rs_refine_packed_workspace_bytes(int64_t n_cand)
+{
+    const int64_t cap = n_cand > 0 ? n_cand : 0, tiles = cap / RF_TILE + 2;
+    return rs_roundup(cap * 8, 256) + rs_roundup(tiles * 16, 256) + rs_roundup(rs_order_tmp_bytes(tiles), 256);
+}
+
+extern "C" int rs_refine_candidates_packed(const int64_t *d_cand_pos, const uint64_t *d_cand_sym, int64_t n_cand,
+                                           const double *seq_table, int W, double threshold, int64_t *d_out_pos,
+                                           uint64_t *d_counters2, void *d_work, int64_t work_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_cand < 0 || !seq_table || !d_counters2) { rs_set_error("rs_refine_candidates_packed: bad argument"); return RS_ERR_INVALID; }
+    if (W < 1 || W > 31) { rs_set_error("packed symbols hold motif widths 1..31"); return RS_ERR_INVALID; }
+    if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
+    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    if (n_cand == 0) return RS_OK;
+    if (!d_cand_pos || !d_cand_sym || !d_out_pos) { rs_set_error("rs_refine_candidates_packed: null buffer"); return RS_ERR_INVALID; }
+    if (!d_work || work_bytes < rs_refine_packed_workspace_bytes(n_cand)) {
+        rs_set_error("workspace too small: need %lld bytes", (long long)rs_refine_packed_workspace_bytes(n_cand));
+        return RS_ERR_WORKSPACE;
+    }
+    const int64_t n_tiles = (n_cand + RF_TILE - 1) / RF_TILE, tiles = n_cand / RF_TILE + 2;
+    RefinePackedParams prm = {};
+    prm.in_pos = d_cand_pos; prm.in_sym = (const unsigned long long *)d_cand_sym; prm.n_cand = n_cand;
+    prm.threshold = threshold; prm.W = W;
+    uint8_t *wk = (uint8_t *)d_work;
+    prm.st.pos = (int64_t *)wk;
+    prm.st.tile_seg = (ulonglong2 *)(wk + rs_roundup(n_cand * 8, 256));
+    prm.st.counters = (unsigned long long *)d_counters2;
+    prm.st.capacity = n_cand;
+    for (int k = 0; k < W * 4; k++) prm.qd[k] = seq_table[k];
+    refine_packed_kernel<<<(unsigned)n_tiles, RF_THREADS, 0, st>>>(prm);
+    RS_CUDA(cudaGetLastError());
+    OrderDest od = {d_out_pos, nullptr, nullptr, nullptr, nullptr, 0};
+    return rs_order_hits(prm.st, n_tiles, od, wk + rs_roundup(n_cand * 8, 256) + rs_roundup(tiles * 16, 256), st);
+}

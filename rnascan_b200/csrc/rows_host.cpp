@@ -93,6 +93,31 @@ int64_t quantize_impl(const T *rows, int64_t n, const uint8_t *codes, double sca
 }
 
 template <typename T>
+int64_t quantize4_impl(const T *rows, int64_t n, const uint8_t *codes, double scale, uint32_t *out, int threads)
+{
+    const double k = 15.0 / scale;
+    std::atomic<int64_t> bad(0);
+    parallel_blocks(n, threads, 1 << 16, [&](int64_t lo, int64_t hi) {
+        int64_t b = 0;
+        for (int64_t r = lo; r < hi; r++) {
+            uint32_t w = 0;
+            for (int c = 0; c < 7; c++) {
+                const double v = (double)rows[r * 7 + c];
+                if (!(v >= 0.0 && v <= scale)) { b++; continue; }                  // NaN lands here too
+                double q = floor(v * k);
+                if (q > 15.0) q = 15.0;
+                while (q > 0.0 && q * (scale / 15.0) > v) q -= 1.0;             // the floor must never overshoot p
+                w |= (uint32_t)q << (4 * c);
+            }
+            w |= (uint32_t)((codes ? codes[r] : 0) & 0xF) << 28;
+            out[r] = w;
+        }
+        if (b) bad.fetch_add(b);
+    });
+    return bad.load();
+}
+
+template <typename T>
 void gather_impl(const T *rows, int64_t n_rows, const uint8_t *codes, int64_t code_stride, const int64_t *pos,
                  int64_t n_cand, int W, T *out_rows, uint8_t *out_codes, int threads)
 {
@@ -107,8 +132,17 @@ void gather_impl(const T *rows, int64_t n_rows, const uint8_t *codes, int64_t co
                 continue;
             }
             memcpy(o, rows + (size_t)p * 7, sizeof(T) * (size_t)W * 7);
-            if (codes) for (int j = 0; j < W; j++) oc[j] = codes[(size_t)(p + j) * code_stride];
-            else memset(oc, 0, (size_t)W);
+            if (codes && code_stride == -4) {                 // top nibble of 4-byte quantised rows
+                const uint32_t *q4 = reinterpret_cast<const uint32_t *>(codes);
+                for (int j = 0; j < W; j++) {
+                    const uint32_t c = q4[p + j] >> 28;
+                    oc[j] = c < 4u ? (uint8_t)c : (c == 0xFu ? (uint8_t)RS_SEP : (uint8_t)RS_RNA_OTHER);
+                }
+            } else if (codes) {
+                for (int j = 0; j < W; j++) oc[j] = codes[(size_t)(p + j) * code_stride];
+            } else {
+                memset(oc, 0, (size_t)W);
+            }
         }
     });
 }
@@ -155,6 +189,19 @@ extern "C" int rs_host_quantize_q8(const void *rows, int rows_dtype, int64_t n_r
     return RS_OK;
 }
 
+extern "C" int rs_host_quantize_q4(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes, double scale,
+                                   uint32_t *out_rows4, int threads, int64_t *n_out_of_range)
+{
+    if ((!rows || !out_rows4) && n_rows > 0) { rs_set_error("rs_host_quantize_q4: null buffer"); return RS_ERR_INVALID; }
+    if (!(scale > 0.0) || !std::isfinite(scale)) { rs_set_error("rs_host_quantize_q4: scale must be positive and finite"); return RS_ERR_INVALID; }
+    int64_t bad;
+    if (rows_dtype == RS_F32) bad = quantize4_impl((const float *)rows, n_rows, codes, scale, out_rows4, threads);
+    else if (rows_dtype == RS_F64) bad = quantize4_impl((const double *)rows, n_rows, codes, scale, out_rows4, threads);
+    else { rs_set_error("rows_dtype must be RS_F32 or RS_F64"); return RS_ERR_INVALID; }
+    if (n_out_of_range) *n_out_of_range = bad;
+    return RS_OK;
+}
+
 extern "C" int rs_host_gather_windows(const void *rows, int rows_dtype, int64_t n_rows, const uint8_t *codes,
                                       int64_t code_stride, const int64_t *pos, int64_t n_cand, int W,
                                       void *out_rows, uint8_t *out_codes, int threads)
@@ -162,7 +209,7 @@ extern "C" int rs_host_gather_windows(const void *rows, int rows_dtype, int64_t 
     if (n_cand < 0 || n_rows < 0 || W < 1 || W > RS_MAX_W) { rs_set_error("rs_host_gather_windows: bad argument"); return RS_ERR_INVALID; }
     if (n_cand == 0) return RS_OK;
     if (!rows || !pos || !out_rows || !out_codes) { rs_set_error("rs_host_gather_windows: null buffer"); return RS_ERR_INVALID; }
-    if (code_stride < 1) code_stride = 1;
+    if (code_stride < 1 && code_stride != -4) code_stride = 1;
     if (rows_dtype == RS_F32)
         gather_impl((const float *)rows, n_rows, codes, code_stride, pos, n_cand, W, (float *)out_rows, out_codes, threads);
     else if (rows_dtype == RS_F64)

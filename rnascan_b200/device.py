@@ -841,6 +841,7 @@ class HostProfile(object):
         self.n = int(rows.shape[0])
         self.dtype = _lib.RS_F32 if rows.dtype == np.float32 else _lib.RS_F64
         self.q8, self.q8_scale = q8, q8_scale
+        self.q4 = None                               # (n, 4) uint8 view of the 4-byte quantised rows (make_q4)
         self._stats = None if stats is None else tuple(float(v) for v in stats)
 
     def stats(self):
@@ -872,6 +873,33 @@ class HostProfile(object):
         return True
 
 
+def _make_q4(self, codes=None, out=None):
+    """Build the 4-byte quantised filter form (seven floored 4-bit channels + the symbol in the top nibble).
+    `out`: a (n, 4) uint8 array to fill.  Returns False when the rows do not fit it."""
+    mx, bad, neg, vmax = self.stats()
+    if bad or neg or self.n == 0:
+        return False
+    scale = vmax if vmax > 0 else 1.0
+    q4 = np.empty((self.n, 4), np.uint8) if out is None else out
+    n_bad = ctypes.c_int64(0)
+    check(lib.rs_host_quantize_q4(_np_ptr(self.rows), self.dtype, self.n, _np_ptr(codes), float(scale),
+                                  q4.ctypes.data, HOST_THREADS, ctypes.byref(n_bad)))
+    if n_bad.value:
+        return False
+    self.q4, self.q8_scale = q4, float(scale)
+    return True
+
+
+HostProfile.make_q4 = _make_q4
+
+
+def q4_guard(struct_table, scale):
+    """The 4-bit form's guard band in score units: scale / 15 times the sum of the table's positive entries (rows
+    with -inf count their positive part)."""
+    t = np.asarray(struct_table, np.float64)
+    return float(scale) / 15.0 * float(np.where(np.isfinite(t) & (t > 0), t, 0.0).sum())
+
+
 def filter_applies(struct_table, threshold, absrow_max):
     """Can the fp32 filter kernels decide candidates for this scan?  (Else: the exact fp64 kernel.)"""
     t = np.asarray(struct_table, np.float64)
@@ -892,21 +920,22 @@ class HostProfileScanner(object):
 
     def __init__(self, n, W, form, chunk_rows=1 << 23, device=None, cand_per_row=1.0 / 256):
         require_cuda()
-        if form not in ("f32", "shadow", "q8"):
-            raise ValueError("form must be 'f32', 'shadow' or 'q8'")
+        if form not in ("f32", "shadow", "q8", "q4"):
+            raise ValueError("form must be 'f32', 'shadow', 'q8' or 'q4'")
         self.device = torch.device(device or "cuda")
         self.n, self.W, self.form = int(n), int(W), form
         self.chunk = max(256, int(chunk_rows) // 256 * 256)
         self.starts = list(range(0, max(self.n - self.W + 1, 1), self.chunk)) if self.n >= self.W else []
-        if form == "q8" and not self.starts and self.n > 0:
+        self.quantised = form in ("q8", "q4")     # the rows carry the symbols: no separate symbol stream
+        if self.quantised and not self.starts and self.n > 0:
             self.starts = [0]                       # nothing to scan, but the symbols still count
         self.rows_max = padded_count(min(self.chunk + self.W - 1, max(self.n, 1))) + 256
-        cols, tdt = (8, torch.uint8) if form == "q8" else (len(CHANNELS), torch.float32)
+        cols, tdt = ((8 if form == "q8" else 4), torch.uint8) if self.quantised else (len(CHANNELS), torch.float32)
         self.cols, self.tdt = cols, tdt
         self.dbuf = [torch.empty((self.rows_max, cols), dtype=tdt, device=self.device) for _ in range(2)]
         self.stage = None                           # pinned staging, made on first use with a pageable source
-        self.codes = None if form == "q8" else torch.empty(padded_count(self.n) + 1024, dtype=torch.uint8,
-                                                           device=self.device)
+        self.codes = None if self.quantised else torch.empty(padded_count(self.n) + 1024, dtype=torch.uint8,
+                                                             device=self.device)
         self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
         self.counts_host = torch.zeros(8, dtype=torch.int64, pin_memory=True)
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -915,12 +944,14 @@ class HostProfileScanner(object):
         self.cap = max(4096, int(self.chunk * cand_per_row))
         self._alloc_cand()
         self.h2d_bytes = self.d2h_bytes = 0
-        self.n_candidates = self.n_filter_pass = 0
+        self.n_candidates = self.n_filter_pass = self.n_struct_candidates = 0
         self.launches = 0
 
     def _alloc_cand(self):
         k = max(len(self.starts), 1)
         self.cand = torch.empty((k, self.cap), dtype=torch.int64, device=self.device)
+        # 4-bit rows: every candidate's packed symbols, for the sequence table that arrives after the filter pass
+        self.cand_sym = torch.empty((k, self.cap), dtype=torch.int64, device=self.device) if self.form == "q4" else None
         self.cand_counters = torch.zeros((k, 2), dtype=torch.int64, device=self.device)
         self.cand_counters_host = torch.zeros((k, 2), dtype=torch.int64, pin_memory=True)
         self.work_bytes = int(lib.rs_filter_workspace_bytes(self.chunk + self.W + 256, self.cap))
@@ -953,10 +984,10 @@ class HostProfileScanner(object):
             if k >= 2:
                 self.copy_stream.wait_event(self.freed[slot])
             self.dbuf[slot][:rows].copy_(piece, non_blocking=True)
-            if self.form == "q8":                   # rows past the end of the stream read as separators
+            if self.quantised:                      # rows past the end of the stream read as separators
                 self.dbuf[slot][rows:rows + 512].fill_(0xFF)
             self.loaded[slot].record(self.copy_stream)
-        self.h2d_bytes += rows * self.cols * (1 if self.form == "q8" else 4)
+        self.h2d_bytes += rows * self.cols * (1 if self.quantised else 4)
         return rows
 
     def run(self, codes, filt_src, exact_rows, struct_table, seq, threshold, absrow_max, q8_scale=1.0,
@@ -976,19 +1007,21 @@ class HostProfileScanner(object):
         comp = torch.cuda.current_stream(self.device)
         deferred_seq = callable(seq)
         ts = None if (seq is None or deferred_seq) else _table(seq, 4)
-        fmt = {"f32": _lib.RS_ROWS_F32, "shadow": _lib.RS_ROWS_F32_SHADOW, "q8": _lib.RS_ROWS_Q8}[self.form]
+        fmt = {"f32": _lib.RS_ROWS_F32, "shadow": _lib.RS_ROWS_F32_SHADOW, "q8": _lib.RS_ROWS_Q8,
+               "q4": _lib.RS_ROWS_Q4}[self.form]
+        want_sym = self.form == "q4" and deferred_seq
         while True:
             self.h2d_bytes = self.d2h_bytes = 0
             self.launches = 0
             self.copy_stream.wait_stream(comp)
-            if self.form != "q8":
+            if not self.quantised:
                 h = codes if isinstance(codes, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(codes))
                 self.codes[:n].copy_(h[:n], non_blocking=True)
                 self.codes[n:].fill_(_lib.RS_SEP)
                 self.h2d_bytes += n
             if deferred_seq:
                 self.counts.zero_()
-                if self.form != "q8":
+                if not self.quantised:
                     check(lib.rs_hist_rna(_ptr(self.codes), n, _ptr(self.counts), comp.cuda_stream))
                     self.launches += 1
             pending = {}
@@ -999,11 +1032,12 @@ class HostProfileScanner(object):
                 slot = k & 1
                 comp.wait_event(self.loaded[slot])
                 count_rows = min(self.chunk, n - c0)
-                want_counts = deferred_seq and self.form == "q8"
-                check(lib.rs_filter_profile(0 if self.form == "q8" else _ptr(self.codes) + c0, _ptr(self.dbuf[slot]),
+                want_counts = deferred_seq and self.quantised
+                check(lib.rs_filter_profile(0 if self.quantised else _ptr(self.codes) + c0, _ptr(self.dbuf[slot]),
                                             fmt, float(q8_scale), rows, 0 if ts is None else ts.ctypes.data,
                                             tq.ctypes.data, W, threshold, float(absrow_max), c0, count_rows,
                                             _ptr(self.counts) if want_counts else 0, self.cap, _ptr(self.cand[k]),
+                                            _ptr(self.cand_sym[k]) if want_sym else 0,
                                             _ptr(self.cand_counters[k]), _ptr(self.work), self.work_bytes,
                                             comp.cuda_stream))
                 self.launches += 2                  # filter + ordering
@@ -1017,7 +1051,7 @@ class HostProfileScanner(object):
             comp.synchronize()
             cc = self.cand_counters_host.numpy()[:len(self.starts)]
             self.d2h_bytes += cc.size * 8
-            found = cc[:, 0] if len(self.starts) else np.zeros(0, np.int64)
+            found = cc[:, 0].copy() if len(self.starts) else np.zeros(0, np.int64)     # (cc views the pinned buffer)
             if len(found) and int(found.max()) > self.cap:
                 self.cap = int(found.max() * 1.25) + 1024
                 self._alloc_cand()
@@ -1030,12 +1064,31 @@ class HostProfileScanner(object):
             comp.synchronize()
             self.d2h_bytes += 64
         self.n_filter_pass = int(cc[:, 1].sum()) if len(self.starts) else 0
+        if deferred_seq:
+            ts = _table(seq(self.counts_host.numpy()), 4)
+            if ts.shape[0] != W:
+                raise ValueError("sequence and structure motifs must have the same width")
+        if want_sym and len(found) and int(found.sum()):
+            # thin the candidates with the sequence table ON THE DEVICE (their symbols came with them) before
+            # anything is gathered on the host; survivors replace the candidates of their chunk, in order
+            wb = int(lib.rs_refine_packed_workspace_bytes(self.cap))
+            rwork = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            kept = torch.empty_like(self.cand)
+            for k, f in enumerate(found.tolist()):
+                if f:
+                    check(lib.rs_refine_candidates_packed(_ptr(self.cand[k]), _ptr(self.cand_sym[k]), int(f),
+                                                          ts.ctypes.data, W, threshold, _ptr(kept[k]),
+                                                          _ptr(self.cand_counters[k]), _ptr(rwork), wb, comp.cuda_stream))
+                    self.launches += 2
+            self.cand_counters_host.copy_(self.cand_counters, non_blocking=True)
+            comp.synchronize()
+            self.n_struct_candidates = int(found.sum())
+            found = np.where(found > 0, self.cand_counters_host.numpy()[:len(self.starts), 0], 0)
+            self.cand, kept = kept, self.cand
         parts = [self.cand[k, :int(f)].cpu().numpy() for k, f in enumerate(found.tolist()) if f]
         cand = np.concatenate(parts) if parts else np.zeros(0, np.int64)
         self.d2h_bytes += cand.size * 8
         self.n_candidates = int(cand.size)
-        if deferred_seq:
-            ts = _table(seq(self.counts_host.numpy()), 4)
         if ts is not None and ts.shape[0] != W:
             raise ValueError("sequence and structure motifs must have the same width")
         return self._resolve(cand, codes if exact_codes is None else exact_codes, filt_src, exact_rows, ts, tq,
@@ -1050,6 +1103,9 @@ class HostProfileScanner(object):
         if codes is None and self.form == "q8":     # the symbols ride in byte 7 of the quantised rows
             q = filt_src.numpy() if isinstance(filt_src, torch.Tensor) else np.asarray(filt_src)
             code_ptr, code_stride = q.ctypes.data + 7, 8
+        elif codes is None and self.form == "q4":   # ... or in the top nibble of the 4-byte rows
+            q = filt_src.numpy() if isinstance(filt_src, torch.Tensor) else np.asarray(filt_src)
+            code_ptr, code_stride = q.ctypes.data, -4
         elif codes is None:
             code_ptr, code_stride = 0, 1
         else:

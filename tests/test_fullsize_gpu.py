@@ -150,8 +150,9 @@ def test_sampled_positions_against_the_cpu_oracle(env, oracle):
 
 @pytest.mark.parametrize("thr", [6.0, 2.5])
 def test_host_resident_pipelines_equal_the_device_resident_scan_full_size(env, thr):
-    """100 M rows in HOST memory through device.HostProfileScanner -- 8-byte quantised rows (background counted in the
-    filter pass) and float32 rows -- against rs_scan_fused on the resident streams: identical positions and scores,
+    """100 M rows in HOST memory through device.HostProfileScanner -- 8-byte and 4-byte quantised rows (background
+    counted in the filter pass; 4-byte: sequence table applied to the packed symbols on the device) and float32 rows
+    -- against rs_scan_fused on the resident streams: identical positions and scores,
     identical counts."""
     dev, st, pf, tq, bench = env["dev"], env["st"], env["pf"], env["tq"], env["bench"]
     n = st.n
@@ -172,9 +173,10 @@ def test_host_resident_pipelines_equal_the_device_resident_scan_full_size(env, t
         seen.append(np.array(counts8, np.int64))
         return tables(counts8)[0]
 
-    for form, src, cd in (("q8", hp.q8, None), ("f32", rows, codes)):
+    assert hp.make_q4(codes)
+    for form, src, cd in (("q8", hp.q8, None), ("q4", hp.q4, None), ("f32", rows, codes)):
         sc = dev.HostProfileScanner(n, tq.shape[0], form)
-        got = sc.run(cd, src, rows, tq, seq_fn, thr, hp.absrow_max(), q8_scale=hp.q8_scale if form == "q8" else 1.0)
+        got = sc.run(cd, src, rows, tq, seq_fn, thr, hp.absrow_max(), q8_scale=hp.q8_scale if form != "f32" else 1.0)
         assert np.array_equal(seen[-1], env["counts"]), form
         assert np.array_equal(got[0], want[0]), form
         assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), form

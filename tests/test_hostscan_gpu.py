@@ -66,6 +66,9 @@ def run_form(dev, form, codes, rows, seq, tq, thr, chunk_rows=1 << 23, cand_per_
     if form == "q8":
         assert hp.make_q8(codes)
         src, scale, cd = hp.q8, hp.q8_scale, None
+    elif form == "q4":
+        assert hp.make_q4(codes)
+        src, scale, cd = hp.q4, hp.q8_scale, None
     else:
         src, scale, cd = rows, 1.0, codes
     sc = dev.HostProfileScanner(len(codes), W, form, chunk_rows=chunk_rows, cand_per_row=cand_per_row)
@@ -73,7 +76,7 @@ def run_form(dev, form, codes, rows, seq, tq, thr, chunk_rows=1 << 23, cand_per_
     return out, sc
 
 
-FORMS64 = ["shadow", "q8"]
+FORMS64 = ["shadow", "q8", "q4"]
 
 
 @pytest.mark.parametrize("form", FORMS64)
@@ -92,7 +95,7 @@ def test_struct_mode_matches_oracle(dev, oracle, form, W, zero, thr):
     assert scanner.n_candidates >= len(wpos)
 
 
-@pytest.mark.parametrize("form", ["f32", "shadow", "q8"])
+@pytest.mark.parametrize("form", ["f32", "shadow", "q8", "q4"])
 @pytest.mark.parametrize("W,thr", [(7, 0.0), (7, 1.5), (10, -2.0), (16, -4.0)])
 def test_and_mode_matches_oracle(dev, oracle, form, W, thr):
     dtype = np.float32 if form == "f32" else np.float64
@@ -105,7 +108,7 @@ def test_and_mode_matches_oracle(dev, oracle, form, W, thr):
     assert_same_float(sc, wsc)
 
 
-@pytest.mark.parametrize("form", ["f32", "shadow", "q8"])
+@pytest.mark.parametrize("form", ["f32", "shadow", "q8", "q4"])
 def test_computed_background_counts_in_the_same_pass(dev, oracle, form):
     """seq given as a callable of the counts: the device counts the symbols (inside the quantised filter
     kernel / rs_hist_rna) and the sequence table is applied in the resolve step."""
@@ -186,7 +189,7 @@ def test_shadow_rows_at_float32_rounding_midpoints(dev, oracle):
 
 
 @pytest.mark.parametrize("n", [0, 3, 7, 8, 1151, 1152, 1153, 2310, 9999])
-@pytest.mark.parametrize("form", ["shadow", "q8"])
+@pytest.mark.parametrize("form", ["shadow", "q8", "q4"])
 def test_tiny_and_tile_edge_lengths(dev, oracle, form, n):
     W = 7
     rng = np.random.default_rng(n + 5)
@@ -200,6 +203,8 @@ def test_tiny_and_tile_edge_lengths(dev, oracle, form, n):
     hp = dev.HostProfile(rows)
     if form == "q8" and n:
         assert hp.make_q8(codes)
+    if form == "q4" and n:
+        assert hp.make_q4(codes)
     pos, sq, sc = dev.scan_profile_host(codes, hp, ts, tq, thr, chunk_rows=1024)
     if n >= W:
         wpos, wsq, wsc = oracle_hits(oracle, codes, rows, ts, tq, thr, W)
@@ -248,7 +253,7 @@ def test_filter_entry_point_validates_arguments(dev):
     d = torch.zeros(4096 * 8, dtype=torch.uint8, device="cuda")
     c = torch.zeros(2, dtype=torch.int64, device="cuda")
     args = lambda fmt, W, thr, scale=1.0: lib.rs_filter_profile(d.data_ptr(), d.data_ptr(), fmt, scale, 1000, 0,
-                                                                t.ctypes.data, W, thr, 1.0, 0, 0, 0, 0, 0,
+                                                                t.ctypes.data, W, thr, 1.0, 0, 0, 0, 0, 0, 0,
                                                                 c.data_ptr(), d.data_ptr(), d.numel(), 0)
     assert args(7, 7, 0.0) == _lib.RS_ERR_INVALID                     # unknown row format
     assert args(_lib.RS_ROWS_F32, 25, 0.0) == _lib.RS_ERR_INVALID     # W beyond the filter kernels
@@ -256,6 +261,10 @@ def test_filter_entry_point_validates_arguments(dev):
     assert args(_lib.RS_ROWS_F32, 7, float("-inf")) == _lib.RS_ERR_INVALID
     assert args(_lib.RS_ROWS_Q8, 7, 0.0, scale=0.0) == _lib.RS_ERR_INVALID
     assert args(_lib.RS_ROWS_Q8, 7, 0.0) == _lib.RS_OK
+    assert args(_lib.RS_ROWS_Q4, 7, 0.0) == _lib.RS_OK
+    # candidate symbols are a feature of the 4-bit rows only
+    assert lib.rs_filter_profile(d.data_ptr(), d.data_ptr(), _lib.RS_ROWS_Q8, 1.0, 1000, 0, t.ctypes.data, 7, 0.0, 1.0, 0,
+                                 0, 0, 0, 0, d.data_ptr(), c.data_ptr(), d.data_ptr(), d.numel(), 0) == _lib.RS_ERR_INVALID
 
 
 def test_host_fused_scanner_matches_oracle_and_regrows(dev, oracle):
@@ -289,3 +298,37 @@ def test_host_fused_scanner_matches_oracle_and_regrows(dev, oracle):
     assert len(wpos) > 4 * cap0 and pipe.hb[0].capacity > cap0
     assert np.array_equal(pos, wpos) and sq is None
     assert_same_float(sc, wsc)
+
+
+def test_four_bit_form_floors_and_carries_symbols(dev, oracle):
+    """RS_ROWS_Q4: every stored value is a floor (never above the exact one, less than one step below), the symbol
+    sits in the top nibble; with the sequence table arriving after the filter pass the candidates are thinned on
+    the device (rs_refine_candidates_packed) before the host gathers anything."""
+    from rnascan_b200 import synth
+    W, thr = 7, 1.0
+    codes, off, lengths, rows, _, tq = make_case(400_000, 90, 4040, W)
+    hp = dev.HostProfile(rows)
+    assert hp.make_q4(codes)
+    words = hp.q4.view(np.uint32).ravel()
+    step = hp.q8_scale / 15
+    for c in range(7):
+        stored = ((words >> (4 * c)) & 0xF).astype(np.float64) * step
+        assert (stored <= rows[:, c]).all() and (rows[:, c] - stored < step * (1 + 1e-9)).all()
+    assert np.array_equal((words >> 28).astype(np.uint8), codes & 0xF)
+    prob = synth.pfm_rows(W, 4, np.random.default_rng(9))
+
+    def seq_table(counts8):
+        bg = (np.asarray(counts8[:4], np.float64) + 1) / (float(np.sum(counts8[:4])) + 4)
+        return synth.pssm_table(prob, background=list(bg / bg.sum()))
+
+    sc = dev.HostProfileScanner(len(codes), W, "q4", chunk_rows=65536)
+    pos, sq, st = sc.run(None, hp.q4, rows, tq, seq_table, thr, hp.absrow_max(), q8_scale=hp.q8_scale)
+    counts = np.array([(codes == k).sum() for k in range(4)] + [0] * 4, np.int64)
+    wpos, wsq, wsc = oracle_hits(oracle, codes, rows, seq_table(counts), tq, thr, W)
+    assert len(wpos) > 0
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sq, wsq)
+    assert_same_float(st, wsc)
+    # the structure-only candidates were many, the gathered ones few
+    assert sc.n_struct_candidates > 20 * max(sc.n_candidates, 1) and sc.n_candidates >= len(wpos)
+    assert dev.q4_guard(tq, hp.q8_scale) > 0.5
