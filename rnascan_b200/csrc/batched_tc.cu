@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
              *b_full = acc_empty + 2, *mask_full = b_full + 1;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(mask_full + TC_MASK_STAGES);
     unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(smem + 96 * 1024);   // 4 x TC_CBUF keys
-    uint4 *s_mask = reinterpret_cast<uint4 *>(smem + 160 * 1024);   // [TC_MASK_STAGES][128 positions][2 x uint4]
+    uint4 *s_mask = reinterpret_cast<uint4 *>(smem + 160 * 1024);   // [TC_MASK_STAGES][2 halves][128 positions] x uint4
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             if (use_mask) {
                 const int ms = (int)(it % TC_MASK_STAGES);
                 mbar_wait(&mask_full[ms], (uint32_t)((it / TC_MASK_STAGES) & 1));
-                mk = s_mask[(ms * TC_M + q * 32 + lane) * 2 + half];
+                mk = s_mask[(ms * 2 + half) * TC_M + q * 32 + lane];      // lanes read consecutive 16-byte words
             }
             const uint32_t smask[TC_N / 64] = {mk.x, mk.y, mk.z, mk.w};
             mbar_wait(&acc_full[t], (uint32_t)((it >> 1) & 1));
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) batched_tc_kernel(const __grid_
             if (use_mask) {
                 const int ms = (int)(it % TC_MASK_STAGES);
                 const uint32_t *wm = prm.wmask[f];
-                s_mask[(ms * TC_M + ct) * 2] = make_uint4(m_lo.x & wm[0], m_lo.y & wm[1], m_lo.z & wm[2], m_lo.w & wm[3]);
-                s_mask[(ms * TC_M + ct) * 2 + 1] = make_uint4(m_hi.x & wm[4], m_hi.y & wm[5], m_hi.z & wm[6], m_hi.w & wm[7]);
+                s_mask[(ms * 2) * TC_M + ct] = make_uint4(m_lo.x & wm[0], m_lo.y & wm[1], m_lo.z & wm[2], m_lo.w & wm[3]);
+                s_mask[(ms * 2 + 1) * TC_M + ct] = make_uint4(m_hi.x & wm[4], m_hi.y & wm[5], m_hi.z & wm[6], m_hi.w & wm[7]);
             }
             fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
@@ -437,36 +437,55 @@ __global__ void __launch_bounds__(256) seqmask_build_kernel(uint32_t *mask, int 
                                                             const int *widths, int n_motifs, int stride_rows,
                                                             double threshold)
 {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= (int64_t)65536 * mask_words) return;
-    const uint32_t kmer = (uint32_t)(t / mask_words);
-    const int word = (int)(t % mask_words);
-    uint32_t bits = 0;
-    for (int k = 0; k < 32; k++) {
-        const int m = word * 32 + k;
-        if (m >= n_motifs) break;
-        const int W = widths[m];
-        const double *tab = seq_tables + (size_t)m * stride_rows * 4;
-        double sum = 0.0;
-        const int wp = W < 8 ? W : 8;
-        for (int j = 0; j < wp; j++) sum = __dadd_rn(sum, tab[j * 4 + ((kmer >> (2 * j)) & 3u)]);
-        bool pass;
-        if (W <= 8) {
-            pass = (double)(float)sum > threshold;
-        } else {
-            bool inf = false;
+    // block (word, slab): the 32 motifs of one mask word, 1024 consecutive 8-mers; their tables sit in shared memory
+    __shared__ double s_tab[32 * 8 * 4];          // first 8 rows of each motif
+    __shared__ double s_rest[32];                 // W > 8: the most the rows beyond the 8th can add (NaN: no bound)
+    __shared__ int s_w[32];
+    const int word = blockIdx.x, slab = blockIdx.y;
+    for (int k = threadIdx.x; k < 32 * 32; k += blockDim.x) {
+        const int m = word * 32 + (k >> 5), e = k & 31;                // e = row * 4 + letter
+        s_tab[k] = (m < n_motifs && (e >> 2) < stride_rows) ? seq_tables[(size_t)m * stride_rows * 4 + e] : 0.0;
+    }
+    if (threadIdx.x < 32) {
+        const int m = word * 32 + threadIdx.x;
+        int W = 0;
+        double rest = 0.0;
+        if (m < n_motifs) {
+            W = widths[m];
+            const double *tab = seq_tables + (size_t)m * stride_rows * 4;
             for (int j = 8; j < W; j++) {
                 const double mx = fmax(fmax(tab[j * 4], tab[j * 4 + 1]), fmax(tab[j * 4 + 2], tab[j * 4 + 3]));
-                if (mx != mx || mx == INFINITY) inf = true;      // NaN / +inf entries: no bound, let the exact pass decide
-                sum += mx;
+                if (mx != mx || mx == INFINITY) rest = nan("");         // NaN / +inf entries: let the exact pass decide
+                else rest += mx;
             }
-            // the sequential float64 adds of the real score differ from this sum by a few ulps at most
-            const double bound = sum + fabs(sum) * 1e-12 + 1e-300;
-            pass = inf || sum != sum || (double)(float)bound > threshold;
         }
-        if (pass) bits |= 1u << (31 - k);
+        s_w[threadIdx.x] = W;
+        s_rest[threadIdx.x] = rest;
     }
-    mask[t] = bits;
+    __syncthreads();
+    for (int q = threadIdx.x; q < 1024; q += blockDim.x) {
+        const uint32_t kmer = (uint32_t)slab * 1024u + (uint32_t)q;
+        uint32_t bits = 0;
+        for (int k = 0; k < 32; k++) {
+            const int W = s_w[k];
+            if (W == 0) break;
+            const double *tab = s_tab + k * 32;
+            const int wp = W < 8 ? W : 8;
+            double sum = 0.0;
+            for (int j = 0; j < wp; j++) sum = __dadd_rn(sum, tab[j * 4 + ((kmer >> (2 * j)) & 3u)]);
+            bool pass;
+            if (W <= 8) {
+                pass = (double)(float)sum > threshold;
+            } else {
+                // the sequential float64 adds of the real score differ from this sum by a few ulps at most
+                const double total = sum + s_rest[k];
+                const double bound = total + fabs(total) * 1e-12 + 1e-300;
+                pass = total != total || (double)(float)bound > threshold;
+            }
+            if (pass) bits |= 1u << (31 - k);
+        }
+        mask[(size_t)kmer * mask_words + word] = bits;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ exact re-score
@@ -811,9 +830,8 @@ int rs_scan_batched_tc(const uint8_t *d_codes, const void *d_profile, int64_t n,
     }
     const bool use_mask = mode == RS_MODE_AND && seq_tables != nullptr && g_tc_seqmask;
     if (use_mask) {
-        const int64_t threads = (int64_t)65536 * mask_words;
-        seqmask_build_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_seqmask, mask_words, d_ts, d_w, n_motifs,
-                                                                              stride_rows, threshold);
+        seqmask_build_kernel<<<dim3((unsigned)mask_words, 64), 256, 0, st>>>(d_seqmask, mask_words, d_ts, d_w, n_motifs,
+                                                                            stride_rows, threshold);
         RS_CUDA(cudaGetLastError());
     }
     TcParams tp = {};
