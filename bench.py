@@ -396,6 +396,8 @@ def measure(args, wl, steps, ctx, full, n_target):
         # the structure-only candidate scan overlaps histogram -> all-reduce -> host log-odds (side stream);
         # rs_refine_hits_seq applies the sequence PSSM to the candidates (device.BackgroundFusedScan)
         bgscan = dev.BackgroundFusedScan(n, device, capacity=hb.capacity)
+        if os.environ.get("RS_BENCH_COUNT_IN_KERNEL") in ("0", "1"):         # experiment switch (tools/gpu_r2p.sh)
+            bgscan.count_in_kernel = os.environ["RS_BENCH_COUNT_IN_KERNEL"] == "1"
         hb = bgscan.hb
         tq_fixed = tables(np.zeros(8, np.int64))[1]
 
@@ -630,9 +632,13 @@ def measure(args, wl, steps, ctx, full, n_target):
                                 "c5": "C5 batched %d motif pairs (W 7-12), seq + averaged structure" % N_MOTIFS_C5}[wl],
                    "symbols_per_gpu": n, "records_per_gpu": int(len(shard["lengths"])),
                    "scored_positions_total": all_positions, "W": W_MOTIF, "minscore": THRESHOLD,
-                   "background": ("computed every step: histogram -> all-reduce(int64[8]) -> host log-odds on a side "
+                   "background": (("computed every step: the structure-only candidate scan counts the letters itself "
+                                   "(rs_scan_fused_candidates_counting) -> all-reduce(int64[8]) -> host log-odds; the sequence "
+                                   "PSSM is applied to the candidates afterwards (rs_scan_fused_resolve)")
+                                  if (bgscan is not None and bgscan.count_in_kernel) else
+                                  "computed every step: histogram -> all-reduce(int64[8]) -> host log-odds on a side "
                                   "stream, overlapped with the structure-only candidate scan; the sequence PSSM is "
-                                  "applied to the candidates afterwards (rs_refine_hits_seq)") if bgscan is not None else
+                                  "applied to the candidates afterwards (rs_scan_fused_resolve)") if bgscan is not None else
                                  ("computed every step: histogram -> all-reduce(int64[8]); the device scans with a provisional "
                                   "log-odds table while the counts go to the host, the exact host table decides and scores "
                                   "the candidates (rs_scan_onehot_begin/_finish)" if ohscan is not None else
@@ -648,7 +654,9 @@ def measure(args, wl, steps, ctx, full, n_target):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_position": ALGO_BYTES[wl],
                      "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step,
-                     "traffic": recorded_traffic(wl, n)[0], "traffic_source": recorded_traffic(wl, n)[1]},
+                     "traffic": recorded_traffic(wl, n)[0], "traffic_source": recorded_traffic(wl, n)[1],
+                     "note": "peak = a device-to-device COPY (half reads, half writes); a read-only stream like this "
+                             "kernel's can run a few per cent above it"},
         "clocks": clocks,
     }
     if hits is not None:

@@ -291,6 +291,15 @@ int rs_scan_fused_candidates(const uint8_t *d_codes, const void *d_profile, int 
                              double profile_absrow_max, int64_t hit_capacity,
                              uint64_t *d_cand_counters2, void *d_work, int64_t work_bytes,
                              int64_t *staged_tiles, void *stream);
+/* rs_scan_fused_candidates that also takes the sequence's background counts in the same pass (the symbols are staged
+ * for the scan anyway): d_counts8[0..3] += letters A,C,G,U (not zeroed here).  For streams so long that the
+ * histogram's second read of the symbols costs more than waiting for the counts until the scan has finished;
+ * needs the fp32 filter path (float32 rows, W <= 24, finite / -inf tables, finite threshold), n >= W.          */
+int rs_scan_fused_candidates_counting(const uint8_t *d_codes, const void *d_profile, int profile_dtype,
+                                      int64_t n, const double *struct_table_Wx7, int W, double threshold,
+                                      double profile_absrow_max, int64_t hit_capacity,
+                                      uint64_t *d_cand_counters2, uint64_t *d_counts8, void *d_work,
+                                      int64_t work_bytes, int64_t *staged_tiles, void *stream);
 int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_table_Wx4, int W,
                           double threshold, int64_t staged_tiles, int64_t hit_capacity,
                           int64_t *d_hit_pos, float *d_hit_seq, double *d_hit_struct,

@@ -75,6 +75,8 @@ _SIGS = {
     "rs_scan_onehot_finish": ([_int, _vp, _i64, _vp, _int, _dbl, _i64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_refine_hits_seq": ([_vp, _i64, _vp, _int, _dbl, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_scan_fused_candidates": ([_vp, _vp, _int, _i64, _vp, _int, _dbl, _dbl, _i64, _vp, _vp, _i64, _vp, _vp], _int),
+    "rs_scan_fused_candidates_counting": ([_vp, _vp, _int, _i64, _vp, _int, _dbl, _dbl, _i64, _vp, _vp, _vp, _i64, _vp,
+                                           _vp], _int),
     "rs_scan_fused_resolve": ([_vp, _i64, _vp, _int, _dbl, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_filter_workspace_bytes": ([_i64, _i64], _i64),
     "rs_filter_profile": ([_vp, _vp, _int, _dbl, _i64, _vp, _vp, _int, _dbl, _dbl, _i64, _i64, _vp, _i64, _vp, _vp, _vp,

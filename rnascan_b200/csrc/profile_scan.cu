@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __gri
     if (tid == 0)
         for (int64_t it = 0; it < FT_STAGES - 1 && it < my_tiles; it++) issue(it);
 
+    unsigned cnt[4] = {0u, 0u, 0u, 0u};
+
     for (int64_t it = 0; it < my_tiles; it++) {
         const int s = (int)(it % FT_STAGES);
         if (tid == 0 && it + FT_STAGES - 1 < my_tiles) issue(it + FT_STAGES - 1);
@@ -128,6 +130,20 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __gri
             }
         }
 
+        // ---- background counts of the rows this thread owns (rs_scan_fused_candidates_counting): the symbols are
+        //      staged anyway, so the separate histogram pass -- a second read of 1 of the 30 B per position -- goes away
+        if (prm.count_on) {
+            unsigned packed = 0;                                   // four byte counters, <= 9 each
+#pragma unroll
+            for (int r = 0; r < FT_P; r++) {
+                const unsigned code = codes[tid * FT_P + r];
+                const bool counted = code < 4u && t0 + tid * FT_P + r < prm.count_rows;
+                packed += counted ? (1u << (8u * code)) : 0u;
+            }
+            cnt[0] += packed & 0xffu; cnt[1] += (packed >> 8) & 0xffu;
+            cnt[2] += (packed >> 16) & 0xffu; cnt[3] += packed >> 24;
+        }
+
         // ---- guard band: anything not provably below the threshold is re-scored exactly, the whole CTA sharing
         //      the tile's candidates (resolve_tile_candidates)
         unsigned candmask = 0;
@@ -154,6 +170,15 @@ __global__ void __launch_bounds__(FT_THREADS, 2) fused_filter_kernel(const __gri
                 });
         } else if (tid == 0) {
             prm.st.tile_seg[tile] = make_ulonglong2(0ull, 0ull);
+        }
+    }
+
+    if (prm.count_on) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned v = cnt[k];
+            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if ((tid & 31) == 0 && v) atomicAdd(prm.counts8 + k, (unsigned long long)v);
         }
     }
 }
@@ -476,7 +501,8 @@ static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int pr
                            double profile_absrow_max, int mode, int64_t hit_capacity, int64_t *d_hit_pos,
                            float *d_hit_seq, double *d_hit_struct, uint64_t *d_counters2, void *d_work,
                            int64_t work_bytes, void *stream, const unsigned long long *d_out_base,
-                           int32_t *d_hit_motif, int32_t motif_id, int64_t *staged_tiles_out = nullptr)
+                           int32_t *d_hit_motif, int32_t motif_id, int64_t *staged_tiles_out = nullptr,
+                           uint64_t *d_counts8 = nullptr)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_common(d_profile, profile_dtype, n, struct_table, W);
@@ -512,9 +538,14 @@ static int scan_fused_impl(const uint8_t *d_codes, const void *d_profile, int pr
     if (seq_table) for (int k = 0; k < W * 4; k++) prm.qd[k] = seq_table[k];
 
     int64_t n_tiles;
+    if (d_counts8 && !fast) {
+        rs_set_error("in-kernel background counts need the fp32 filter path (float32 profile, W <= %d, finite tables)", RS_FAST_W);
+        return RS_ERR_INVALID;
+    }
     if (fast) {
         n_tiles = (n + FT_TILE - 1) / FT_TILE;
         prm.n_tiles = n_tiles;
+        prm.count_on = d_counts8 ? 1 : 0; prm.counts8 = (unsigned long long *)d_counts8; prm.count_rows = n;
         rc = FilterDispatch<RS_FAST_W>::run(W, prm, st);
     } else {
         n_tiles = (n + EX_TILE - 1) / EX_TILE;
@@ -540,6 +571,21 @@ extern "C" int rs_scan_fused_candidates(const uint8_t *d_codes, const void *d_pr
     return scan_fused_impl(d_codes, d_profile, profile_dtype, n, nullptr, struct_table, W, threshold,
                            profile_absrow_max, RS_MODE_STRUCT, hit_capacity, nullptr, nullptr, nullptr,
                            d_cand_counters2, d_work, work_bytes, stream, nullptr, nullptr, 0, staged_tiles);
+}
+
+// The same, taking the sequence's background counts in the same pass: d_counts8[0..3] += letters A,C,G,U of the
+// stream (not zeroed here).  Needs the fp32 filter path (else RS_ERR_INVALID: use rs_hist_rna beside the scan).
+extern "C" int rs_scan_fused_candidates_counting(const uint8_t *d_codes, const void *d_profile, int profile_dtype,
+                                                 int64_t n, const double *struct_table, int W, double threshold,
+                                                 double profile_absrow_max, int64_t hit_capacity,
+                                                 uint64_t *d_cand_counters2, uint64_t *d_counts8, void *d_work,
+                                                 int64_t work_bytes, int64_t *staged_tiles, void *stream)
+{
+    if (!staged_tiles || !d_counts8) { rs_set_error("rs_scan_fused_candidates_counting: null argument"); return RS_ERR_INVALID; }
+    if (n < W) { rs_set_error("rs_scan_fused_candidates_counting: stream shorter than the motif (count with rs_hist_rna)"); return RS_ERR_INVALID; }
+    return scan_fused_impl(d_codes, d_profile, profile_dtype, n, nullptr, struct_table, W, threshold,
+                           profile_absrow_max, RS_MODE_STRUCT, hit_capacity, nullptr, nullptr, nullptr,
+                           d_cand_counters2, d_work, work_bytes, stream, nullptr, nullptr, 0, staged_tiles, d_counts8);
 }
 
 extern "C" int rs_scan_fused_resolve(const uint8_t *d_codes, int64_t n, const double *seq_table, int W,

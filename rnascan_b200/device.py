@@ -425,6 +425,12 @@ class BackgroundFusedScan(object):
         self.ready = torch.cuda.Event()
         self.hb = HitBuffers(self.n, int(capacity) if capacity else max(1 << 16, self.n // 256), self.device)
         self.launches = 0
+        # Very long streams: the histogram's second read of the symbols (1 of 30 B per position, competing with the scan
+        # for HBM) costs more than waiting for the counts until the scan has finished -- the scan kernel then counts
+        # the letters itself (rs_scan_fused_candidates_counting).  Measured cross-over: several 10^8 symbols.
+        self.count_in_kernel = self.n >= self.COUNT_IN_KERNEL_FROM
+
+    COUNT_IN_KERNEL_FROM = 700_000_000
 
     def launch(self, codes, profile_rows, profile_dtype, W, struct_table, seq_table_fn, threshold,
                absrow_max, all_reduce=None):
@@ -438,6 +444,25 @@ class BackgroundFusedScan(object):
         # the big kernel first, so that the host-side cost of the side-stream calls (the collective above
         # all) is spent while the device is already busy
         tiles = ctypes.c_int64(0)
+        if self.count_in_kernel and profile_dtype == _lib.RS_F32 and W <= 24 and n >= W and \
+                filter_applies(tq, threshold, absrow_max):
+            self.counts.zero_()
+            check(lib.rs_scan_fused_candidates_counting(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,
+                                                        float(threshold), float(absrow_max), hb.capacity,
+                                                        _ptr(hb.cand_counters), _ptr(self.counts), _ptr(hb.work),
+                                                        hb.work_bytes, ctypes.addressof(tiles), main.cuda_stream))
+            if all_reduce is not None:
+                all_reduce(self.counts)                     # the path's only collective
+            self.counts_host.copy_(self.counts, non_blocking=True)
+            main.synchronize()
+            ts = _table(seq_table_fn(self.counts_host.numpy()), 4)
+            if ts.shape[0] != W:
+                raise ValueError("sequence and structure motifs must have the same width")
+            check(lib.rs_scan_fused_resolve(_ptr(codes), n, ts.ctypes.data, W, float(threshold), tiles.value,
+                                            hb.capacity, _ptr(hb.pos), _ptr(hb.seq), _ptr(hb.struct),
+                                            _ptr(hb.counters), _ptr(hb.work), hb.work_bytes, main.cuda_stream))
+            self.launches = 2          # candidate scan (+ counts), sequence check + ordering
+            return ts
         check(lib.rs_set_reserved_sms(1 if all_reduce is not None else 0))    # room for the collective's kernel
         try:
             check(lib.rs_scan_fused_candidates(_ptr(codes), _ptr(profile_rows), profile_dtype, n, tq.ctypes.data, W,

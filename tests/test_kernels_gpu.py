@@ -288,6 +288,35 @@ def test_scan_fused_bg_matches_oracle_and_one_pass(dev, oracle, dtype, W, thr, c
         assert len(seen) > 2, "a tiny candidate buffer must have forced a regrow + second launch"
 
 
+@pytest.mark.parametrize("W,thr,cap", [(7, 0.0, None), (7, 6.0, None), (18, 0.5, 1000), (1, 0.2, None)])
+def test_scan_fused_bg_counting_inside_the_scan_kernel(dev, oracle, monkeypatch, W, thr, cap):
+    """Very long streams let the scan kernel count the letters itself (rs_scan_fused_candidates_counting) instead of
+    running the histogram beside it; forced here on a small stream: counts exact, hits identical to the oracle."""
+    from rnascan_b200 import synth
+    monkeypatch.setattr(dev.BackgroundFusedScan, "COUNT_IN_KERNEL_FROM", 0)
+    st, pf, codes, rows, _, tq = _profile_case(dev, 700_003, 180, 531 + W, np.float32, W)
+    prob = synth.pfm_rows(W, 4, np.random.default_rng(17 + W))
+    seen = []
+
+    def seq_table(counts8):
+        seen.append(np.array(counts8[:8], np.int64))
+        bg = (np.asarray(counts8[:4], np.float64) + 1) / (float(np.sum(counts8[:4])) + 4)
+        return synth.pssm_table(prob, background=list(bg / bg.sum()))
+
+    pos, sq, sc, counts = dev.scan_fused_bg(st, pf, tq, seq_table, thr, capacity=cap)
+    want_counts = np.array([(codes == k).sum() for k in range(4)], np.int64)
+    assert np.array_equal(counts[:4], want_counts) and not counts[4:].any() and np.array_equal(seen[-1][:4], want_counts)
+    ts = seq_table(want_counts)
+    with np.errstate(all="ignore"):
+        b = oracle.profile_scores(rows, tq)
+    a = oracle.seq_scores(synth.to_text(codes, "rna"), ts)
+    with np.errstate(invalid="ignore"):
+        wpos = np.nonzero((a.astype(np.float64) > thr) & (b > thr))[0]
+    assert np.array_equal(pos, wpos)
+    assert_same_float(sq, a[wpos])
+    assert_same_float(sc, b[wpos])
+
+
 @pytest.mark.parametrize("W,thr", [(7, 0.0), (12, -1.0), (30, -5.0)])
 def test_refine_hits_seq_equals_and_scan(dev, oracle, W, thr):
     """structure-only scan, then rs_refine_hits_seq on its ordered hits == the one-pass AND scan."""
