@@ -1214,11 +1214,24 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     if size > 1:
         first = all_names.index(names[0]) if names else 0          # this rank's files are a contiguous range
         gathered = shard.gather_arrays([rec + first, start0, np.asarray(scores, np.float64)])
-        if gathered is None:
-            return (pd.DataFrame(), n_files, None) if want_arrays else (pd.DataFrame(), n_files)
-        hit_names = [all_names[r] for g in gathered for r in g[0].tolist()]
-        start0 = np.concatenate([g[1] for g in gathered])
-        scores = np.concatenate([g[2] for g in gathered])
+        if gathered is not None:
+            hit_names = [all_names[r] for g in gathered for r in g[0].tolist()]
+            start0 = np.concatenate([g[1] for g in gathered])
+            scores = np.concatenate([g[2] for g in gathered])
+    # Combined mode without a single joint hit: the reference's merge still needs the STRUCTURE frame's columns,
+    # which exist iff some window passes the structure threshold on its own (else its merge raises KeyError, and
+    # so does ours): one structure-only pass settles it -- only in this corner, on every rank when sharded.
+    any_struct_hits = None
+    if seq is not None:
+        need = len(hit_names) == 0 if rank == 0 else None
+        if size > 1:
+            need = shard.broadcast_object(need)
+        if need:
+            local = bool(len(codes)) and len(device.scan_profile_host(codes, hp, None, tq, minscore)[0]) > 0
+            found = shard.gather_objects(local) if size > 1 else [local]
+            any_struct_hits = bool(found and any(found))
+    if size > 1 and rank != 0:            # only rank 0 assembles and prints
+        return (pd.DataFrame(), n_files, None) if want_arrays else (pd.DataFrame(), n_files)
     first_has_hits = None
     if seq is not None and n_files > 1 and rank == 0 and len(lengths):
         # combined mode: `hit_names` only knows the windows where BOTH scores pass, but the column order of the
@@ -1226,13 +1239,14 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         # structure hits: one small structure-only scan of that file settles it
         first = device.HostProfile(np.ascontiguousarray(hp.rows[:int(lengths[0])]))
         first_has_hits = len(device.scan_profile_host(None, first, None, tq, minscore)[0]) > 0
-    frame = _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits)
+    frame = _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits, any_struct_hits)
     if want_arrays and arrays is not None and first_has_hits is False:
         arrays = None                     # unusual column order: the DataFrame path prints it
     return (frame, n_files, arrays) if want_arrays else (frame, n_files)
 
 
-def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits=None):
+def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits=None,
+                        any_struct_hits=None):
     """The frame the reference gets for a directory (rnascan.py:348-375, 408-413): one frame per file built
     by pd.DataFrame(list of Series) -- or, for a file without hits, pd.DataFrame([]) with only the two id
     columns -- then pd.concat and the last two columns moved to the front.  What pandas makes of that mix
@@ -1248,7 +1262,9 @@ def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, f
         _add_sequence_id(proto, "id", "")
     if first_has_hits is True and all_names and all_names[0] not in with_hits:
         any_empty = True                  # (combined mode) its structure hits exist, none of them joint
-    if n == 0 and not first_has_hits:
+    if n == 0 and any_struct_hits and first_has_hits is None:
+        first_has_hits = len(all_names) == 1       # a single file: it is the one with the structure hits
+    if n == 0 and not first_has_hits and not any_struct_hits:
         protos = [empty]
     elif not any_empty:
         protos = [hit]

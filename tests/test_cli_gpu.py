@@ -116,6 +116,32 @@ def test_scan_many_equals_scan_main_per_motif(in_repo):
         assert all(k in keys for k in zip(a["Sequence_ID"], a["Start"]))
 
 
+def test_generated_cases_print_what_the_reference_printed(tmp_path, in_repo):
+    """67 randomly generated CLI runs (all five modes, thresholds from -inf up, zero cells, odd records, shuffled
+    PFM headers, --bgonly): inputs are regenerated from their seeds, stdout must equal what the REFERENCE printed
+    for them in the build container (tests/golden/fuzz, made by tests/golden/make_golden_fuzz.py)."""
+    import warnings
+    import test_differential_cpu as diff
+    from rnascan_b200 import rnascan as ms
+    fuzz = os.path.join(REPO, "tests", "golden", "fuzz")
+    with open(os.path.join(fuzz, "cases.json")) as fh:
+        cases = json.load(fh)
+    assert len(cases) >= 60
+    for seed, case in sorted(cases.items(), key=lambda kv: int(kv[0])):
+        root = str(tmp_path / seed)
+        paths = diff.draw_inputs(np.random.default_rng(9000 + int(seed)), root)
+        argv = [a.format(**paths) if a.startswith("{") else a for a in case["argv"]]
+        ms._BATCH_CACHE.clear()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, _, code = run_cli(argv)
+        ms.REFERENCE_COMPAT = False
+        with open(os.path.join(fuzz, seed + ".stdout")) as fh:
+            want = fh.read()
+        assert code == case["exit"], (seed, case["mode"], argv)
+        assert out == want, (seed, case["mode"], argv)
+
+
 def test_cores_flag_does_not_change_the_result(in_repo):
     base = CASES["rna_mixed_all"]["argv"]
     a = run_cli(base)[0]
