@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 import make_golden as mg  # noqa: E402
 import test_differential_cpu as diff  # noqa: E402
 
-N_SEEDS = 70
+N_SEEDS = 90
 
 
 def main():

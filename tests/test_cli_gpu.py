@@ -117,7 +117,7 @@ def test_scan_many_equals_scan_main_per_motif(in_repo):
 
 
 def test_generated_cases_print_what_the_reference_printed(tmp_path, in_repo):
-    """67 randomly generated CLI runs (all five modes, thresholds from -inf up, zero cells, odd records, shuffled
+    """80-odd randomly generated CLI runs (all modes incl. -t, thresholds from -inf up, zero cells, odd records, shuffled
     PFM headers, --bgonly): inputs are regenerated from their seeds, stdout must equal what the REFERENCE printed
     for them in the build container (tests/golden/fuzz, made by tests/golden/make_golden_fuzz.py)."""
     import warnings

@@ -126,7 +126,21 @@ def draw_inputs(rng, root):
 
 
 def draw_argv(rng, p):
-    mode = str(rng.choice(["rna", "ss", "rnass", "ss_avg", "rnass_avg"]))
+    mode = str(rng.choice(["rna", "ss", "rnass", "ss_avg", "rnass_avg", "testseq_rna", "testseq_ss", "testseq_rnass"],
+                          p=[.2, .15, .15, .15, .2, .05, .05, .05]))
+    if mode.startswith("testseq"):                 # -t: one sequence (and / or structure) on the command line
+        n = int(rng.integers(1, 40))
+        seq = "".join(rng.choice(list("ACGTUacgun"), size=n))
+        st = "".join(rng.choice(list("EHTBLRMe"), size=n))
+        thr = str(rng.choice([" -inf", " -2", "0", "1"]))
+        argv = ["-m", thr, "-C", str(rng.choice(["0", "0.01"]))]
+        if mode == "testseq_rna":
+            argv += ["-p", p["pfm_seq"], "-t", seq]
+        elif mode == "testseq_ss":
+            argv += ["-q", p["pfm_struct"], "-t", st]
+        else:
+            argv += ["-p", p["pfm_seq"], "-q", p["pfm_struct"], "-t", seq + "," + st]
+        return mode, argv, []
     thr = rng.choice([" -inf", " -4", " -1", "0", "0.5", "1.5", "3", "6"])
     argv = ["-m", str(thr), "-C", str(rng.choice(["0", "0.01", "0.5"]))]
     bg = str(rng.choice(["computed", "uniform", "file"]))
@@ -159,7 +173,7 @@ def draw_argv(rng, p):
     return mode, argv, compat
 
 
-@pytest.mark.parametrize("seed", range(70))
+@pytest.mark.parametrize("seed", range(90))
 def test_reference_and_rnascan_b200_print_the_same_bytes(seed, reference, tmp_path, monkeypatch):
     from oracle_backend import install
     rng = np.random.default_rng(9000 + seed)
