@@ -427,10 +427,10 @@ class BackgroundFusedScan(object):
         self.launches = 0
         # Very long streams: the histogram's second read of the symbols (1 of 30 B per position, competing with the scan
         # for HBM) costs more than waiting for the counts until the scan has finished -- the scan kernel then counts
-        # the letters itself (rs_scan_fused_candidates_counting).  Measured cross-over: several 10^8 symbols.
+        # the letters itself (rs_scan_fused_candidates_counting).  Measured: a gain from ~4 * 10^8 symbols on.
         self.count_in_kernel = self.n >= self.COUNT_IN_KERNEL_FROM
 
-    COUNT_IN_KERNEL_FROM = 700_000_000
+    COUNT_IN_KERNEL_FROM = 400_000_000
 
     def launch(self, codes, profile_rows, profile_dtype, W, struct_table, seq_table_fn, threshold,
                absrow_max, all_reduce=None):
