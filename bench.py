@@ -452,6 +452,14 @@ def measure(args, wl, steps, ctx, full, n_target):
                 check(lib.rs_scores_dense_struct(_ptr(codes), n, tq.ctypes.data, W_MOTIF, _ptr(dense_out), sptr))
             launches[0] += 1
 
+    def flush(scrub):
+        # L2 flush between individually timed steps: 512 MB written, then 256 MB of it read back.  The write alone
+        # would leave the 126 MB L2 full of DIRTY lines whose write-back the next step's first kernel pays for
+        # (measured: the histogram's 125 MB read took 36 us behind it instead of 22 us); after the read pass L2 holds
+        # clean lines of unrelated data -- the step starts cold and is billed only its own traffic.
+        scrub.fill_(1)
+        scrub[: 256 << 20].view(torch.int64).sum()
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -485,7 +493,7 @@ def measure(args, wl, steps, ctx, full, n_target):
         scrub = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device)
         pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in pairs:
-            scrub.fill_(1)
+            flush(scrub)
             a.record(stream)
             step()
             b.record(stream)
@@ -517,6 +525,26 @@ def measure(args, wl, steps, ctx, full, n_target):
         raise SystemExit("candidate buffer overflowed: %d > %d" % (int(hb.cand_counters[0].item()), hb.capacity))
     if wl == "c5":
         hits = int(c5_bases[-1].item())
+
+    # ---- optional device timeline of a few more steps (CUPTI through torch.profiler; never part of a bench value)
+    if full and args.trace and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        scrub = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device) if flush_l2 else None
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_run:
+            for _ in range(8):
+                if scrub is not None:
+                    flush(scrub)
+                step()
+            torch.cuda.synchronize()
+        del scrub
+        evs = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof_run.events()
+                      if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+        t_first = evs[0][0] if evs else 0
+        with open(args.trace, "w") as fh:
+            json.dump({"workload": wl, "unit": "us", "note": "kernel / memset / memcpy intervals on the device, 8 steps, "
+                       "CUPTI via torch.profiler; gap_before = idle time since the previous interval ended",
+                       "events": [{"start": a - t_first, "dur": b - a, "gap_before": (a - evs[k - 1][1]) if k else 0.0,
+                                   "name": nm[:90]} for k, (a, b, nm) in enumerate(evs)]}, fh, indent=0)
 
     # ---- sustained: keep stepping for a couple of seconds (power / clock regime of a long job)
     sustained = None
@@ -643,7 +671,7 @@ def measure(args, wl, steps, ctx, full, n_target):
                                   "log-odds table while the counts go to the host, the exact host table decides and scores "
                                   "the candidates (rs_scan_onehot_begin/_finish)" if ohscan is not None else
                                   "computed: histogram -> all-reduce(int64[8]) -> host log-odds, every step"),
-                   "l2_policy": ("L2 flushed between timed steps (512 MB overwrite, untimed); inputs %.2f GB per GPU"
+                   "l2_policy": ("L2 flushed between timed steps (512 MB overwrite, then 256 MB read back so that no dirty lines of the flush remain; untimed); inputs %.2f GB per GPU"
                                  if flush_l2 else "inputs (%.2f GB per GPU) exceed the 126 MB L2") % (input_bytes / 1e9),
                    "parallelism": "shard%d (contiguous record ranges per GPU, no data-path collective)" % world,
                    "untimed_steps_before_the_timed_region": max(args.warmup, 3) + settle},
@@ -845,14 +873,14 @@ def e2e_api(dev, rows_host, lengths, offsets, tq, prof, device, target_rows=32_0
     hp = dev.HostProfile(rows64)
     sep = np.zeros(m, np.uint8)
     sep[offsets[:k] + lengths[:k]] = 0xFF
-    if not hp.make_q8(sep):
+    if not (hp.make_q8(sep) and hp.make_q4(sep)):
         raise RuntimeError("rows do not fit the quantised form")
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     tmp = tempfile.mkdtemp(prefix="rnascan_b200_bench_", dir=base)
     try:
         t0 = time.perf_counter()
         pack.write(tmp, None, rows64, lengths[:k], hp.stats(), hp.q8, hp.q8_scale,
-                   names=["structure.rec%d.txt" % i for i in range(k)])
+                   names=["structure.rec%d.txt" % i for i in range(k)], q4=hp.q4)
         write_s = time.perf_counter() - t0
         del rows64, hp
         alphabet = ContextualSecondaryStructure()
@@ -1033,6 +1061,7 @@ def main():
                     help="fix the per-GPU share instead (weak scaling)")
     ap.add_argument("--sustain-seconds", type=float, default=2.0, dest="sustain_seconds",
                     help="after the K timed steps, keep stepping for this long and report it as `sustained`")
+    ap.add_argument("--trace", default="", help="also write a device timeline of 8 extra steps to this JSON file")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e",
                     help="skip the host-buffer end-to-end leg (e.g. for shards too large to pin on the host)")

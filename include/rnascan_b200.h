@@ -249,13 +249,27 @@ int rs_scan_fused(const uint8_t *d_codes, const void *d_profile, int profile_dty
  *     their exact scores (float32 for alphabet 4, float64 for 7).  A candidate that is not a hit
  *     under the exact table has d_hit_pos = -1 (drop it); d_counters2[0] = entries written,
  *     d_counters2[1] = how many of them are -1 (0 unless a score lies within the margin of the
- *     threshold).  Same d_work / hit_capacity / stream as rs_scan_onehot_begin.               */
+ *     threshold).  Same d_work / hit_capacity / stream as rs_scan_onehot_begin.
+ * rs_scan_onehot_begin_notify : rs_scan_onehot_begin that also TELLS THE HOST the counts, without a
+ *     copy, an event or a stream synchronisation: the first kernel it launches stores
+ *     h_notify8[c] = (tag << 48) | d_counts8[c]  for c = 0..7 into page-locked host memory the device
+ *     can address (cudaHostAlloc; the pointer is used as is, unified addressing).  tag = 1..65535, a
+ *     new value per call; counts are below 2^48.  The host spins until all eight words show the tag
+ *     (the stores are not ordered among themselves), builds its exact table while the scan runs and
+ *     has rs_scan_onehot_finish queued before the scan ends.  d_clear8 (or NULL): eight device
+ *     counters zeroed by the same kernel, e.g. the NEXT call's histogram target (must differ from
+ *     d_counts8).  h_notify8 NULL: no notification (= rs_scan_onehot_begin).                        */
 int rs_provisional_table(const uint64_t *d_counts8, const double *prob, int W, int alphabet,
                          double *d_table_margin /* W*alphabet + 1 doubles */, void *stream);
 int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n,
                          const uint64_t *d_counts8, const double *prob, int W, double threshold,
                          double extra_margin, int64_t hit_capacity, void *d_work,
                          int64_t work_bytes, void *stream);
+int rs_scan_onehot_begin_notify(int alphabet, const uint8_t *d_codes, int64_t n,
+                                const uint64_t *d_counts8, const double *prob, int W,
+                                double threshold, double extra_margin, int64_t hit_capacity,
+                                void *d_work, int64_t work_bytes, uint64_t *h_notify8,
+                                uint32_t tag, uint64_t *d_clear8, void *stream);
 int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64_t n, const double *table,
                           int W, double threshold, int64_t hit_capacity, int64_t *d_hit_pos,
                           void *d_hit_score, uint64_t *d_counters2, void *d_work,

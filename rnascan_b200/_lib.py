@@ -33,6 +33,7 @@ def _load():
 lib = _load()
 
 _i64, _vp, _int, _dbl = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_u32 = ctypes.c_uint32
 _SIGS = {
     "rs_version": ([], _int),
     "rs_last_error": ([], ctypes.c_char_p),
@@ -72,6 +73,8 @@ _SIGS = {
                        _vp, _i64, _vp], _int),
     "rs_provisional_table": ([_vp, _vp, _int, _int, _vp, _vp], _int),
     "rs_scan_onehot_begin": ([_int, _vp, _i64, _vp, _vp, _int, _dbl, _dbl, _i64, _vp, _i64, _vp], _int),
+    "rs_scan_onehot_begin_notify": ([_int, _vp, _i64, _vp, _vp, _int, _dbl, _dbl, _i64, _vp, _i64, _vp, _u32, _vp,
+                                     _vp], _int),
     "rs_scan_onehot_finish": ([_int, _vp, _i64, _vp, _int, _dbl, _i64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_refine_hits_seq": ([_vp, _i64, _vp, _int, _dbl, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "rs_scan_fused_candidates": ([_vp, _vp, _int, _i64, _vp, _int, _dbl, _dbl, _i64, _vp, _vp, _i64, _vp, _vp], _int),

@@ -61,9 +61,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// bit r of lut[idx] = window of W symbols starting at symbol r of the 8-mer `idx` is a hit
-__global__ void kmer_lut_kernel(uint8_t *__restrict__ lut, const KmerTable tab, int W, double threshold)
+// zero the finish kernel's ticket + aggregates from a kernel that runs before it anyway (saves a memset node)
+__device__ __forceinline__ void zero_words(unsigned long long *w, int n_words)
 {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_words; k += gridDim.x * blockDim.x) w[k] = 0ull;
+}
+
+// bit r of lut[idx] = window of W symbols starting at symbol r of the 8-mer `idx` is a hit
+__global__ void kmer_lut_kernel(uint8_t *__restrict__ lut, const KmerTable tab, int W, double threshold,
+                                unsigned long long *zero, int n_zero)
+{
+    zero_words(zero, n_zero);
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int Q = 9 - W;
     unsigned bits = 0;
@@ -79,10 +87,39 @@ __global__ void kmer_lut_kernel(uint8_t *__restrict__ lut, const KmerTable tab, 
 // Same from a PROVISIONAL table (provisional.cuh) that every CTA derives from the device-resident counts.
 // float casts are monotone, so every window the exact table would report has
 // (float)(s + margin) > threshold here: the bits are a superset.
+// Host notification (rs_scan_onehot_begin_notify): the counts go straight into page-locked host memory -- no copy
+// engine, no event, no stream synchronisation between the histogram and the host's exact table.  Every word carries
+// the call's 16-bit tag above the 48-bit count, so the eight stores need no ordering among themselves (no system-wide
+// fence on the device): the host waits until all eight words show the tag.  clear8: another 8-counter array zeroed
+// here (the NEXT step's histogram target).
+struct CountsNotify {
+    unsigned long long *host8;      // NULL: no notification
+    unsigned long long tag;         // 1 .. 65535
+    unsigned long long *clear8;     // or NULL
+};
+
+__device__ __forceinline__ void counts_notify(const unsigned long long *__restrict__ counts8, const CountsNotify &nt)
+{
+    if (threadIdx.x < 8) {
+        if (nt.clear8) nt.clear8[threadIdx.x] = 0ull;
+        if (nt.host8)
+            *(volatile unsigned long long *)(nt.host8 + threadIdx.x) =
+                (nt.tag << 48) | (counts8[threadIdx.x] & 0xFFFFFFFFFFFFull);
+    }
+}
+
+__global__ void counts_notify_kernel(const unsigned long long *__restrict__ counts8, const CountsNotify nt)
+{
+    counts_notify(counts8, nt);
+}
+
 __global__ void kmer_lut_dev_kernel(uint8_t *__restrict__ lut, const unsigned long long *__restrict__ counts8,
-                                    const __grid_constant__ ProvProb prob, double threshold, double extra_margin)
+                                    const __grid_constant__ ProvProb prob, double threshold, double extra_margin,
+                                    const CountsNotify nt, unsigned long long *zero, int n_zero)
 {
     __shared__ double tab[RS_PROV_MAX_W * 4];
+    if (blockIdx.x == 0) counts_notify(counts8, nt);
+    zero_words(zero, n_zero);
     const int W = prob.W;
     const double margin = rs_prov_table_cta<4>(counts8, prob, tab) + extra_margin;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,6 +316,9 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
     unsigned long long total;
     const unsigned long long excl = fin_block_scan(segcnt, total);
     if (threadIdx.x == 0) {
+        // counters[1] (candidates the exact table rejects) is zeroed HERE, by the first CTA, before its aggregate is
+        // published: every other CTA reads that aggregate in its look-back before it scores anything
+        if (vb == 0) prm.counters[1] = 0ull;
         __threadfence();
         ((volatile unsigned long long *)prm.wk.agg)[vb] = total + 1ull;
     }
@@ -293,6 +333,7 @@ __global__ void __launch_bounds__(FIN_THREADS) kmer_finish_kernel(const __grid_c
         }
         part += v - 1ull;
     }
+    __threadfence();
     unsigned long long before;
     fin_block_scan(part, before);
     if (vb == (unsigned)(prm.n_ctas - 1) && threadIdx.x == 0) {
@@ -658,12 +699,12 @@ static OneHotGeom onehot_geom(int A, int W, int64_t n)
 template <int A>
 static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, const uint64_t *d_counts8,
                         const double *prob, double extra_margin, int W, double threshold, uint8_t *wk_lut,
-                        cudaStream_t st)
+                        cudaStream_t st, CountsNotify nt = CountsNotify())
 {
     const OneHotGeom g = onehot_geom(A, W, n);
     KmerWork wk;
     carve_work(wk_lut, g.n_masks, g.n_segs, g.n_ctas, wk);
-    RS_CUDA(fin_arm(wk, g.n_ctas, st));
+    if (!g.kmer) RS_CUDA(fin_arm(wk, g.n_ctas, st));     // k-mer path: the table kernel zeroes ticket + aggregates
     ProvProb pp = {};
     if (d_counts8) {
         pp.W = W; pp.A = A;
@@ -674,11 +715,12 @@ static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, 
         prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.n_tiles = g.n_tiles; prm.wk = wk;
         if (d_counts8) {
             kmer_lut_dev_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, (const unsigned long long *)d_counts8, pp,
-                                                                    threshold, extra_margin);
+                                                                    threshold, extra_margin, nt, wk.ticket,
+                                                                    2 + g.n_ctas);
         } else {
             KmerTable kt = {};
             for (int k = 0; k < W * 4; k++) kt.t[k] = table[k];
-            kmer_lut_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, kt, W, threshold);
+            kmer_lut_kernel<<<KM_LUT_BYTES / 256, 256, 0, st>>>(wk.lut, kt, W, threshold, wk.ticket, 2 + g.n_ctas);
         }
         RS_CUDA(cudaGetLastError());
         switch (W) {
@@ -692,6 +734,10 @@ static int onehot_begin(const uint8_t *d_codes, int64_t n, const double *table, 
         case 8: return launch_kmer<8>(prm, st);
         default: rs_set_error("internal: k-mer scan needs W <= 8"); return RS_ERR_INVALID;
         }
+    }
+    if (d_counts8 && (nt.host8 || nt.clear8)) {
+        counts_notify_kernel<<<1, 32, 0, st>>>((const unsigned long long *)d_counts8, nt);
+        RS_CUDA(cudaGetLastError());
     }
     MaskScanParams prm = {};
     prm.codes = d_codes; prm.n = n; prm.padded = rs_padded_count(n); prm.threshold = threshold;
@@ -746,20 +792,40 @@ static int begin_finish_args(int alphabet, const uint8_t *d_codes, int64_t n, in
     return RS_OK;
 }
 
-extern "C" int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n, const uint64_t *d_counts8,
-                                    const double *prob, int W, double threshold, double extra_margin,
-                                    int64_t hit_capacity, void *d_work, int64_t work_bytes, void *stream)
+extern "C" int rs_scan_onehot_begin_notify(int alphabet, const uint8_t *d_codes, int64_t n, const uint64_t *d_counts8,
+                                           const double *prob, int W, double threshold, double extra_margin,
+                                           int64_t hit_capacity, void *d_work, int64_t work_bytes,
+                                           uint64_t *h_notify8, uint32_t tag, uint64_t *d_clear8, void *stream)
 {
     int rc = begin_finish_args(alphabet, d_codes, n, W, threshold);
     if (rc) return rc;
     if (!d_counts8 || !prob) { rs_set_error("null counts or probabilities"); return RS_ERR_INVALID; }
     if (!(extra_margin >= 0)) { rs_set_error("extra_margin must be >= 0"); return RS_ERR_INVALID; }
-    if (n < W) return RS_OK;
+    if (d_clear8 == d_counts8) { rs_set_error("d_clear8 must not be the counts being read"); return RS_ERR_INVALID; }
+    if (h_notify8 && (tag < 1 || tag > 65535)) { rs_set_error("notification tag must be 1..65535"); return RS_ERR_INVALID; }
+    CountsNotify nt;
+    nt.host8 = (unsigned long long *)h_notify8; nt.tag = tag; nt.clear8 = (unsigned long long *)d_clear8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < W) {                                        // nothing to scan: the host is still told the counts
+        if (nt.host8 || nt.clear8) {
+            counts_notify_kernel<<<1, 32, 0, st>>>((const unsigned long long *)d_counts8, nt);
+            RS_CUDA(cudaGetLastError());
+        }
+        return RS_OK;
+    }
     WorkLayout wl = rs_work_layout(n, hit_capacity);
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
     uint8_t *wk = (uint8_t *)d_work + wl.off_lut;
-    return alphabet == 4 ? onehot_begin<4>(d_codes, n, nullptr, d_counts8, prob, extra_margin, W, threshold, wk, (cudaStream_t)stream)
-                         : onehot_begin<7>(d_codes, n, nullptr, d_counts8, prob, extra_margin, W, threshold, wk, (cudaStream_t)stream);
+    return alphabet == 4 ? onehot_begin<4>(d_codes, n, nullptr, d_counts8, prob, extra_margin, W, threshold, wk, st, nt)
+                         : onehot_begin<7>(d_codes, n, nullptr, d_counts8, prob, extra_margin, W, threshold, wk, st, nt);
+}
+
+extern "C" int rs_scan_onehot_begin(int alphabet, const uint8_t *d_codes, int64_t n, const uint64_t *d_counts8,
+                                    const double *prob, int W, double threshold, double extra_margin,
+                                    int64_t hit_capacity, void *d_work, int64_t work_bytes, void *stream)
+{
+    return rs_scan_onehot_begin_notify(alphabet, d_codes, n, d_counts8, prob, W, threshold, extra_margin, hit_capacity,
+                                       d_work, work_bytes, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64_t n, const double *table, int W,
@@ -772,8 +838,10 @@ extern "C" int rs_scan_onehot_finish(int alphabet, const uint8_t *d_codes, int64
     if (!table || !d_counters2 || hit_capacity < 0 || (hit_capacity > 0 && (!d_hit_pos || !d_hit_score))) {
         rs_set_error("rs_scan_onehot_finish: bad argument"); return RS_ERR_INVALID;
     }
-    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
-    if (n < W) return RS_OK;
+    if (n < W) {                                        // else: the finish kernel writes both counters itself
+        RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+        return RS_OK;
+    }
     WorkLayout wl = rs_work_layout(n, hit_capacity);
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }
     uint8_t *wk = (uint8_t *)d_work + wl.off_lut;

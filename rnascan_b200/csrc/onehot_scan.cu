@@ -411,7 +411,8 @@ static int scan_impl(const uint8_t *ca, const uint8_t *cb, int64_t n, const doub
         rs_set_error("missing score buffer"); return RS_ERR_INVALID;
     }
     if (threshold != threshold) { rs_set_error("threshold is NaN"); return RS_ERR_INVALID; }
-    RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
+    // W <= 16 goes through kmer_finish_kernel, which writes both counters itself (one memset node fewer)
+    if (n < W || W > 16) RS_CUDA(cudaMemsetAsync(d_counters2, 0, 2 * sizeof(uint64_t), st));
     if (n < W) return RS_OK;
     WorkLayout wl = rs_work_layout(n, cap);
     if (!d_work || work_bytes < wl.total) { rs_set_error("workspace too small: need %lld bytes", (long long)wl.total); return RS_ERR_WORKSPACE; }

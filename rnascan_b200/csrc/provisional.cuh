@@ -31,17 +31,24 @@ __device__ __forceinline__ double rs_prov_table_cta(const unsigned long long *__
         for (int c = 0; c < A; c++) s_bg[c] = bg[c] / norm;                      // Biopython renormalises
     }
     __syncthreads();
+    // one (row, column) entry per thread: the double-precision log2 is a long dependent chain, W * A of them
+    // side by side instead of A in a row per thread
+    for (int e = threadIdx.x; e < W * TS; e += blockDim.x) {
+        const int j = e / TS, c = e - j * TS;
+        double v = 0.0;
+        if (c < A) {
+            const double p = prm.p[j * A + c], b = s_bg[c];
+            if (b > 0) v = p > 0 ? log2(p / b) : -INFINITY;                      // p <= 0 / NaN: as motifs.log_odds
+            else       v = p > 0 ? INFINITY : nan("");
+        }
+        tab[e] = v;
+    }
+    __syncthreads();
     for (int j = threadIdx.x; j < W; j += blockDim.x) {
         double rowmax = 0.0;
-        for (int c = 0; c < TS; c++) {
-            double v = 0.0;
-            if (c < A) {
-                const double p = prm.p[j * A + c], b = s_bg[c];
-                if (b > 0) v = p > 0 ? log2(p / b) : -INFINITY;                  // p <= 0 / NaN: as motifs.log_odds
-                else       v = p > 0 ? INFINITY : nan("");
-                if (isfinite(v)) rowmax = fmax(rowmax, fabs(v));
-            }
-            tab[j * TS + c] = v;
+        for (int c = 0; c < A; c++) {
+            const double v = tab[j * TS + c];
+            if (isfinite(v)) rowmax = fmax(rowmax, fabs(v));
         }
         s_rowmax[j] = rowmax;
     }

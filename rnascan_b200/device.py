@@ -13,6 +13,7 @@ Layout in HBM:
 """
 import ctypes
 import os
+import time
 
 import numpy as np
 import torch
@@ -555,8 +556,12 @@ class BackgroundOneHotScan(object):
         self.A = 4 if kind == "rna" else 7
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
         self.counts = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.counts_next = torch.zeros(8, dtype=torch.int64, device=self.device)   # unsharded: zeroed by the device
         self.counts_global = torch.zeros(8, dtype=torch.int64, device=self.device)
         self.counts_host = torch.zeros(16, dtype=torch.int64).pin_memory()      # [0:8] global, [8:16] this shard
+        self.note = torch.zeros(8, dtype=torch.int64).pin_memory()    # written by the device: (tag << 48) | count
+        self.epoch = 0
+        self._clean = True                                   # self.counts holds zeros
         self.counted = torch.cuda.Event()
         self.rescanned = False
         self.ready = torch.cuda.Event()
@@ -571,7 +576,10 @@ class BackgroundOneHotScan(object):
         prob = _table(prob, A)
         W = prob.shape[0]
         main = torch.cuda.current_stream(self.device)
+        if all_reduce is None:
+            return self._launch_unsharded(codes, prob, table_fn, threshold, extra_margin, main)
         self.counts.zero_()
+        self._clean = False
         check((lib.rs_hist_rna if A == 4 else lib.rs_hist)(_ptr(codes), n, _ptr(self.counts), main.cuda_stream))
         self.counted.record(main)
         # Sharded runs: the decision pass starts from THIS shard's counts with `shard_margin` of extra slack
@@ -612,6 +620,49 @@ class BackgroundOneHotScan(object):
                                         _ptr(hb.pos), _ptr(hb.seq if A == 4 else hb.struct), _ptr(hb.counters),
                                         _ptr(hb.work), hb.work_bytes, main.cuda_stream))
         main.wait_stream(self.side)
+        return table
+
+    NOTIFY_TIMEOUT_S = 20.0
+
+    def _launch_unsharded(self, codes, prob, table_fn, threshold, extra_margin, main):
+        """One device, no collective: no side stream, no copy, no event.  The first kernel of the decision pass
+        stores the counts, tagged with this launch's number, into the pinned host buffer
+        (rs_scan_onehot_begin_notify); the host spins until all eight words carry the tag, builds the exact table while the scan runs and queues the finish behind it.  The same
+        kernel zeroes the OTHER counter array, the next launch's histogram target."""
+        n, hb, A = self.n, self.hb, self.A
+        W = prob.shape[0]
+        sptr = main.cuda_stream
+        if not self._clean:
+            self.counts.zero_()
+        self._clean = False                                  # until the device has zeroed the next target
+        check((lib.rs_hist_rna if A == 4 else lib.rs_hist)(_ptr(codes), n, _ptr(self.counts), sptr))
+        self.epoch = self.epoch % 65535 + 1                  # 1..65535; the buffer starts as zeros
+        ch, note = self.counts_host.numpy(), self.note.numpy().view(np.uint64)
+        check(lib.rs_scan_onehot_begin_notify(A, _ptr(codes), n, _ptr(self.counts), prob.ctypes.data, W,
+                                              float(threshold), float(extra_margin), hb.capacity, _ptr(hb.work),
+                                              hb.work_bytes, self.note.data_ptr(), self.epoch,
+                                              _ptr(self.counts_next), sptr))
+        self.counts, self.counts_next = self.counts_next, self.counts
+        self._clean = True
+        tag, spins, t0 = np.uint64(self.epoch), 0, None
+        shift = np.uint64(48)
+        while not ((note >> shift) == tag).all():
+            spins += 1
+            if spins & 0x3FF == 0:                           # every 1024 polls: look at the clock
+                now = time.perf_counter()
+                t0 = t0 or now
+                if now - t0 > self.NOTIFY_TIMEOUT_S:
+                    torch.cuda.synchronize(self.device)      # surfaces a device error if that is the cause
+                    raise RuntimeError("the device never reported the background counts")
+        ch[:8] = (note & np.uint64((1 << 48) - 1)).astype(np.int64)
+        ch[8:] = ch[:8]
+        table = _table(table_fn(ch[:8]), A)
+        if table.shape[0] != W:
+            raise ValueError("table_fn returned a table of another width")
+        self.rescanned = False
+        check(lib.rs_scan_onehot_finish(A, _ptr(codes), n, table.ctypes.data, W, float(threshold), hb.capacity,
+                                        _ptr(hb.pos), _ptr(hb.seq if A == 4 else hb.struct), _ptr(hb.counters),
+                                        _ptr(hb.work), hb.work_bytes, sptr))
         return table
 
     def results(self):
@@ -855,7 +906,7 @@ class HostProfile(object):
     when they are float32, their float32 shadow when they are float64, or the 8-byte quantised form
     `q8` (n, 8) uint8 with `q8_scale` when one is supplied (profile packs) or built with make_q8()."""
 
-    def __init__(self, rows, q8=None, q8_scale=None, stats=None):
+    def __init__(self, rows, q8=None, q8_scale=None, stats=None, q4=None):
         if rows.dtype not in (np.float32, np.float64):
             rows = np.ascontiguousarray(rows, dtype=np.float64)
         if rows.ndim != 2 or rows.shape[1] != len(CHANNELS):
@@ -866,7 +917,7 @@ class HostProfile(object):
         self.n = int(rows.shape[0])
         self.dtype = _lib.RS_F32 if rows.dtype == np.float32 else _lib.RS_F64
         self.q8, self.q8_scale = q8, q8_scale
-        self.q4 = None                               # (n, 4) uint8 view of the 4-byte quantised rows (make_q4)
+        self.q4 = q4                                 # (n, 4) uint8 view of the 4-byte quantised rows (make_q4)
         self._stats = None if stats is None else tuple(float(v) for v in stats)
 
     def stats(self):
@@ -1196,9 +1247,16 @@ def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, 
         out = scan_fused(stream, profile, seq, tq, threshold)
         return out + (None,) if return_scanner else out
     if form is None:
-        form = "q8" if hp.q8 is not None else ("f32" if hp.dtype == _lib.RS_F32 else "shadow")
+        # the smallest form whose guard band leaves the threshold selective: 4 bytes per position when its band is
+        # at most 0.4 of a positive threshold, else 8 bytes; rows without a quantised form go as float32
+        if hp.q4 is not None and threshold > 0 and q4_guard(tq, hp.q8_scale) <= 0.4 * threshold:
+            form = "q4"
+        elif hp.q8 is not None:
+            form = "q8"
+        else:
+            form = "f32" if hp.dtype == _lib.RS_F32 else "shadow"
     sc = HostProfileScanner(n, W, form, chunk_rows=min(int(chunk_rows), max(n, 256)))
-    src = hp.q8 if form == "q8" else hp.rows
+    src = {"q8": hp.q8, "q4": hp.q4}.get(form, hp.rows)
     out = sc.run(codes, src, hp.rows, tq, seq, threshold, hp.absrow_max(),
-                 q8_scale=hp.q8_scale if form == "q8" else 1.0, all_reduce=all_reduce)
+                 q8_scale=hp.q8_scale if form in ("q8", "q4") else 1.0, all_reduce=all_reduce)
     return out + (sc,) if return_scanner else out

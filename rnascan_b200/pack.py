@@ -9,10 +9,12 @@ and later scans map it instead of parsing:
     bytes 8..15   little-endian uint64: length H of the JSON header that follows
     JSON header   {"version", "n_rows", "files": [[basename, size, mtime_ns, rows, row_offset], ...],
                    "stats": [max_abs_row_sum, n_nonfinite, n_negative, max_abs_value],
-                   "q8_scale": float | null, "off_q8", "off_rows"}
+                   "q8_scale": float | null, "off_q8", "off_q4", "off_rows"}
     off_q8        uint8  [n_rows][8]   quantised filter rows (include/rnascan_b200.h, RS_ROWS_Q8); byte 7 is
                                        0, or 0xFF on the separator row that follows every profile; absent
                                        (q8_scale null) when the rows do not fit the form
+    off_q4        uint8  [n_rows][4]   the 4-byte form (RS_ROWS_Q4: floored 4-bit channels, top nibble 0 or 0xF),
+                                       used when its wider guard band still leaves the threshold selective
     off_rows      float64[n_rows][7]   the exact rows, bit-identical to what pandas parses, B,E,H,L,M,R,T
 
 Both sections start at multiples of 4096 and are read through ``numpy.memmap``: a scan copies all of the
@@ -29,13 +31,13 @@ import numpy as np
 MAGIC = b"RSB200P1"
 NAME = "rnascan_b200.pack"
 ALIGN = 4096
-VERSION = 1
+VERSION = 2
 
 
 class ProfilePack(object):
-    def __init__(self, path, header, q8, rows):
+    def __init__(self, path, header, q8, rows, q4=None):
         self.path, self.header = path, header
-        self.q8, self.rows = q8, rows
+        self.q8, self.q4, self.rows = q8, q4, rows
         files = header["files"]
         self.names = [f[0] for f in files]
         self.lengths = np.array([f[3] for f in files], np.int64)
@@ -64,7 +66,7 @@ def _file_entries(files, lengths, offsets):
     return out
 
 
-def write(directory, files, packed_rows, lengths, stats, q8=None, q8_scale=None, names=None):
+def write(directory, files, packed_rows, lengths, stats, q8=None, q8_scale=None, names=None, q4=None):
     """Write the pack of `files` (paths, in scan order; or `names` alone for a pack that stands for the
     text files) whose rows are `packed_rows` (sum L + len(files), 7) float64 with a zero separator row
     after each profile.  Written to a temporary name and renamed, so readers never see a partial pack."""
@@ -78,15 +80,19 @@ def write(directory, files, packed_rows, lengths, stats, q8=None, q8_scale=None,
     else:
         entries = _file_entries(files, lengths, offsets)
     header = {"version": VERSION, "n_rows": n_rows, "files": entries, "stats": [float(v) for v in stats],
-              "q8_scale": None if q8 is None else float(q8_scale), "off_q8": 0, "off_rows": 0}
+              "q8_scale": None if q8 is None else float(q8_scale), "off_q8": 0, "off_q4": 0, "off_rows": 0}
+    if q8 is None:
+        q4 = None
     # two passes: the offsets are part of the header whose length they depend on
     for _ in range(3):
         blob = json.dumps(header).encode("utf-8")
         off_q8 = _roundup(16 + len(blob))
-        off_rows = _roundup(off_q8 + (n_rows * 8 if q8 is not None else 0))
-        if header["off_q8"] == off_q8 and header["off_rows"] == off_rows:
+        off_q4 = _roundup(off_q8 + (n_rows * 8 if q8 is not None else 0))
+        off_rows = _roundup(off_q4 + (n_rows * 4 if q4 is not None else 0))
+        if header["off_q8"] == off_q8 and header["off_rows"] == off_rows and header["off_q4"] == (off_q4 if q4 is not None else 0):
             break
         header["off_q8"], header["off_rows"] = off_q8, off_rows
+        header["off_q4"] = off_q4 if q4 is not None else 0
     blob = json.dumps(header).encode("utf-8")
     path = pack_path(directory)
     tmp = path + ".tmp.%d" % os.getpid()
@@ -97,6 +103,9 @@ def write(directory, files, packed_rows, lengths, stats, q8=None, q8_scale=None,
         if q8 is not None:
             fh.seek(header["off_q8"])
             np.ascontiguousarray(q8, np.uint8).tofile(fh)
+        if q4 is not None:
+            fh.seek(header["off_q4"])
+            np.ascontiguousarray(q4, np.uint8).tofile(fh)
         fh.seek(header["off_rows"])
         np.ascontiguousarray(packed_rows, np.float64).tofile(fh)
     os.replace(tmp, path)
@@ -125,7 +134,10 @@ def read(directory):
         q8 = None
         if header.get("q8_scale") is not None and n_rows:
             q8 = np.memmap(path, dtype=np.uint8, mode="r", offset=header["off_q8"], shape=(n_rows, 8))
-        return ProfilePack(path, header, q8, rows)
+        q4 = None
+        if q8 is not None and header.get("off_q4"):
+            q4 = np.memmap(path, dtype=np.uint8, mode="r", offset=header["off_q4"], shape=(n_rows, 4))
+        return ProfilePack(path, header, q8, rows, q4)
     except (OSError, ValueError, KeyError, struct.error):
         return None
 

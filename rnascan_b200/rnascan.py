@@ -1100,16 +1100,17 @@ def _load_profile_dir(directory, write_pack=False):
         r0 = int(pk.offsets[lo]) if hi > lo else 0
         r1 = int(pk.offsets[hi - 1] + pk.lengths[hi - 1] + 1) if hi > lo else 0
         hp = device.HostProfile(pk.rows[r0:r1], q8=None if pk.q8 is None else pk.q8[r0:r1], q8_scale=pk.q8_scale,
-                                stats=pk.stats)
+                                stats=pk.stats, q4=None if pk.q4 is None else pk.q4[r0:r1])
         return files[lo:hi], files, hp, lengths
     packed, lengths = _read_profiles_packed(files[lo:hi])
     hp = device.HostProfile(packed)
     if write_pack and size == 1 and n_files:
         sep = np.zeros(packed.shape[0], np.uint8)
         sep[np.cumsum(lengths + 1) - 1] = device._lib.RS_SEP
-        ok = hp.make_q8(sep)
+        ok = hp.make_q8(sep) and hp.make_q4(sep)
         try:
-            pack.write(directory, files, packed, lengths, hp.stats(), hp.q8 if ok else None, hp.q8_scale)
+            pack.write(directory, files, packed, lengths, hp.stats(), hp.q8 if ok else None, hp.q8_scale,
+                       q4=hp.q4 if ok else None)
         except OSError as exc:
             eprint("Could not write %s: %s" % (pack.pack_path(directory), exc))
     return files[lo:hi], files, hp, lengths
@@ -1158,6 +1159,10 @@ def _profile_dir_streams(directory, debug, seq_batches, write_pack):
         q8 = np.array(hp.q8)                          # the pack's rows carry no sequence: add the symbols
         q8[:, 7] = codes
         hp.q8 = q8
+        if hp.q4 is not None:
+            q4 = np.array(hp.q4)
+            q4[:, 3] = (q4[:, 3] & 0x0F) | ((codes & 0x0F) << 4)
+            hp.q4 = q4
     all_names = list(all_files) if debug else [path[cut:-4] for path in all_files]
     out = (files, all_names, hp, lengths, names, offsets, codes)
     if _PROFILE_DIR_CACHE_ON[0]:

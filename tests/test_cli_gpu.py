@@ -240,6 +240,41 @@ def _pack_case(tmp_path, mode):
     assert code == 0 and alone == plain
 
 
+def test_pack_scan_picks_the_smallest_filter_form_the_threshold_allows(tmp_path, in_repo):
+    """A pack holds the 8-byte and the 4-byte filter rows.  The 4-byte form goes to the device when its guard band
+    is at most 0.4 of a positive threshold, the 8-byte form otherwise; the output does not depend on the choice."""
+    import shutil
+    from rnascan_b200 import pack
+    work = tmp_path / "profiles"
+    shutil.copytree(os.path.join(INP, "profiles_mixed"), work)
+    # a motif close to the background: few, small positive log-odds, so the 4-bit form's band (scale / 15 times the
+    # sum of the positive entries, about 0.1 here) is well below 0.4 x 0.3
+    import ast
+    bg = ast.literal_eval(open(os.path.join(INP, "bg_struct_example.txt")).read())
+    pfm = tmp_path / "near_bg.txt"
+    with open(pfm, "w") as fh:
+        fh.write("PO\t" + "\t".join("BEHLMRT") + "\n")
+        for w, up in enumerate(("E", "H", "L")):
+            row = {c: bg[c] * (1.12 if c == up else 1.0) for c in "BEHLMRT"}
+            tot = sum(row.values())
+            fh.write("%d\t%s\n" % (w, "\t".join(repr(row[c] / tot) for c in "BEHLMRT")))
+    base = ["-q", str(pfm), "-B", os.path.join(INP, "bg_struct_example.txt"), "-C", "0"]
+    forms = {}
+    for thr in (" -3", "0.1", "0.3"):
+        argv = base + ["-m", thr, str(work)]
+        plain = run_cli(argv)[0]
+        run_cli(argv + ["--pack"])
+        pk = pack.read(str(work))
+        assert pk.q4 is not None and pk.q4.shape == (pk.q8.shape[0], 4)
+        stats = tmp_path / "stats.json"
+        mapped = run_cli(argv + ["--stats", str(stats)])[0]
+        assert mapped == plain
+        st = json.loads(stats.read_text().splitlines()[-1])
+        assert st["profile_source"] == "pack"
+        forms[thr] = st["profile_filter_form"]
+    assert forms[" -3"] == "q8" and forms["0.3"] == "q4", forms
+
+
 def test_stats_option_writes_one_json_line(tmp_path, in_repo):
     """--stats FILE: phases, sizes and throughput of the run as one JSON line; stdout is unchanged."""
     base = CASES["rna_mixed_all"]["argv"]

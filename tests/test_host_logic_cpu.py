@@ -172,6 +172,34 @@ ms.main(%(argv)r)
 """
 
 
+def test_pack_round_trips_both_quantised_forms(tmp_path):
+    """rnascan_b200.pack version 2: float64 rows, the 8-byte and the 4-byte filter rows, all page aligned and
+    mapped back bit for bit; a pack of another version reads as absent (the text is parsed again)."""
+    from rnascan_b200 import pack
+    rng = np.random.default_rng(5)
+    lengths = np.array([5, 1, 9], np.int64)
+    n = int((lengths + 1).sum())
+    rows = rng.random((n, 7))
+    q8 = rng.integers(0, 256, (n, 8), dtype=np.uint8)
+    q4 = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+    d = tmp_path / "p"
+    d.mkdir()
+    names = ["structure.r%d.txt" % i for i in range(3)]
+    pack.write(str(d), None, rows, lengths, (1.0, 0, 0, 1.0), q8, 0.5, names=names, q4=q4)
+    pk = pack.read(str(d))
+    assert pk.header["version"] == 2 and pk.q8_scale == 0.5
+    for off in ("off_q8", "off_q4", "off_rows"):
+        assert pk.header[off] % 4096 == 0 and pk.header[off] > 0
+    assert np.array_equal(pk.rows, rows) and np.array_equal(pk.q8, q8) and np.array_equal(pk.q4, q4)
+    pack.write(str(d), None, rows, lengths, (1.0, 0, 0, 1.0), None, None, names=names, q4=q4)
+    pk = pack.read(str(d))
+    assert pk.q8 is None and pk.q4 is None and np.array_equal(pk.rows, rows)
+    raw = bytearray(open(pack.pack_path(str(d)), "rb").read())
+    raw[:8] = b"RSB200P0"
+    open(pack.pack_path(str(d)), "wb").write(bytes(raw))
+    assert pack.read(str(d)) is None
+
+
 def test_native_library_output_stays_out_of_hits_tab_under_torchrun(tmp_path):
     """NCCL prints its version banner on file descriptor 1 while the process group comes up; under torchrun
     the CLI points fd 1 at stderr for the run and writes hits.tab to a private duplicate of the real stdout

@@ -444,6 +444,50 @@ def test_scan_onehot_bg_sharded_starts_from_local_counts(dev, oracle, other, exp
     assert_same_float(sc, want[wpos])
 
 
+@pytest.mark.parametrize("kind,W", [("rna", 7), ("rna", 11), ("struct", 5)])
+def test_onehot_counts_reach_the_host_without_a_copy(dev, oracle, kind, W):
+    """One device: the decision pass's first kernel stores the counts into pinned host memory and zeroes the next
+    launch's counters (rs_scan_onehot_begin_notify).  Launch after launch -- and mixed with the sharded form on the
+    same object -- the counts the host sees are those of the data, never an accumulation; shorter-than-motif input
+    still reports its counts."""
+    from rnascan_b200 import synth
+    from rnascan_b200.device import lib, _ptr
+    A = 4 if kind == "rna" else 7
+    st0, codes, lengths = make_stream(dev, 300_000, 200, seed=620 + W, kind=kind)
+    st = dev.SymbolStream(codes, st0.offsets, lengths, kind=kind)
+    pfm = synth.pfm_rows(W, A, np.random.default_rng(621)) + 0.01
+    prob = pfm / pfm.sum(axis=1, keepdims=True)
+    fn = _bg_table_fn(prob, A)
+    local = np.array([(codes == k).sum() for k in range(8)], np.int64)
+    local[A:] = 0
+    table = fn(local)
+    if kind == "rna":
+        want = oracle.seq_scores(synth.to_text(codes, "rna"), table)
+    else:
+        want = oracle.alpha_scores(synth.to_text(codes, "struct"), table, "BEHLMRT")
+    wpos = oracle.search_hits(want, 1.0)
+    job = dev.BackgroundOneHotScan(st.n, kind, st.codes.device, capacity=st.n)
+    for sharded in (False, False, True, False, False):
+        job.launch(st.codes, prob, fn, 1.0, all_reduce=(lambda t: t) if sharded else None)
+        pos, sc, _ = job.results()
+        assert np.array_equal(job.counts_host.numpy()[:8], local), sharded
+        assert np.array_equal(pos, wpos)
+        assert_same_float(sc, want[wpos])
+    # n < W: nothing is scanned, the host is still told
+    note = torch.zeros(8, dtype=torch.int64).pin_memory()
+    cdev = torch.tensor([5, 6, 7, 8, 0, 0, 0, 0], dtype=torch.int64, device="cuda")
+    clear = torch.ones(8, dtype=torch.int64, device="cuda")
+    short = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    assert lib.rs_scan_onehot_begin_notify(A, _ptr(short), W - 1, _ptr(cdev), np.ascontiguousarray(prob).ctypes.data,
+                                           W, 1.0, 0.0, 16, None, 0, note.data_ptr(), 41, _ptr(clear), 0) == 0
+    torch.cuda.synchronize()
+    assert note.tolist() == [(41 << 48) | v for v in (5, 6, 7, 8, 0, 0, 0, 0)] and clear.sum().item() == 0
+    assert lib.rs_scan_onehot_begin_notify(A, _ptr(short), 200, _ptr(cdev), np.ascontiguousarray(prob).ctypes.data,
+                                           W, 1.0, 0.0, 16, None, 0, note.data_ptr(), 42, _ptr(cdev), 0) != 0
+    assert lib.rs_scan_onehot_begin_notify(A, _ptr(short), 200, _ptr(cdev), np.ascontiguousarray(prob).ctypes.data,
+                                           W, 1.0, 0.0, 16, None, 0, note.data_ptr(), 65536, _ptr(clear), 0) != 0
+
+
 def test_scan_onehot_begin_rejects_wide_motifs(dev):
     st = dev.SymbolStream(np.zeros(5000, np.uint8), kind="rna")
     with pytest.raises(ValueError):

@@ -15,9 +15,9 @@ rows = rng.dirichlet(0.3 * np.ones(7), size=total)
 rows[off + lengths] = 0.0
 hp = dev.HostProfile(rows)
 sep = np.zeros(total, np.uint8); sep[off + lengths] = 0xFF
-assert hp.make_q8(sep)
+assert hp.make_q8(sep) and hp.make_q4(sep)
 tmp = tempfile.mkdtemp(prefix="apiprof_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-pack.write(tmp, None, rows, lengths, hp.stats(), hp.q8, hp.q8_scale, names=["structure.rec%d.txt" % i for i in range(len(lengths))])
+pack.write(tmp, None, rows, lengths, hp.stats(), hp.q8, hp.q8_scale, q4=hp.q4, names=["structure.rec%d.txt" % i for i in range(len(lengths))])
 tq = synth.pssm_table(synth.pfm_rows(7, 7, np.random.default_rng(103)), background=[synth.SS_P[c] for c in "BEHLMRT"])
 alphabet = ContextualSecondaryStructure()
 pssm = {"m": matrix.ExtendedPositionSpecificScoringMatrix(alphabet, {l: tq[:, "BEHLMRT".index(l)].tolist() for l in alphabet.letters})}

@@ -39,8 +39,8 @@ def main(out, n_fasta, n_rows):
     hp = dev.HostProfile(rows)
     sep = np.zeros(m, np.uint8)
     sep[off[:k] + lengths[:k]] = 0xFF
-    assert hp.make_q8(sep)
-    pack.write(os.path.join(out, "profiles"), None, rows, lengths[:k], hp.stats(), hp.q8, hp.q8_scale,
+    assert hp.make_q8(sep) and hp.make_q4(sep)
+    pack.write(os.path.join(out, "profiles"), None, rows, lengths[:k], hp.stats(), hp.q8, hp.q8_scale, q4=hp.q4,
                names=["structure.rec%d.txt" % i for i in range(k)])
     write_pfm(os.path.join(out, "seq.pfm"), synth.pfm_rows(7, 4, np.random.default_rng(102)) + 0.01, "ACGU")
     write_pfm(os.path.join(out, "struct.pfm"), synth.pfm_rows(7, 7, np.random.default_rng(103)) + 0.01, "BEHLMRT")

@@ -13,3 +13,12 @@ print(d["sustained"], d["clocks"])
 for k, v in d["other_workloads"].items():
     print(k, {a: b for a, b in v.items() if a in ("value", "ms_per_step", "kernel_ms", "frac", "e2e", "frac_executed")})
 PY
+timeout 300 python bench.py --workload c2 --steps 200 --warmup 20 --no-cpu-baseline --trace gpurun_out/c2_timeline.json > gpurun_out/c2_bench_1.json 2> gpurun_out/c2_bench_1.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/c2_bench_1.json"))
+print("c2", d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"])
+t = json.load(open("gpurun_out/c2_timeline.json"))["events"]
+for e in t[-7:]:
+    print("%9.1f %7.1f gap %6.1f  %s" % (e["start"], e["dur"], e["gap_before"], e["name"][:60]))
+PY
