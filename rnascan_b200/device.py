@@ -983,6 +983,17 @@ def filter_applies(struct_table, threshold, absrow_max):
                 0 <= absrow_max < 1e30 and not np.isnan(t).any() and not (t == np.inf).any())
 
 
+def pick_filter_form(hp, struct_table, threshold):
+    """The smallest filter form whose guard band leaves the threshold selective: 4 bytes per position when that
+    form's band is at most 0.4 of a positive threshold, else 8 bytes; rows without a quantised form go as float32
+    (their own dtype, or the float32 shadow of float64 rows)."""
+    if hp.q4 is not None and threshold > 0 and q4_guard(struct_table, hp.q8_scale) <= 0.4 * threshold:
+        return "q4"
+    if hp.q8 is not None:
+        return "q8"
+    return "f32" if hp.dtype == _lib.RS_F32 else "shadow"
+
+
 class HostProfileScanner(object):
     """Averaged-profile scan (optionally AND the sequence PSSM) of HOST-resident streams through
     rs_filter_profile -> rs_host_gather_windows -> rs_resolve_candidates.
@@ -1247,14 +1258,7 @@ def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, 
         out = scan_fused(stream, profile, seq, tq, threshold)
         return out + (None,) if return_scanner else out
     if form is None:
-        # the smallest form whose guard band leaves the threshold selective: 4 bytes per position when its band is
-        # at most 0.4 of a positive threshold, else 8 bytes; rows without a quantised form go as float32
-        if hp.q4 is not None and threshold > 0 and q4_guard(tq, hp.q8_scale) <= 0.4 * threshold:
-            form = "q4"
-        elif hp.q8 is not None:
-            form = "q8"
-        else:
-            form = "f32" if hp.dtype == _lib.RS_F32 else "shadow"
+        form = pick_filter_form(hp, tq, threshold)
     sc = HostProfileScanner(n, W, form, chunk_rows=min(int(chunk_rows), max(n, 256)))
     src = {"q8": hp.q8, "q4": hp.q4}.get(form, hp.rows)
     out = sc.run(codes, src, hp.rows, tq, seq, threshold, hp.absrow_max(),

@@ -140,13 +140,24 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
 
 def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 21, form=None,
                       return_scanner=False):
+    form_arg = form
     if codes is None:
         codes = np.zeros(hp.n, np.uint8)
     stream = FakeSymbolStream(codes, kind="rna")
     if callable(seq):
         seq = seq(histogram(stream).numpy())
     out = scan_fused(stream, FakeProfileStream(hp.rows), seq, struct_table, threshold)
-    return out + (None,) if return_scanner else out
+    if not return_scanner:
+        return out
+    from rnascan_b200 import device                 # the product's own choice of filter form (pure host logic)
+    tq = np.asarray(struct_table, np.float64)
+    applies = device.filter_applies(tq, threshold, hp.absrow_max())
+
+    class Scanner(object):
+        form = form_arg or device.pick_filter_form(hp, tq, threshold)
+        h2d_bytes = 0
+        n_candidates = len(out[0])
+    return out + (Scanner if applies else None,)
 
 
 def scan_onehot_bg(stream, prob, table_fn, threshold, all_reduce=None, capacity=None, extra_margin=0.0):
