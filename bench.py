@@ -888,9 +888,11 @@ def e2e_api(dev, rows_host, lengths, offsets, tq, prof, device, target_rows=32_0
             alphabet, {l: tq[:, "BEHLMRT".index(l)].tolist() for l in alphabet.letters})}
         ns = ap.Namespace(minscore=THRESHOLD, debug=False, pack=False)
         positions = int(np.maximum(lengths[:k] - W_MOTIF + 1, 0).sum())
+        t0 = time.perf_counter()
         frame = ms.scan_main(tmp, pssm, alphabet, None, ns)
+        first_s = time.perf_counter() - t0
         times = []
-        for _ in range(3):
+        for _ in range(4):
             t0 = time.perf_counter()
             frame = ms.scan_main(tmp, pssm, alphabet, None, ns)
             times.append(time.perf_counter() - t0)
@@ -910,6 +912,9 @@ def e2e_api(dev, rows_host, lengths, offsets, tq, prof, device, target_rows=32_0
                                % (len(frame), len(pos)))
         sec = float(np.median(times))
         return {"value": positions / sec / 1e9, "unit": "Gpos/s", "ms_per_call": sec * 1e3, "symbols": m, "records": k,
+                "calls_ms": [round(first_s * 1e3, 2)] + [round(t * 1e3, 2) for t in times],
+                "calls_note": "value = median of calls 2..5; call 1 maps the pack (page faults) and allocates, call 2 "
+                              "copies the quantised section into page-locked memory once (pack.page_locked), later calls ship chunks straight from it",
                 "hits": int(len(frame)), "pack_bytes": os.path.getsize(pack.pack_path(tmp)), "pack_write_s": write_s,
                 "pack_on": "tmpfs" if base else "disk",
                 "api": "rnascan_b200.rnascan.scan_main(<directory holding rnascan_b200.pack>, pssm, alphabet, None, args): "

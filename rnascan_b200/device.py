@@ -918,6 +918,7 @@ class HostProfile(object):
         self.dtype = _lib.RS_F32 if rows.dtype == np.float32 else _lib.RS_F64
         self.q8, self.q8_scale = q8, q8_scale
         self.q4 = q4                                 # (n, 4) uint8 view of the 4-byte quantised rows (make_q4)
+        self.page_locked = None                      # (fn(form) -> pinned tensor | None, {form: array it stands for})
         self._stats = None if stats is None else tuple(float(v) for v in stats)
 
     def stats(self):
@@ -1261,6 +1262,10 @@ def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, 
         form = pick_filter_form(hp, tq, threshold)
     sc = HostProfileScanner(n, W, form, chunk_rows=min(int(chunk_rows), max(n, 256)))
     src = {"q8": hp.q8, "q4": hp.q4}.get(form, hp.rows)
+    if hp.page_locked is not None and form in ("q8", "q4") and src is hp.page_locked[1][form]:
+        locked = hp.page_locked[0](form)            # the pack's own section, untouched: maybe held in pinned memory
+        if locked is not None:
+            src = locked
     out = sc.run(codes, src, hp.rows, tq, seq, threshold, hp.absrow_max(),
                  q8_scale=hp.q8_scale if form in ("q8", "q4") else 1.0, all_reduce=all_reduce)
     return out + (sc,) if return_scanner else out

@@ -45,6 +45,38 @@ class ProfilePack(object):
         self.q8_scale = header.get("q8_scale")
         self.stats = tuple(header["stats"])
         self.n_rows = int(header["n_rows"])
+        self._asked = {}          # section name -> how often a page-locked copy was asked for
+        self._locked = {}         # section name -> pinned torch tensor holding a copy of the section, or None
+
+    def page_locked(self, name):
+        """The quantised section `name` ("q4" | "q8") as a PINNED torch uint8 tensor (a copy held in page-locked host
+        memory, from which the device copies without staging), or None.  The copy is made on the SECOND request: a
+        one-shot CLI run never pays for it, a process that scans the same pack again and again does once and then
+        ships chunks at link speed.  Sections above RNASCAN_PIN_CACHE_BYTES (default 8 GiB) are never copied;
+        callers then stage chunk by chunk as before.  (Page-locking the mapping itself with cudaHostRegister was
+        tried first: the driver refuses read-only file mappings here.)"""
+        if name in self._locked:
+            return self._locked[name]
+        self._asked[name] = self._asked.get(name, 0) + 1
+        arr = getattr(self, name, None)
+        if arr is None or self._asked[name] < 2:
+            return None
+        tensor = None
+        if arr.nbytes <= int(os.environ.get("RNASCAN_PIN_CACHE_BYTES", str(8 << 30))):
+            import torch
+            from . import _lib
+            from .device import HOST_THREADS
+            try:
+                tensor = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=True)
+                src = np.asarray(arr)
+                _lib.check(_lib.lib.rs_host_copy(tensor.data_ptr(), src.ctypes.data, src.nbytes, HOST_THREADS))
+            except RuntimeError:                                # no page-locked memory to be had
+                tensor = None
+        self._locked[name] = tensor
+        return tensor
+
+    def release(self):
+        self._locked = {}
 
 
 def pack_path(directory):
@@ -112,9 +144,40 @@ def write(directory, files, packed_rows, lengths, stats, q8=None, q8_scale=None,
     return path
 
 
+# One mapping per pack file and process: a new mapping means a page fault per 4 KB page on the first touch (16 ms per
+# 256 MB section, more than the copy to the device takes) and an munmap of gigabytes when it is dropped.  Keyed by the
+# file's identity (write() replaces the file, so a refreshed pack is another inode); two entries at most.
+_CACHE = {}
+
+
 def read(directory):
     """The pack of `directory` (memory-mapped) or None when there is none / it is not readable."""
-    path = pack_path(directory)
+    path = os.path.realpath(pack_path(directory))
+    try:
+        st = os.stat(path)
+    except OSError:
+        _drop(path)
+        return None
+    key = (st.st_ino, st.st_size, st.st_mtime_ns)
+    hit = _CACHE.get(path)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    _drop(path)
+    pk = _map(path)
+    if pk is not None:
+        while len(_CACHE) >= 2:
+            _drop(next(iter(_CACHE)))
+        _CACHE[path] = (key, pk)
+    return pk
+
+
+def _drop(path):
+    hit = _CACHE.pop(path, None)
+    if hit is not None:
+        hit[1].release()
+
+
+def _map(path):
     try:
         with open(path, "rb") as fh:
             if fh.read(8) != MAGIC:

@@ -1101,6 +1101,8 @@ def _load_profile_dir(directory, write_pack=False):
         r1 = int(pk.offsets[hi - 1] + pk.lengths[hi - 1] + 1) if hi > lo else 0
         hp = device.HostProfile(pk.rows[r0:r1], q8=None if pk.q8 is None else pk.q8[r0:r1], q8_scale=pk.q8_scale,
                                 stats=pk.stats, q4=None if pk.q4 is None else pk.q4[r0:r1])
+        if size == 1:                                  # repeated scans of one pack: a pinned copy of the section (pack.py)
+            hp.page_locked = (pk.page_locked, {"q8": hp.q8, "q4": hp.q4})
         return files[lo:hi], files, hp, lengths
     packed, lengths = _read_profiles_packed(files[lo:hi])
     hp = device.HostProfile(packed)
