@@ -2,6 +2,7 @@
 replaced by the CPU oracle (tests/oracle_backend.py) so that packing, hit mapping, frame
 assembly, messages and TSV text are compared with the reference's golden outputs.  The same
 cases run through the real kernels in tests/test_cli_gpu.py (-m gpu)."""
+import os
 import warnings
 
 import numpy as np
@@ -197,6 +198,31 @@ def test_pack_round_trips_both_quantised_forms(tmp_path):
     raw = bytearray(open(pack.pack_path(str(d)), "rb").read())
     raw[:8] = b"RSB200P0"
     open(pack.pack_path(str(d)), "wb").write(bytes(raw))
+    assert pack.read(str(d)) is None
+
+
+def test_pack_mapping_is_cached_per_process_and_dropped_when_the_file_changes(tmp_path):
+    from rnascan_b200 import pack
+    rng = np.random.default_rng(6)
+    lengths = np.array([4, 7], np.int64)
+    n = int((lengths + 1).sum())
+    rows = rng.random((n, 7))
+    q8 = rng.integers(0, 256, (n, 8), dtype=np.uint8)
+    q4 = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+    d = tmp_path / "p"
+    d.mkdir()
+    names = ["structure.a.txt", "structure.b.txt"]
+    pack.write(str(d), None, rows, lengths, (1.0, 0, 0, 1.0), q8, 0.5, names=names, q4=q4)
+    first = pack.read(str(d))
+    assert pack.read(str(d)) is first                       # same mapping: no new page faults, no munmap
+    assert first.page_locked("q4") is None                  # first request: never copied (one-shot runs)
+    second = first.page_locked("q4")                        # second request: a pinned copy -- or None without CUDA
+    assert second is None or (second.is_pinned() and np.array_equal(second.numpy(), q4))
+    assert first.page_locked("q4") is second
+    pack.write(str(d), None, rows + 1.0, lengths, (8.0, 0, 0, 2.0), q8, 0.5, names=names, q4=q4)
+    fresh = pack.read(str(d))
+    assert fresh is not first and np.array_equal(fresh.rows, rows + 1.0)
+    os.remove(pack.pack_path(str(d)))
     assert pack.read(str(d)) is None
 
 
