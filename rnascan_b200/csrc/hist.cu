@@ -4,23 +4,46 @@
 // A symbol is counted in bin (code & 7) iff bit 3 of its code is clear (separators 0xFF,
 // ambiguous bases 0x0C/0x0F and lower-case structure letters are not counted -- SURVEY.md H11).
 //
-// HBM-bound at 1 B/symbol: each thread streams 16-byte vectors; per 32-bit word the three
-// index bit-planes are masked with the validity plane and the 8 subset sums
-// (v, b0, b1, b2, b0b1, b0b2, b1b2, b0b1b2) are accumulated as packed byte counters in
-// registers (no shared-memory atomics in the loop).  Bin counts follow by inclusion-exclusion
-// once per thread, then warp shuffles -> shared memory -> ONE global atomic per bin per CTA.
+// HBM-bound at 1 B/symbol: each thread streams 16-byte vectors.  Per 32-bit word the validity plane
+// v (bit 0 of every counted byte) and the masked index planes b0, 2*b1, 4*b2 (each left at its own bit
+// position: w & (v << s), no shift of the data) are formed with a handful of logic operations, and ALL
+// the summing is done by dp4a -- dot products with 0x01010101 for the plane sums, dot products of two
+// planes for the pair sums (the byte-wise multiply is free there) -- into 32-bit accumulators.  That
+// moves the additions off the ALU pipe, which round 1's packed byte counters kept 60 % busy (ncu), and
+// removes the periodic flushing of those counters.  Bin counts follow by inclusion-exclusion over the
+// subset sums (v, b0, b1, b2, b0b1, b0b2, b1b2, b0b1b2) once per thread, then warp shuffles -> shared
+// memory -> ONE global atomic per bin per CTA.
 #include "common.cuh"
 
 #define HI_THREADS 256
-
-__device__ __forceinline__ unsigned bytesum(unsigned x)       // sum of the four byte lanes
-{
-    return __dp4a(x, 0x01010101u, 0u);
-}
+#define HI_UNROLL 4               // independent 16-byte loads in flight per thread (2 and 8 measured: no better;
+                                  // so were 8 CTAs per SM at 32 registers and fewer, fatter CTAs)
 
 // PLANES = 3: any stream (letter index in bits 0-2).  PLANES = 2: nucleotide streams, whose
 // counted symbols are 0..3 (bit 2 never set with bit 3 clear): half the arithmetic.
+// acc[T]: subset sum T (bit s of T set <=> plane s in the product) SCALED by scale(T) = prod 2^s.
 template <int PLANES>
+__device__ __forceinline__ void hist_word(unsigned w, unsigned (&acc)[1 << PLANES])
+{
+    const unsigned ONES = 0x01010101u;
+    const unsigned v = ~(w >> 3) & ONES;                  // counted: bit 3 clear
+    const unsigned b0 = w & v;
+    const unsigned b1 = w & (v * 2u);                     // bit 1 of every counted byte, value 2
+    acc[0] = __dp4a(v, ONES, acc[0]);
+    acc[1] = __dp4a(b0, ONES, acc[1]);
+    acc[2] = __dp4a(b1, ONES, acc[2]);                    // 2 * S1
+    acc[3] = __dp4a(b0, b1, acc[3]);                      // 2 * S01
+    if (PLANES == 3) {
+        const unsigned b2 = w & (v * 4u);                 // value 4
+        const unsigned b01 = b0 & (b1 >> 1);
+        acc[4] = __dp4a(b2, ONES, acc[4]);                // 4 * S2
+        acc[5] = __dp4a(b0, b2, acc[5]);                  // 4 * S02
+        acc[6] = __dp4a(b1, b2, acc[6]);                  // 8 * S12
+        acc[7] = __dp4a(b01, b2, acc[7]);                 // 4 * S012
+    }
+}
+
+template <int PLANES, int UNROLL = HI_UNROLL>
 __global__ void __launch_bounds__(HI_THREADS) hist_kernel(const uint8_t *__restrict__ codes, int64_t n,
                                                           unsigned long long *__restrict__ counts)
 {
@@ -35,44 +58,32 @@ __global__ void __launch_bounds__(HI_THREADS) hist_kernel(const uint8_t *__restr
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 
     while (i < nvec) {
+        // 32-bit accumulators: a word adds at most 4 * 16 to one of them; flushed every 2^20 vectors
         unsigned acc[NS];
 #pragma unroll
         for (int k = 0; k < NS; k++) acc[k] = 0;
-        // 3 rounds of 4 independent 16-byte loads (12 vectors * 4 words: byte counters stay < 256)
-        for (int rep = 0; rep < 3 && i < nvec; rep++) {
-            uint4 q[4];
+        for (int rep = 0; rep < (1 << 20) / UNROLL && i < nvec; rep++) {
+            uint4 q[UNROLL];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < UNROLL; u++) {
                 const int64_t j = i + u * gstride;
                 q[u] = j < nvec ? __ldg(v + j) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             }
-            i += 4 * gstride;
+            i += UNROLL * gstride;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const unsigned w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const unsigned w = w4[t];
-                    const unsigned nv = ~(w >> 3) & 0x01010101u;      // counted: bit 3 clear
-                    const unsigned b0 = w & nv;
-                    const unsigned b1 = (w >> 1) & nv;
-                    acc[0] += nv;
-                    acc[1] += b0;
-                    acc[2] += b1;
-                    acc[3] += b0 & b1;
-                    if (PLANES == 3) {
-                        const unsigned b2 = (w >> 2) & nv;
-                        acc[4] += b2;
-                        acc[5] += b0 & b2;
-                        acc[6] += b1 & b2;
-                        acc[7] += b0 & b1 & b2;
-                    }
-                }
+            for (int u = 0; u < UNROLL; u++) {
+                hist_word<PLANES>(q[u].x, acc);
+                hist_word<PLANES>(q[u].y, acc);
+                hist_word<PLANES>(q[u].z, acc);
+                hist_word<PLANES>(q[u].w, acc);
             }
         }
 #pragma unroll
-        for (int k = 0; k < NS; k++) tot[k] += bytesum(acc[k]);
+        for (int k = 0; k < NS; k++) tot[k] += acc[k];
     }
+    // undo the scaling of the plane sums (see hist_word)
+    tot[2] >>= 1; tot[3] >>= 1;
+    if (PLANES == 3) { tot[4] >>= 2; tot[5] >>= 2; tot[6] >>= 3; tot[7] >>= 2; }
     // tail symbols (n % 16) by the first threads of block 0
     if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
         const unsigned c = codes[nvec * 16 + threadIdx.x];
@@ -123,7 +134,7 @@ static int hist_launch(const uint8_t *d_codes, int64_t n, uint64_t *d_counts8, v
     const int dev = rs_current_device();
     if (!per_sm[dev]) {
         int v = 0;
-        RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hist_kernel<PLANES>, HI_THREADS, 0));
+        RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hist_kernel<PLANES, HI_UNROLL>, HI_THREADS, 0));
         per_sm[dev] = v > 0 ? v : 4;
     }
     int64_t cap = (int64_t)rs_sm_count() * per_sm[dev];

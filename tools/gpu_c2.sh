@@ -1,7 +1,7 @@
 #!/bin/bash
 # C2 (sequence-only scan, computed background): parity of the one-hot paths, the bench line, a device timeline
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_fullsize_gpu.py -x -q -k "onehot or seq or pair or struct" 2>&1 | tail -4 | tee gpurun_out/c2_pytest.log
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_fullsize_gpu.py -x -q  2>&1 | tail -4 | tee gpurun_out/c2_pytest.log
 timeout 300 python bench.py --workload c2 --steps 200 --warmup 20 --no-cpu-baseline --trace gpurun_out/c2_timeline.json > gpurun_out/c2_bench_1.json 2> gpurun_out/c2_bench_1.err
 tail -3 gpurun_out/c2_bench_1.err
 python - <<PY
