@@ -227,6 +227,13 @@ __device__ __forceinline__ int32_t rs_round3_milli(double x)
 // OUT: 0 = the calculate() types (float32 for A = 4, float64 for A = 7), 1 = int32 thousandths (A = 7).
 // (Tried and dropped: a 7^4-entry table of the exact prefix ((t0 + t1) + t2) + t3, one LDS.64 instead of four --
 // its random 8-byte reads collide on the banks about as often as they save wavefronts: 0.285 vs 0.282 ms at W = 7.)
+// What bounds it (round 2): the load/store unit.  Per 32 windows the kernel needs W LDS.64 of table entries (2
+// wavefronts each: 256 bytes into the registers at 128 B per clock), ~3 wavefronts of window symbols and 2 line
+// accesses for the store: 19 LSU cycles at W = 7, i.e. 0.263 ms for 125 M windows at 1.9 GHz; measured 0.284-0.289.
+// Eight consecutive windows per thread (each symbol's table offset and validity formed once, 37 instead of 58
+// instructions per window, 16-byte stores) was built and measured: bit-identical, but 0.346 ms -- a lane's 64
+// contiguous output bytes make every store instruction touch 16 lines instead of 2, and the table lookups, which
+// are the bulk of the LSU time, are not reduced by it.
 template <int A, int W, int OUT>
 __global__ void __launch_bounds__(DW_THREADS) dense_w_kernel(const __grid_constant__ OneHotParams prm)
 {
