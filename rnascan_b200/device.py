@@ -1021,6 +1021,13 @@ class HostProfileScanner(object):
         cols, tdt = ((8 if form == "q8" else 4), torch.uint8) if self.quantised else (len(CHANNELS), torch.float32)
         self.cols, self.tdt = cols, tdt
         self.dbuf = [torch.empty((self.rows_max, cols), dtype=tdt, device=self.device) for _ in range(2)]
+        # Rows past the end of a chunk must read as separators.  A full chunk always ends at the same row, so the
+        # rows behind it are set ONCE here; only a shorter (last) chunk needs them set again after its copy -- a
+        # fill kernel between every two copies on the copy stream kept the copy engine from running back to back.
+        self.full_rows = min(self.chunk + self.W - 1, max(self.n, 1))
+        if self.quantised:
+            for b in self.dbuf:
+                b.fill_(0xFF)
         self.stage = None                           # pinned staging, made on first use with a pageable source
         self.codes = None if self.quantised else torch.empty(padded_count(self.n) + 1024, dtype=torch.uint8,
                                                              device=self.device)
@@ -1072,7 +1079,7 @@ class HostProfileScanner(object):
             if k >= 2:
                 self.copy_stream.wait_event(self.freed[slot])
             self.dbuf[slot][:rows].copy_(piece, non_blocking=True)
-            if self.quantised:                      # rows past the end of the stream read as separators
+            if self.quantised and rows != self.full_rows:      # a short chunk: separators behind it (see __init__)
                 self.dbuf[slot][rows:rows + 512].fill_(0xFF)
             self.loaded[slot].record(self.copy_stream)
         self.h2d_bytes += rows * self.cols * (1 if self.quantised else 4)
@@ -1236,7 +1243,7 @@ class HostProfileScanner(object):
         return pos, sq, st
 
 
-def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 21, form=None,
+def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 23, form=None,
                       return_scanner=False):
     """Averaged-profile scan of host-resident rows (a HostProfile) through the filter + gather + resolve
     path; same results as scan_fused(SymbolStream(codes), ProfileStream(hp.rows), ...).  `codes`: uint8[n]

@@ -138,7 +138,7 @@ def scan_fused(stream, profile, seq_table, struct_table, threshold, capacity=Non
     return out + (0,) if return_stats else out
 
 
-def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 21, form=None,
+def scan_profile_host(codes, hp, seq, struct_table, threshold, all_reduce=None, chunk_rows=1 << 23, form=None,
                       return_scanner=False):
     form_arg = form
     if codes is None:
