@@ -481,6 +481,11 @@ def measure(args, wl, steps, ctx, full, n_target):
         settle = int(min(1000, max(0, 0.3 / max(per_step_s, 1e-6))))
         for _ in range(settle):
             step()
+    # a garbage-collector pause on ONE rank is a visible fraction of a 12 ms timed region (20 sub-millisecond steps,
+    # max over ranks): collect now, keep the collector off until the region is over
+    import gc
+    gc.collect()
+    gc.disable()
     barrier()
     launches[0] = 0
     per_step = N_MOTIFS_C5 if wl == "c5" else 1      # upper bound on profiled launches per step
@@ -507,6 +512,7 @@ def measure(args, wl, steps, ctx, full, n_target):
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
+    gc.enable()
     kms = np.zeros(max(steps, 1) * per_step, np.float32)
     nrec = np.zeros(1, np.int32)
     check(lib.rs_prof_end(kms.ctypes.data, len(kms), nrec.ctypes.data))
