@@ -26,7 +26,20 @@ import warnings
 from collections import defaultdict
 
 import numpy as np
-import pandas as pd
+
+
+class _LazyPandas(object):
+    """pandas on first use.  A FASTA scan needs it neither for its PFMs (_read_pfm_counts) nor for hits.tab (the
+    native writer): importing it costs 1-3 s of a run whose device work is milliseconds.  Profile directories,
+    -t, empty results and anything unusual still go through pandas, exactly as before."""
+
+    def __getattr__(self, name):
+        import pandas
+        globals()["pd"] = pandas
+        return getattr(pandas, name)
+
+
+pd = _LazyPandas()
 
 from . import motifs
 from . import seq as _seq
@@ -243,10 +256,75 @@ def load_motif(pfm_file, *args):
 def pfm2pssm(pfm_file, pseudocount, alphabet, background=None):
     """PFM file -> normalize(pseudocount) -> log_odds(background) -> PSSM
     (rnascan.py:238-252).  The first column is dropped; header letters may come in any order."""
-    table = pd.read_csv(pfm_file.open() if isinstance(pfm_file, _PfmBlock) else pfm_file, sep="\t")
-    counts = table.drop(columns=table.columns[0]).to_dict(orient="list")
+    counts = _pfm_counts(pfm_file)
     values = motifs.Motif(alphabet=alphabet, counts=counts).pssm(pseudocount, background)
     return matrix.ExtendedPositionSpecificScoringMatrix(alphabet, values)
+
+
+def _pfm_counts(pfm_file):
+    """{letter: column values} of a PFM table, first column dropped: what
+    ``pd.read_csv(f, sep="\\t").drop(columns=first).to_dict(orient="list")`` gives (rnascan.py:242-245)."""
+    counts = _read_pfm_counts(pfm_file)
+    if counts is None:
+        table = pd.read_csv(pfm_file.open() if isinstance(pfm_file, _PfmBlock) else pfm_file, sep="\t")
+        counts = table.drop(columns=table.columns[0]).to_dict(orient="list")
+    return counts
+
+
+_PLAIN_INT = re.compile(r"^[+-]?[0-9]{1,15}$")
+
+
+def _read_pfm_counts(pfm_file):
+    """The same dictionary without pandas, for tables in the plain format -- a header of unique names, every row
+    with as many tab-separated fields as the header, every value a plain decimal number -- or None (then pandas
+    reads the file: quotes, blanks, NaN, ragged rows, index inference, ... are its business).  Numbers are
+    converted as pandas converts them: its default converter is not correctly rounded, rs_host_parse_doubles
+    restates it bit for bit (tests/test_host_cpu.py); an all-integer column stays int64 as in pandas."""
+    from . import _lib
+    try:
+        if isinstance(pfm_file, _PfmBlock):
+            text = pfm_file.text
+        else:
+            with open(pfm_file, "r", newline="") as handle:
+                text = handle.read()
+    except (OSError, UnicodeDecodeError):
+        return None
+    if not text.isascii() or '"' in text or "\r" in text.replace("\r\n", "\n") or "\x00" in text:
+        return None
+    lines = [ln for ln in text.replace("\r\n", "\n").split("\n") if ln != ""]
+    if len(lines) < 2:
+        return None
+    names = lines[0].split("\t")
+    if len(names) < 2 or len(set(names)) != len(names) or any(n == "" or n != n.strip() for n in names):
+        return None
+    if any(_PLAIN_INT.match(n) or n.startswith("Unnamed") for n in names):
+        return None
+    rows = [ln.split("\t") for ln in lines[1:]]
+    if any(len(r) != len(names) for r in rows):
+        return None
+    counts = {}
+    for c in range(1, len(names)):
+        tokens = [r[c] for r in rows]
+        if any(t == "" or t != t.strip() for t in tokens):
+            return None
+        if all(_PLAIN_INT.match(t) for t in tokens):
+            counts[names[c]] = [int(t) for t in tokens]          # an int64 column
+            continue
+        blob = "\n".join(tokens).encode("ascii")
+        out = np.zeros(len(tokens), np.float64)
+        ok = np.zeros(len(tokens), np.uint8)
+        n_out = np.zeros(1, np.int64)
+        if _lib.lib.rs_host_parse_doubles(blob, len(blob), out.ctypes.data, len(out), n_out.ctypes.data,
+                                          ok.ctypes.data) != 0 or int(n_out[0]) != len(tokens):
+            return None
+        values = out.tolist()
+        for k, t in enumerate(tokens):
+            if not ok[k]:
+                if not _PLAIN_INT.match(t):
+                    return None                                   # not a number the converter takes: pandas decides
+                values[k] = float(int(t))                         # an integer token in a float column (exact)
+        counts[names[c]] = values
+    return counts
 
 
 class _PfmBlock(object):
@@ -820,7 +898,7 @@ def _scan_fasta(fasta_file, pssm, alphabet, minscore, restrict=None):
                                  logodds), n_records
 
 
-NATIVE_WRITER_MIN_ROWS = 50000       # from this many rows on main() formats hits.tab natively (no DataFrame)
+NATIVE_WRITER_MIN_ROWS = 1           # from this many rows on main() formats hits.tab natively (no DataFrame)
 
 
 class _Hits(object):
@@ -997,8 +1075,7 @@ def _scan_fasta_hits_computed_bg(fasta_file, pfm_file, pseudocount, alphabet, mi
         return None
     batch = batches[0]
     try:
-        table = pd.read_csv(pfm_file, sep="\t")
-        counts = table.drop(columns=table.columns[0]).to_dict(orient="list")
+        counts = _pfm_counts(pfm_file)
         norm = motifs.normalize_counts(motifs.Motif(alphabet=alphabet, counts=counts).counts, alphabet.letters,
                                        pseudocount)
         prob = np.array([norm[c] for c in columns], dtype=np.float64).T.copy()
@@ -1865,7 +1942,7 @@ def _write_stats(dest, seq_type, runtime):
     c, ph = STATS.counts, STATS.phases
     positions = c.get("scored_positions", 0)
     form = STATS.notes.get("profile_filter_form")
-    per_row = {"q8": 8.0, "f32": 29.0, "shadow": 29.0}.get(form, 0.0)
+    per_row = {"q4": 4.0, "q8": 8.0, "f32": 29.0, "shadow": 29.0}.get(form, 0.0)
     dev_bytes = c.get("symbols", 0) * 1.0 + c.get("profile_rows", 0) * per_row
     out = {"mode": seq_type, "world_size": _world_size(), "total_s": runtime,
            "phases_s": {k: round(v, 6) for k, v in sorted(ph.items())},

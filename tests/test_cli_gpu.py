@@ -43,11 +43,28 @@ def same(a, b):
 
 @pytest.mark.parametrize("name", ALIGNED)
 def test_cli_output_is_byte_identical_native_writer(name, in_repo, monkeypatch):
-    """Same golden files through the C++ hits.tab formatter (rs_host_format_hits*), which main() uses
-    from NATIVE_WRITER_MIN_ROWS rows on instead of building DataFrames."""
+    """Same golden files with the OTHER way of printing.  main() formats FASTA results through the C++ hits.tab
+    formatter (rs_host_format_hits*) from NATIVE_WRITER_MIN_ROWS = 1 row on; here the threshold is out of reach,
+    so every result is assembled as DataFrames and printed by pandas, as the reference does."""
     from rnascan_b200 import rnascan as ms
-    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 0)
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 10 ** 12)
     test_cli_output_is_byte_identical(name, in_repo)
+
+
+def test_fasta_run_does_not_import_pandas(in_repo):
+    """A FASTA scan reads its PFM without pandas and prints through the native writer: pandas (1-3 s of import)
+    is never loaded -- and the output is the golden one."""
+    import subprocess
+    import sys
+    name = "rna_mixed_all"
+    code = ("import sys, warnings; warnings.simplefilter('ignore'); from rnascan_b200 import rnascan as ms\n"
+            "try:\n    ms.main(%r)\nexcept SystemExit:\n    pass\n"
+            "sys.stderr.write('PANDAS_LOADED=%%s\\n' %% ('pandas' in sys.modules))\n" % (CASES[name]["argv"],))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    with open(os.path.join(CLI, name + ".stdout")) as fh:
+        assert out.stdout == fh.read()
+    assert "PANDAS_LOADED=False" in out.stderr, out.stderr[-500:]
 
 
 @pytest.mark.parametrize("name", ALIGNED)

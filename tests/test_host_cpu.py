@@ -698,3 +698,80 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert out["cpu_baseline"]["kind"] in ("reference", "port") and out["cpu_baseline"]["cores"] >= 1
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["value"] == out["value"]
     assert "workload" in out["config"]
+
+
+def test_pfm_reader_without_pandas_equals_pandas_or_declines(tmp_path):
+    """rnascan._read_pfm_counts (PFM tables without importing pandas) must give exactly what
+    pd.read_csv(...).drop(first column).to_dict("list") gives -- same keys, same Python types, same bits --
+    or decline (None) and leave the file to pandas.  Random tables in many number formats, plus the oddities
+    it has to decline."""
+    import pandas as pd
+    from rnascan_b200 import rnascan as ms
+    rng = np.random.default_rng(77)
+
+    def token(kind):
+        v = float(rng.random()) * float(rng.choice([1.0, 1e-3, 37.0, 1e5]))
+        if kind == 0:
+            return repr(v)
+        if kind == 1:
+            return "%.17g" % v
+        if kind == 2:
+            return "%.4f" % v
+        if kind == 3:
+            return "%d" % int(v * 10)
+        if kind == 4:
+            return "%.3e" % v
+        if kind == 5:
+            return "-" + repr(v)
+        if kind == 6:
+            return ("%.6f" % v).lstrip("0") or "0"          # ".123456"
+        if kind == 7:
+            return "%d." % int(v)
+        return str(rng.choice(["nan", "inf", "", " 0.5", "0.5 ", "1e400", "0x10", "1,5", "12345678901234567890", "abc"]))
+
+    n_equal = n_declined = 0
+    for case in range(400):
+        ncol = int(rng.integers(2, 9))
+        nrow = int(rng.integers(1, 9))
+        letters = list(rng.permutation(list("ACGUBEHLMRT"))[:ncol - 1])
+        header = ["PO"] + letters
+        odd = rng.random() < 0.25
+        col_kind = [int(rng.integers(0, 8)) for _ in range(ncol)]
+        lines = ["\t".join(header)]
+        for r in range(nrow):
+            fields = [str(r + 1)]
+            for c in range(1, ncol):
+                kind = col_kind[c] if rng.random() < 0.8 else int(rng.integers(0, 8))
+                if odd and rng.random() < 0.1:
+                    kind = 8
+                fields.append(token(kind))
+            lines.append("\t".join(fields))
+        text = "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
+        if rng.random() < 0.1:
+            text = text.replace("\n", "\r\n")
+        if rng.random() < 0.05:
+            text = text.replace("\n", "\n\n", 1)                     # a blank line (pandas skips it)
+        if odd and rng.random() < 0.2:
+            text = text.replace("\t", "\t\t", 1)                     # a ragged header or row
+        path = tmp_path / ("pfm%d.txt" % case)
+        path.write_bytes(text.encode("ascii"))
+        got = ms._read_pfm_counts(str(path))
+        if got is None:
+            n_declined += 1
+            continue
+        table = pd.read_csv(str(path), sep="\t")
+        want = table.drop(columns=table.columns[0]).to_dict(orient="list")
+        assert list(got) == list(want), (case, text)
+        for name in got:
+            assert len(got[name]) == len(want[name]), (case, name, text)
+            for a, b in zip(got[name], want[name]):
+                assert type(a) is type(b), (case, name, a, b, text)
+                if isinstance(a, float):
+                    assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64), (case, name, a, b)
+                else:
+                    assert a == b
+        n_equal += 1
+    assert n_equal > 200 and n_declined > 20, (n_equal, n_declined)
+    # a multi-PFM block goes through the same reader
+    block = ms._PfmBlock("m1", "PO\tA\tC\tG\tU\n1\t0.1\t0.2\t0.3\t0.4\n", "x.multi")
+    assert ms._read_pfm_counts(block) == {"A": [0.1], "C": [0.2], "G": [0.3], "U": [0.4]}

@@ -14,14 +14,14 @@ from oracle_backend import install
 
 FUNCS = [getattr(gpu_cases, n) for n in dir(gpu_cases) if n.startswith("test_")
          and n not in ("test_cli_output_is_byte_identical", "test_cli_output_is_byte_identical_native_writer",
-                       "test_pwm_module_signature_and_errors")]
+                       "test_pwm_module_signature_and_errors", "test_fasta_run_does_not_import_pandas")]
 
 
 @pytest.mark.parametrize("name", gpu_cases.ALIGNED)
 def test_cli_native_writer_against_golden(name, in_repo, monkeypatch):
     from rnascan_b200 import rnascan as ms
     install(monkeypatch)
-    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 0)
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 10 ** 12)       # the other way of printing: DataFrames
     _call(gpu_cases.test_cli_output_is_byte_identical, name=name, in_repo=in_repo)
 
 
@@ -224,6 +224,49 @@ def test_pack_mapping_is_cached_per_process_and_dropped_when_the_file_changes(tm
     assert fresh is not first and np.array_equal(fresh.rows, rows + 1.0)
     os.remove(pack.pack_path(str(d)))
     assert pack.read(str(d)) is None
+
+
+_NO_PANDAS_WORKER = r"""
+import os, sys, warnings
+sys.path.insert(0, %(repo)r)
+sys.path.insert(0, os.path.join(%(repo)r, "tests"))
+os.chdir(%(repo)r)
+import oracle_backend
+from rnascan_b200 import rnascan as ms
+
+
+class Patch(object):
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+oracle_backend.install(Patch())
+warnings.simplefilter("ignore")
+try:
+    ms.main(%(argv)r)
+except SystemExit:
+    pass
+sys.stderr.write("PANDAS_LOADED=%%s\n" %% ("pandas" in sys.modules))
+"""
+
+
+@pytest.mark.parametrize("name", ["rna_mixed_all", "ss_mixed_thr", "rnass_fasta_all"])
+def test_fasta_runs_never_import_pandas(name, tmp_path):
+    """FASTA scans with hits read their PFMs without pandas (_read_pfm_counts) and print through the native writer:
+    pandas is not even imported -- and stdout is the golden file.  (Host logic; the kernels are the oracle's.)"""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(repo, "tests", "golden", "cli", "cases.json")) as fh:
+        argv = json.load(fh)[name]["argv"]
+    script = tmp_path / "worker.py"
+    script.write_text(_NO_PANDAS_WORKER % {"repo": repo, "argv": argv})
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    with open(os.path.join(repo, "tests", "golden", "cli", name + ".stdout")) as fh:
+        assert out.stdout == fh.read()
+    assert "PANDAS_LOADED=False" in out.stderr, out.stderr[-800:]
 
 
 def test_native_library_output_stays_out_of_hits_tab_under_torchrun(tmp_path):
