@@ -1329,6 +1329,28 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     return (frame, n_files, arrays) if want_arrays else (frame, n_files)
 
 
+_DIR_PROTOTYPES = {}
+
+
+def _dir_frame_prototype(shape):
+    """One-row stand-ins for the per-file frames of the reference -- "hit": pd.DataFrame(list of Series), "empty":
+    pd.DataFrame([]) -- with the id columns added, concatenated in the order `shape` names and the last two
+    columns moved to the front, all through the reference's own pandas calls.  Column order and dtypes of the
+    result depend on nothing else, so each of the five shapes is worked out once per process."""
+    proto = _DIR_PROTOTYPES.get(shape)
+    if proto is None:
+        parts = []
+        for kind in (shape.split(",") if shape else []):
+            part = pd.DataFrame([pd.Series(["m", 1, 2, ".", 0.5], index=HIT_COLUMNS)]) if kind == "hit" \
+                else pd.DataFrame([])
+            _add_sequence_id(part, "id", "")
+            parts.append(part)
+        proto = pd.concat(parts) if parts else pd.DataFrame()
+        cols = proto.columns.tolist()
+        proto = _DIR_PROTOTYPES[shape] = proto[cols[-2:] + cols[:-2]]
+    return proto
+
+
 def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits=None,
                         any_struct_hits=None):
     """The frame the reference gets for a directory (rnascan.py:348-375, 408-413): one frame per file built
@@ -1340,25 +1362,19 @@ def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, f
     n = len(hit_names)
     with_hits = set(hit_names)
     any_empty = any(name not in with_hits for name in all_names)
-    hit = pd.DataFrame([pd.Series([motif_id, 1, 2, ".", 0.5], index=HIT_COLUMNS)])
-    empty = pd.DataFrame([])
-    for proto in (hit, empty):
-        _add_sequence_id(proto, "id", "")
     if first_has_hits is True and all_names and all_names[0] not in with_hits:
         any_empty = True                  # (combined mode) its structure hits exist, none of them joint
     if n == 0 and any_struct_hits and first_has_hits is None:
         first_has_hits = len(all_names) == 1       # a single file: it is the one with the structure hits
     if n == 0 and not first_has_hits and not any_struct_hits:
-        protos = [empty]
+        shape = "empty"
     elif not any_empty:
-        protos = [hit]
+        shape = "hit"
     else:
         if first_has_hits is None:
             first_has_hits = all_names[0] in with_hits
-        protos = [hit, empty] if first_has_hits else [empty, hit]
-    proto = pd.concat(protos) if all_names else pd.DataFrame()
-    cols = proto.columns.tolist()
-    proto = proto[cols[-2:] + cols[:-2]]
+        shape = "hit,empty" if first_has_hits else "empty,hit"
+    proto = _dir_frame_prototype(shape if all_names else "")
     data = {"Sequence_ID": np.array(hit_names, dtype=object), "Description": np.array([""] * n, dtype=object),
             "Motif_ID": np.array([motif_id] * n, dtype=object), "Start": np.asarray(start0, np.int64) + 1,
             "End": np.asarray(start0, np.int64) + width, "Sequence": np.array(["."] * n, dtype=object),
