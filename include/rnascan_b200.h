@@ -139,6 +139,8 @@ int rs_host_annotate_structures(const char *text, const int64_t *offsets, const 
  * score kinds: 0 float32 (already rounded) as numpy float32 text; 1 the same widened to a Python
  * float; 2 float64 with Python's round(x, 3) applied here; 3 float64 unrounded (averaged profiles);
  * 4 int32 thousandths of round(x, 3) as rs_scores_dense_struct_milli delivers them (single-modality only).
+ * rs_host_format_hits: score_kind | 0x100 prints Start and End as float64 text ("12.0"), which is what
+ * pandas makes of a profile directory in which some file had no hit.
  * Returns RS_OK and *written; RS_ERR_WORKSPACE when `capacity` is too small (*written = need);
  * RS_ERR_INVALID when a value is outside the covered text formats (caller falls back).        */
 int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const int64_t *rec, const char *id_blob,

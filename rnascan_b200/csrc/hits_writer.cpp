@@ -172,16 +172,21 @@ extern "C" int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const
 {
     if (n_rows < 0 || !written || (n_rows > 0 && (!rec || !id_off || !desc_off || !start0 || !scores || !motif_id)))
         return RS_ERR_INVALID;
-    if (score_kind < 0 || (score_kind > 2 && score_kind != 4)) return RS_ERR_INVALID;
+    // bit 8 of score_kind: Start and End as float64 text ("12.0") -- what pandas prints for a directory of averaged
+    // profiles in which some file had no hit (the empty per-file frame turns the concatenated columns float)
+    const bool float_pos = (score_kind & 0x100) != 0;
+    score_kind &= 0xFF;
+    if (score_kind < 0 || score_kind > 4) return RS_ERR_INVALID;
     const Strings ids{id_blob, id_off}, descs{desc_blob, desc_off};
     const size_t motif_len = strlen(motif_id);
     return run_rows(n_rows, out, capacity, written, [&](Out &o, int64_t a, int64_t b) {
         for (int64_t r = a; r < b; r++) {
+            if (float_pos && start0[r] + width >= 1000000000000000LL) return false;   // repr() turns to exponents at 1e16
             ids.put(o, rec[r]); o.put('\t');
             descs.put(o, rec[r]); o.put('\t');
             o.put_field(motif_id, (int64_t)motif_len); o.put('\t');
-            o.put_int(start0[r] + 1); o.put('\t');
-            o.put_int(start0[r] + width); o.put('\t');
+            o.put_int(start0[r] + 1); if (float_pos) { o.put('.'); o.put('0'); } o.put('\t');
+            o.put_int(start0[r] + width); if (float_pos) { o.put('.'); o.put('0'); } o.put('\t');
             if (text) o.put_field(reinterpret_cast<const char *>(text) + text_pos[r], width);
             else o.put('.');
             o.put('\t');
@@ -189,6 +194,7 @@ extern "C" int rs_host_format_hits(int64_t n_rows, int64_t match_id_first, const
             if (score_kind == 0) fine = put_f32(o, static_cast<const float *>(scores)[r]);
             else if (score_kind == 1) fine = put_f64(o, (double)static_cast<const float *>(scores)[r]);
             else if (score_kind == 2) fine = put_f64(o, round3(static_cast<const double *>(scores)[r]));
+            else if (score_kind == 3) fine = put_f64(o, static_cast<const double *>(scores)[r]);
             else fine = put_milli(o, static_cast<const int32_t *>(scores)[r]);
             if (!fine) return false;
             o.put('\t');

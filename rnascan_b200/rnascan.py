@@ -1295,6 +1295,9 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
     if want_arrays and size == 1 and seq is not None:
         arrays = (list(hit_names), start0.copy(), np.zeros(0, np.float32) if seq_scores is None else seq_scores,
                   np.asarray(scores, np.float64))
+    elif want_arrays and size == 1:       # structure only: what the native writer needs (_DirHits)
+        arrays = _DirHits(motif_id, width, list(names), np.asarray(rec, np.int64), np.asarray(start0, np.int64),
+                          np.asarray(scores, np.float64), _dir_frame_shape(all_names, hit_names))
     if size > 1:
         first = all_names.index(names[0]) if names else 0          # this rank's files are a contiguous range
         gathered = shard.gather_arrays([rec + first, start0, np.asarray(scores, np.float64)])
@@ -1315,7 +1318,7 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
             found = shard.gather_objects(local) if size > 1 else [local]
             any_struct_hits = bool(found and any(found))
     if size > 1 and rank != 0:            # only rank 0 assembles and prints
-        return (pd.DataFrame(), n_files, None) if want_arrays else (pd.DataFrame(), n_files)
+        return (_Deferred(lambda: pd.DataFrame()), n_files, None) if want_arrays else (pd.DataFrame(), n_files)
     first_has_hits = None
     if seq is not None and n_files > 1 and rank == 0 and len(lengths):
         # combined mode: `hit_names` only knows the windows where BOTH scores pass, but the column order of the
@@ -1323,10 +1326,13 @@ def _scan_profile_dir(directory, pssm, minscore, debug, seq_batches=None, seq_pm
         # structure hits: one small structure-only scan of that file settles it
         first = device.HostProfile(np.ascontiguousarray(hp.rows[:int(lengths[0])]))
         first_has_hits = len(device.scan_profile_host(None, first, None, tq, minscore)[0]) > 0
-    frame = _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits, any_struct_hits)
-    if want_arrays and arrays is not None and first_has_hits is False:
+    build = lambda: _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits,
+                                        any_struct_hits)
+    if not want_arrays:
+        return build(), n_files
+    if arrays is not None and first_has_hits is False:
         arrays = None                     # unusual column order: the DataFrame path prints it
-    return (frame, n_files, arrays) if want_arrays else (frame, n_files)
+    return _Deferred(build), n_files, arrays      # the frame only if the native writer cannot print the result
 
 
 _DIR_PROTOTYPES = {}
@@ -1351,6 +1357,40 @@ def _dir_frame_prototype(shape):
     return proto
 
 
+def _dir_frame_shape(all_names, hit_names, first_has_hits=None, any_struct_hits=None):
+    """Which per-file frames the reference concatenates, as far as the result's columns and dtypes go: "hit" (every
+    file has one), "hit,empty" / "empty,hit" (some file has none; the first file's frame decides the column order),
+    "empty" (no hit anywhere), "" (no file)."""
+    if not all_names:
+        return ""
+    n = len(hit_names)
+    with_hits = set(hit_names)
+    any_empty = any(name not in with_hits for name in all_names)
+    if first_has_hits is True and all_names[0] not in with_hits:
+        any_empty = True                  # (combined mode) its structure hits exist, none of them joint
+    if n == 0 and any_struct_hits and first_has_hits is None:
+        first_has_hits = len(all_names) == 1       # a single file: it is the one with the structure hits
+    if n == 0 and not first_has_hits and not any_struct_hits:
+        return "empty"
+    if not any_empty:
+        return "hit"
+    if first_has_hits is None:
+        first_has_hits = all_names[0] in with_hits
+    return "hit,empty" if first_has_hits else "empty,hit"
+
+
+class _Deferred(object):
+    """A value worked out when (and if) somebody asks for it."""
+
+    def __init__(self, fn):
+        self._fn, self._done, self._value = fn, False, None
+
+    def __call__(self):
+        if not self._done:
+            self._value, self._done, self._fn = self._fn(), True, None
+        return self._value
+
+
 def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, first_has_hits=None,
                         any_struct_hits=None):
     """The frame the reference gets for a directory (rnascan.py:348-375, 408-413): one frame per file built
@@ -1360,21 +1400,7 @@ def _averaged_dir_frame(all_names, hit_names, motif_id, start0, width, scores, f
     columns remain when no file had one) is learnt from one-row prototypes run through the same calls, then
     applied to the whole result at once."""
     n = len(hit_names)
-    with_hits = set(hit_names)
-    any_empty = any(name not in with_hits for name in all_names)
-    if first_has_hits is True and all_names and all_names[0] not in with_hits:
-        any_empty = True                  # (combined mode) its structure hits exist, none of them joint
-    if n == 0 and any_struct_hits and first_has_hits is None:
-        first_has_hits = len(all_names) == 1       # a single file: it is the one with the structure hits
-    if n == 0 and not first_has_hits and not any_struct_hits:
-        shape = "empty"
-    elif not any_empty:
-        shape = "hit"
-    else:
-        if first_has_hits is None:
-            first_has_hits = all_names[0] in with_hits
-        shape = "hit,empty" if first_has_hits else "empty,hit"
-    proto = _dir_frame_prototype(shape if all_names else "")
+    proto = _dir_frame_prototype(_dir_frame_shape(all_names, hit_names, first_has_hits, any_struct_hits))
     data = {"Sequence_ID": np.array(hit_names, dtype=object), "Description": np.array([""] * n, dtype=object),
             "Motif_ID": np.array([motif_id] * n, dtype=object), "Start": np.asarray(start0, np.int64) + 1,
             "End": np.asarray(start0, np.int64) + width, "Sequence": np.array(["."] * n, dtype=object),
@@ -1496,6 +1522,40 @@ def load_background(bg_file, uniform, *args):
 ###############################################################################
 # Main
 ###############################################################################
+class _DirHits(object):
+    """Hits of a structure-only scan of a profile directory as arrays (single process), for the native writer:
+    the text pandas prints for the reference's concatenated per-file frames when the first file has a hit --
+    Start / End as integers when every file has one ("hit"), as floats when some file has none ("hit,empty").
+    Other shapes (first file without hits: another column order; no hit at all) are left to the DataFrame path."""
+
+    def __init__(self, motif_id, width, names, rec, start0, scores, shape):
+        self.motif_id, self.width, self.names = motif_id, width, names
+        self.rec, self.start0, self.scores, self.shape = rec, start0, scores, shape
+
+    def write_native(self, out):
+        if self.shape not in ("hit", "hit,empty") or len(self.rec) < max(1, NATIVE_WRITER_MIN_ROWS):
+            return False
+        blobs = _StringBlobs(self.names, [""] * len(self.names))
+        kind = 3 | (0x100 if self.shape == "hit,empty" else 0)
+        header = "\t".join(["Sequence_ID", "Description", "Motif_ID", "Start", "End", "Sequence", "LogOdds",
+                            "Match_ID"]) + "\n"
+        sc = np.ascontiguousarray(self.scores, np.float64)
+        pieces = []
+        for a in range(0, len(self.rec), NATIVE_CHUNK_ROWS):
+            b = min(len(self.rec), a + NATIVE_CHUNK_ROWS)
+            text = _native_rows(b - a, 1 + a, self.rec[a:b], blobs, None, self.motif_id, None, self.start0[a:b],
+                                self.width, None, None, self.start0[a:b], kind, sc[a:b], None, None)
+            if text is None:
+                if pieces:
+                    raise ValueError("hit score outside the text formats of the native hits.tab writer")
+                return False
+            if not pieces:
+                _emit(out, header)
+            _emit(out, text)
+            pieces.append(b - a)
+        return True
+
+
 class _Joint(object):
     """Windows where BOTH scores pass, as arrays in the order of the sequence input (= the order of
     the reference's inner join, whose left side is the sequence frame)."""
@@ -1559,7 +1619,7 @@ def _combined_hits(seq_file, struct_file, seq_pssm, struct_pssm, args):
                                                  seq_batches=seq_batches, seq_pm=seq_pm, want_arrays=True,
                                                  write_pack=getattr(args, "pack", False))
         eprint("Processed %d sequences" % count)
-        joint.struct_frame = lambda: frame
+        joint.struct_frame = frame        # deferred: built only when the DataFrame path prints
         if arrays is None or len(seq_batches) != 1 or _world_size() > 1:
             joint.rec = None              # frames only
             return joint
@@ -1847,6 +1907,7 @@ def _run(args, seq_type, rank, precomputed=None):
     seq_file = struct_file = None
     seq_pssm = None
     seq_hits = struct_hits = joint = None          # array-level results (single process, FASTA inputs)
+    dir_hits = dir_frame = None                    # structure-only scan of a profile directory
     seq_results = struct_results = None
     arrays_ok = _world_size() == 1 and not args.testseq
 
@@ -1909,6 +1970,14 @@ def _run(args, seq_type, rank, precomputed=None):
                 eprint("Scanning sequences ")
                 struct_hits = _scan_fasta_hits(struct_file, struct_pssm, structure, args.minscore)
                 eprint("Processed %d sequences" % struct_hits.n_records)
+            elif seq_type == "SS" and arrays_ok and os.path.isdir(struct_file):
+                # scan_main's directory branch (same messages), keeping the hit arrays for the native writer; the
+                # DataFrame is only built if that writer cannot print the result
+                eprint("Scanning averaged secondary structures ")
+                dir_frame, count, dir_hits = _scan_profile_dir(struct_file, struct_pssm, args.minscore, args.debug,
+                                                               want_arrays=True,
+                                                               write_pack=getattr(args, "pack", False))
+                eprint("Processed %d sequences" % count)
             else:
                 struct_results = scan_main(struct_file, struct_pssm, structure, bg, args)
 
@@ -1925,7 +1994,11 @@ def _run(args, seq_type, rank, precomputed=None):
             hits = seq_hits if seq_type == "RNA" else struct_hits
             if hits is not None and hits.n_records > 0 and hits.total() >= NATIVE_WRITER_MIN_ROWS:
                 written = hits.write_native(sys.stdout)
+            elif seq_type == "SS" and dir_hits is not None:
+                written = dir_hits.write_native(sys.stdout)
         if not written:
+            if seq_type == "SS" and struct_results is None and struct_hits is None and dir_frame is not None:
+                struct_results = dir_frame()
             if seq_results is None and seq_hits is not None:
                 seq_results = seq_hits.frame()
             if struct_results is None and struct_hits is not None:

@@ -51,6 +51,61 @@ def test_cli_output_is_byte_identical_native_writer(name, in_repo, monkeypatch):
     test_cli_output_is_byte_identical(name, in_repo)
 
 
+def test_directory_results_print_natively_without_building_a_frame(tmp_path, in_repo, monkeypatch):
+    for order in ("hit_first", "none_first"):
+        _directory_native_case(order, tmp_path / order, monkeypatch)
+
+
+def _directory_native_case(order, tmp_path, monkeypatch):
+    """Structure-only scan of a profile directory: when the first file has a hit the text pandas would print for the
+    reference's concatenated per-file frames -- Start / End as FLOATS as soon as some file has no hit -- comes from
+    the native writer and no DataFrame is built; with a first file without hits (another column order) the frames do
+    the printing.  Same bytes either way.  The combined FASTA + directory mode never builds the structure frame."""
+    import shutil
+    from rnascan_b200 import rnascan as ms
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 1)
+    work = tmp_path / "profiles"
+    os.makedirs(work)
+    example = os.path.join(INP, "profiles_example", "structure.hg19_dna.txt")
+    none = sorted(os.listdir(os.path.join(INP, "profiles_mixed")))[0]
+    shutil.copy(example, work / "structure.a_hit.txt")
+    shutil.copy(os.path.join(INP, "profiles_mixed", none), work / "structure.b_none.txt")
+    shutil.copy(example, work / "structure.c_hit.txt")
+    listing = sorted(str(work / f) for f in os.listdir(work))
+    if order == "none_first":
+        listing = [listing[1], listing[0], listing[2]]
+    monkeypatch.setattr(ms, "_profile_files", lambda directory: list(listing))
+    built = []
+    real = ms._averaged_dir_frame
+    monkeypatch.setattr(ms, "_averaged_dir_frame", lambda *a, **k: built.append(1) or real(*a, **k))
+    argv = ["-q", os.path.join(INP, "SLBP_pfm_assembled_normalized_struct.txt"), "-B",
+            os.path.join(INP, "bg_struct_example.txt"), "-m", "2", str(work)]
+    native, err1, code = run_cli(argv)
+    assert code == 0 and native.count("\n") == 1 + 16
+    assert len(built) == (0 if order == "hit_first" else 1)
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 10 ** 12)
+    frames, err2, _ = run_cli(argv)
+    assert native == frames and err1 == err2
+    if order == "hit_first":
+        first = native.splitlines()[1].split("\t")
+        assert first[0] == "a_hit" and first[3] == "10.0" and first[4] == "27.0"     # float Start / End
+    else:
+        assert native.splitlines()[0].split("\t")[:2] == ["Sequence", "LogOdds"]      # the other column order
+    # combined mode over the same directory: the joint writer prints, the structure frame is never built
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 1)
+    monkeypatch.setattr(ms, "_profile_files", lambda directory: [str(work / "structure.a_hit.txt")])
+    shutil.copy(example, work / "structure.hg19_dna.txt")
+    monkeypatch.setattr(ms, "_profile_files", lambda directory: [str(work / "structure.hg19_dna.txt")])
+    del built[:]
+    cargv = ["-p", os.path.join(INP, "SLBP_pfm_assembled_normalized_seq.txt"), "-q",
+             os.path.join(INP, "SLBP_pfm_assembled_normalized_struct.txt"), "-u", "-m", " -inf",
+             os.path.join(INP, "HIST2H3C_3p_end.fa"), str(work)]
+    joint, _, code = run_cli(cargv)
+    assert code == 0 and joint.count("\n") > 3 and not built
+    monkeypatch.setattr(ms, "NATIVE_WRITER_MIN_ROWS", 10 ** 12)
+    assert run_cli(cargv)[0] == joint and built
+
+
 def test_fasta_run_does_not_import_pandas(in_repo):
     """A FASTA scan reads its PFM without pandas and prints through the native writer: pandas (1-3 s of import)
     is never loaded -- and the output is the golden one."""
